@@ -1,0 +1,122 @@
+"""TEST INFRASTRUCTURE ONLY -- never imported by the product package.
+
+Import shim for the *live* Python reference (``/root/reference``), which exists only in the
+development container (it is absent on the GPU box).  It is used by
+
+  * ``oracle/gen_golden.py``   -- to generate the committed fixtures under ``tests/golden/``;
+  * ``tests/test_oracle_vs_reference.py`` -- differential test of the C restatement
+    (``oracle/ah_oracle.c``) against the reference, skipped when the reference is absent.
+
+The reference cannot be imported as shipped in this image: it pulls in ``redis``
+(environment/airhockey.py:7, lib/utils/connect.py:8), ``keras`` (lib/utils/noisy_dense.py:4-7 via
+lib/utils/__init__.py:2), ``pytz`` (lib/rewards.py:7), ``tensorflow`` (lib/utils/helpers.py:6),
+``imp`` (lib/agents/*.py, removed in Python 3.12) and ``np.Infinity`` (lib/rewards.py:31, removed
+in NumPy 2).  None of those touch the arithmetic of the environment step, so they are stubbed.
+"""
+from __future__ import annotations
+
+import datetime
+import logging
+import os
+import sys
+import tempfile
+import types
+from unittest.mock import MagicMock
+
+import numpy as np
+
+REFERENCE_ROOT = os.environ.get("AH_REFERENCE_ROOT", "/root/reference")
+
+
+def reference_available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "environment", "airhockey.py"))
+
+
+_installed = False
+
+
+def install() -> None:
+    """Install the stubs and put the reference on ``sys.path`` (idempotent)."""
+    global _installed
+    if _installed:
+        return
+    if not reference_available():
+        raise RuntimeError(f"reference not found under {REFERENCE_ROOT}")
+
+    class _Redis:  # no-op client standing in for redis.Redis / redis.StrictRedis
+        def __init__(self, *a, **k):
+            pass
+
+        def get(self, key):
+            return "null"
+
+        def set(self, key, value):
+            return True
+
+        def publish(self, channel, payload):
+            return 0
+
+        def pubsub(self, **k):
+            return MagicMock()
+
+    redis = types.ModuleType("redis")
+    redis.Redis = _Redis
+    redis.StrictRedis = _Redis
+    redis.ConnectionError = type("ConnectionError", (Exception,), {})
+    sys.modules["redis"] = redis
+
+    for name in ("keras", "keras.backend", "keras.layers", "keras.models", "keras.optimizers",
+                 "keras.initializers", "keras.utils", "tensorflow", "imp"):
+        sys.modules.setdefault(name, MagicMock())
+    # `class NoisyDense(Layer)` must be definable
+    sys.modules["keras.layers"].Layer = type("Layer", (object,), {})
+
+    pytz = types.ModuleType("pytz")
+    pytz.timezone = lambda name: datetime.timezone.utc
+    sys.modules["pytz"] = pytz
+
+    if not hasattr(np, "Infinity"):
+        np.Infinity = np.inf
+
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    os.environ.setdefault("PROJECT", tempfile.mkdtemp(prefix="ah_ref_project_"))
+    logging.disable(logging.CRITICAL)
+    _installed = True
+
+
+def silence_side_channels() -> None:
+    """No-op the Redis posts and the per-`done` CSV row (pure-simulation variant)."""
+    install()
+    import lib.rewards as rewards
+    from lib.utils.connect import RedisConnection
+
+    RedisConnection.post = lambda self, payload: None
+    RedisConnection.publish = lambda self, channel, payload=True: None
+    rewards.record_data_csv = lambda *a, **k: None
+
+
+def numpy_dot_is_fma(trials: int = 20000, seed: int = 7) -> bool:
+    """Self-probe: is ``np.dot([a,b],[c,d]) == fma(b, d, fl(a*c))`` on this build?
+
+    Returns True when every discriminating case matches the FMA form, False when every one
+    matches the plain form ``fl(fl(a*c) + fl(b*d))``; raises if the build is neither.
+    """
+    from fractions import Fraction
+
+    rng = np.random.default_rng(seed)
+    n_fma = n_plain = 0
+    for _ in range(trials):
+        a, b, c, d = (float(v) for v in rng.uniform(-35, 35, 4))
+        plain = a * c + b * d
+        fma = float(Fraction(b) * Fraction(d) + Fraction(a * c))
+        if plain == fma:
+            continue
+        got = float(np.dot(np.array([a, b]), np.array([c, d])))
+        n_fma += got == fma
+        n_plain += got == plain
+    if n_fma and not n_plain:
+        return True
+    if n_plain and not n_fma:
+        return False
+    raise RuntimeError(f"np.dot is neither plain nor fma-tail: fma={n_fma} plain={n_plain}")
