@@ -1,0 +1,650 @@
+// B200-native batched air-hockey environment step: kernels + the C ABI of include/ah_b200.h.
+//
+// Mapping: ONE THREAD OWNS ONE ENVIRONMENT.  A thread loads its env's state from the SoA arrays with 128-bit
+// coalesced accesses, keeps the 13 reals + counters in registers across K fused frames (3 physics sub-updates
+// each), writes the per-frame outputs straight into caller-owned tensors, and stores the state back once.
+// Persistent grid: SMs x resident-blocks CTAs, grid-stride over the envs.  Per-block statistics are reduced
+// with warp shuffles / REDUX and leave the SM as one atomic set per block.  No tensor cores: there is no dense
+// contraction anywhere in this path.
+//
+// Compile with -fmad=false (see build.py): the FP64 instantiation must not contract a*b+c.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <new>
+#include <type_traits>
+
+#include "../../include/ah_b200.h"
+#include "ah_physics.cuh"
+#include "ah_rng.cuh"
+
+namespace ah {
+
+// ------------------------------------------------------------------------------------------------ device block
+struct DevBlock {
+    unsigned long long stats[AH_NSTATS];   // AH_STAT_*
+    unsigned long long frame;              // global frame counter (Philox action index)
+    unsigned long long ring_appended;      // Observation tuples appended to the ring so far
+    unsigned int ticket;                   // last-block-done detection
+    unsigned int pad[27];
+};
+static_assert(sizeof(DevBlock) == 256, "DevBlock is 256 bytes");
+
+template <typename R> struct Vec4T;
+template <> struct Vec4T<float> { using type = float4; };
+template <> struct Vec4T<double> { using type = double4; };
+
+template <typename R>
+struct StatePtrs {
+    typename Vec4T<R>::type* puck;
+    typename Vec4T<R>::type* robot;
+    typename Vec4T<R>::type* opp;
+    R* prev_dist;
+    int4* meta;
+};
+
+template <typename R>
+__device__ __forceinline__ Env<R> load_env(const StatePtrs<R>& s, int64_t i) {
+    Env<R> e;
+    const auto p = s.puck[i];
+    const auto r = s.robot[i];
+    const auto o = s.opp[i];
+    const int4 m = s.meta[i];
+    e.px = p.x; e.py = p.y; e.pdx = p.z; e.pdy = p.w;
+    e.rx = r.x; e.ry = r.y; e.rdx = r.z; e.rdy = r.w;
+    e.ox = o.x; e.oy = o.y; e.odx = o.z; e.ody = o.w;
+    e.prev_dist = s.prev_dist[i];
+    e.robot_score = m.x & 0xffff; e.opp_score = (m.x >> 16) & 0xffff;
+    e.resets = (uint32_t)m.y; e.game_frames = m.z; e.game_return = m.w;
+    return e;
+}
+
+template <typename R>
+__device__ __forceinline__ void store_env(const StatePtrs<R>& s, int64_t i, const Env<R>& e) {
+    typename Vec4T<R>::type p, r, o;
+    p.x = e.px; p.y = e.py; p.z = e.pdx; p.w = e.pdy;
+    r.x = e.rx; r.y = e.ry; r.z = e.rdx; r.w = e.rdy;
+    o.x = e.ox; o.y = e.oy; o.z = e.odx; o.w = e.ody;
+    s.puck[i] = p; s.robot[i] = r; s.opp[i] = o;
+    s.prev_dist[i] = e.prev_dist;
+    s.meta[i] = make_int4((e.robot_score & 0xffff) | (e.opp_score << 16), (int)e.resets, e.game_frames, e.game_return);
+}
+
+template <typename R>
+__device__ __forceinline__ void store_obs(R* base, int64_t row, const Obs<R>& o) {
+    using V = typename Vec4T<R>::type;
+    V a, b;
+    a.x = o.v[0]; a.y = o.v[1]; a.z = o.v[2]; a.w = o.v[3];
+    b.x = o.v[4]; b.y = o.v[5]; b.z = o.v[6]; b.w = o.v[7];
+    V* dst = reinterpret_cast<V*>(base) + 2 * row;
+    dst[0] = a; dst[1] = b;
+}
+
+// ------------------------------------------------------------------------------------------------ resets
+struct ResetSrc {
+    const double* table;   // [n][R][2] or nullptr => Philox
+    int R;
+    uint64_t seed, env_id0;
+};
+
+// AirHockey.reset  airhockey.py:171-187 ; Puck.reset puck.py:111-118 ; Mallet.reset mallet.py:78-84
+template <typename R>
+__device__ __forceinline__ void env_reset(Env<R>& e, bool total, const ResetSrc& rs, int64_t i, unsigned& overflow) {
+    if (total) { e.opp_score = 0; e.robot_score = 0; }
+    R dx, dy;
+    if (rs.table) {
+        if (e.resets < (uint32_t)rs.R) {
+            const double2 v = reinterpret_cast<const double2*>(rs.table)[(size_t)i * rs.R + e.resets];
+            dx = (R)v.x; dy = (R)v.y;
+        } else { dx = R(0); dy = R(0); overflow += 1; }
+    } else {
+        reset_velocity(rs.seed, rs.env_id0 + (uint64_t)i, e.resets, dx, dy);
+    }
+    e.resets += 1;
+    e.px = K<R>::mid_x; e.py = K<R>::mid_y; e.pdx = dx; e.pdy = dy;   // puck to the centre, fresh velocity
+    e.rdx = R(0); e.rdy = R(0); e.odx = R(0); e.ody = R(0);           // mallets: velocity only, positions kept
+}
+
+// ------------------------------------------------------------------------------------------------ step kernel
+template <typename R>
+struct StepArgs {
+    StatePtrs<R> st;
+    int64_t n;
+    int K;
+    const void* actions;
+    int action_kind;
+    ResetSrc rs;
+    R* obs_state; R* obs_new_state; R* reward; uint8_t* done; int8_t* score; uint8_t* game_over;
+    R* obs_next; int obs_next_per_frame;
+    int collect_stats;
+    // ring
+    R* ring_state; R* ring_new_state; void* ring_action; R* ring_reward; uint8_t* ring_done; int64_t ring_capacity;
+    int dot_fma, friction;
+    DevBlock* blk;
+};
+
+struct Tally {   // per-thread event counters of one launch
+    int frames, robot_goals, opp_goals, robot_wins, opp_wins, dones, reward_sum, reward_sq, games, nonfinite;
+    long long len_sum, len_sq, ret_sum;
+};
+
+__device__ __forceinline__ long long warp_sum(long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+constexpr int kThreads = 256;
+
+template <typename R, int ACT>   // ACT: 1 discrete, 2 continuous, 3 philox
+__global__ void __launch_bounds__(kThreads) step_kernel(const StepArgs<R> a) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const unsigned long long frame0 = a.blk->frame;
+    const unsigned long long ring0 = a.blk->ring_appended;
+    const bool repeat = (a.action_kind == AH_ACT_DISCRETE_REPEAT) || (a.action_kind == AH_ACT_CONTINUOUS_REPEAT);
+    const bool dot_fma = a.dot_fma != 0, friction = a.friction != 0;
+    Tally t = {};
+    unsigned overflow = 0;
+
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
+        Env<R> e = load_env<R>(a.st, i);
+        Philox4 ablock = {};
+        uint32_t ablock_id = 0xffffffffu;
+        for (int k = 0; k < a.K; ++k) {
+            const int64_t row = (int64_t)k * a.n + i;
+            // ---- the robot's action for this frame
+            int ia = -1; R ax = R(0), ay = R(0);
+            if (ACT == 1) {
+                ia = reinterpret_cast<const int8_t*>(a.actions)[repeat ? i : row];
+            } else if (ACT == 2) {
+                using V2 = typename std::conditional<sizeof(R) == 4, float2, double2>::type;
+                const V2 v = reinterpret_cast<const V2*>(a.actions)[repeat ? i : row];
+                ax = v.x; ay = v.y;
+            } else {
+                const unsigned long long f = frame0 + (unsigned long long)k;
+                const uint32_t bid = (uint32_t)(f >> 6);
+                if (bid != ablock_id) { ablock = action_block(a.rs.seed, a.rs.env_id0 + (uint64_t)i, bid); ablock_id = bid; }
+                ia = action_from_block(ablock, (uint32_t)(f & 63u));
+            }
+            // ---- robot.move(a): sub-update #1                      game.py:136 -> agent.py:32-36
+            move_robot<R>(e, ACT == 2, ia, ax, ay);
+            physics_tail<R>(e, dot_fma, friction);
+            const Obs<R> s0 = get_state<R>(e, true);                // Observation.state      agent.py:61
+            // ---- robot.step(a) -> self.move(a): sub-update #2      agent.py:64
+            move_robot<R>(e, ACT == 2, ia, ax, ay);
+            physics_tail<R>(e, dot_fma, friction);
+            const Obs<R> s1 = get_state<R>(e, true);                // Observation.new_state  agent.py:67
+            // ---- Rewards                                           agent.py:70-71
+            int rw, sc; bool dn;
+            rewards_call<R>(e, dot_fma, rw, sc, dn);
+            e.game_frames += 1; e.game_return += rw;
+            // ---- env.update_score(score)                           game.py:142 -> airhockey.py:149-169
+            if (sc != 0) {
+                if (sc > 0) { e.robot_score += 1; t.robot_goals += 1; } else { e.opp_score += 1; t.opp_goals += 1; }
+                env_reset<R>(e, false, a.rs, i, overflow);
+            }
+            // ---- stats(): win flags are read BEFORE the opponent moves and before the total reset (game.py:101-109)
+            int go = 0;
+            if (e.robot_score == 10) go = 1;
+            if (e.opp_score == 10) go = 2;
+            // ---- env.update_state(agent_name="computer"): sub-update #3   game.py:166
+            computer_ai<R>(e);
+            physics_tail<R>(e, dot_fma, friction);
+            // ---- 10-goal game over                                 game.py:169-177
+            if (go != 0) {
+                t.games += 1; t.robot_wins += (go == 1); t.opp_wins += (go == 2);
+                t.len_sum += e.game_frames; t.len_sq += (long long)e.game_frames * e.game_frames;
+                t.ret_sum += e.game_return;
+                e.game_frames = 0; e.game_return = 0;
+                env_reset<R>(e, true, a.rs, i, overflow);
+            }
+            t.frames += 1; t.dones += dn ? 1 : 0; t.reward_sum += rw; t.reward_sq += rw * rw;
+            // ---- outputs, straight into the caller's tensors
+            if (a.obs_state) store_obs<R>(a.obs_state, row, s0);
+            if (a.obs_new_state) store_obs<R>(a.obs_new_state, row, s1);
+            if (a.reward) a.reward[row] = (R)rw;
+            if (a.done) a.done[row] = dn ? 1 : 0;
+            if (a.score) a.score[row] = (int8_t)sc;
+            if (a.game_over) a.game_over[row] = (uint8_t)go;
+            if (a.obs_next && (a.obs_next_per_frame || k == a.K - 1))
+                store_obs<R>(a.obs_next, a.obs_next_per_frame ? row : i, get_state<R>(e, true));
+            if (a.ring_capacity > 0) {      // fused MemoryBuffer.append(Observation(...))   lib/buffer.py:24-32
+                const int64_t slot = (int64_t)((ring0 + (unsigned long long)k) % (unsigned long long)a.ring_capacity);
+                const int64_t rrow = slot * a.n + i;
+                store_obs<R>(a.ring_state, rrow, s0);
+                store_obs<R>(a.ring_new_state, rrow, s1);
+                if (ACT == 2) { reinterpret_cast<R*>(a.ring_action)[2 * rrow] = ax; reinterpret_cast<R*>(a.ring_action)[2 * rrow + 1] = ay; }
+                else reinterpret_cast<int8_t*>(a.ring_action)[rrow] = (int8_t)ia;
+                a.ring_reward[rrow] = (R)rw;
+                a.ring_done[rrow] = dn ? 1 : 0;
+            }
+        }
+        if (!(isfinite((double)e.px) && isfinite((double)e.py) && isfinite((double)e.pdx) && isfinite((double)e.pdy))) t.nonfinite += 1;
+        store_env<R>(a.st, i, e);
+    }
+
+    // ---- statistics: warp shuffle reduction, then one atomic set per block
+    __shared__ long long red[kThreads / 32][14];
+    if (a.collect_stats) {
+        long long v[14] = {t.frames, t.robot_goals, t.opp_goals, t.robot_wins, t.opp_wins, t.dones, t.reward_sum,
+                           t.reward_sq, t.games, t.len_sum, t.len_sq, t.ret_sum, t.nonfinite, (long long)overflow};
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int q = 0; q < 14; ++q) {
+            // events are rare: skip the shuffle tree when no lane of the warp has anything to add
+            const bool any = __any_sync(0xffffffffu, v[q] != 0);
+            const long long s = any ? warp_sum(v[q]) : 0;
+            if (lane == 0) red[warp][q] = s;
+        }
+        __syncthreads();
+        if (threadIdx.x < 14) {
+            long long s = 0;
+#pragma unroll
+            for (int w = 0; w < kThreads / 32; ++w) s += red[w][threadIdx.x];
+            if (s != 0) atomicAdd(&a.blk->stats[threadIdx.x], (unsigned long long)s);
+        }
+    }
+    // ---- the last block to finish advances the device-side counters (graph-capturable: no host value baked in)
+    __shared__ bool is_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned tk = atomicAdd(&a.blk->ticket, 1u);
+        is_last = (tk == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last && threadIdx.x == 0) {
+        a.blk->frame = frame0 + (unsigned long long)a.K;
+        if (a.ring_capacity > 0) a.blk->ring_appended = ring0 + (unsigned long long)a.K;
+        a.blk->ticket = 0;
+        __threadfence();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ small kernels
+template <typename R>
+__global__ void init_state_kernel(StatePtrs<R> st, int64_t n) {     // airhockey.py:25-63, puck.py:16, rewards.py:31
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Env<R> e;
+    e.px = K<R>::mid_x; e.py = K<R>::mid_y; e.pdx = R(-3); e.pdy = R(0);
+    e.rx = K<R>::mid_x - R(100); e.ry = K<R>::mid_y; e.rdx = R(0); e.rdy = R(0);
+    e.ox = K<R>::mid_x + R(100); e.oy = K<R>::mid_y; e.odx = R(0); e.ody = R(0);
+    e.prev_dist = (R)INFINITY;
+    e.robot_score = 0; e.opp_score = 0; e.resets = 0; e.game_frames = 0; e.game_return = 0;
+    store_env<R>(st, i, e);
+}
+
+template <typename R>
+__global__ void reset_kernel(StatePtrs<R> st, int64_t n, int total, const uint8_t* mask, ResetSrc rs, DevBlock* blk) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (mask && !mask[i]) return;
+    Env<R> e = load_env<R>(st, i);
+    unsigned overflow = 0;
+    env_reset<R>(e, total != 0, rs, i, overflow);
+    if (total) { e.game_frames = 0; e.game_return = 0; }
+    store_env<R>(st, i, e);
+    if (overflow) atomicAdd(&blk->stats[13], 1ull);
+}
+
+// AirHockey.update_state  airhockey.py:96-134 : one sub-update
+template <typename R>
+__global__ void update_state_kernel(StatePtrs<R> st, int64_t n, const void* actions, int action_kind, int agent,
+                                    int dot_fma, int friction) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    using V2 = typename std::conditional<sizeof(R) == 4, float2, double2>::type;
+    Env<R> e = load_env<R>(st, i);
+    if (agent == AH_AGENT_ROBOT) {                                   // :100-101
+        if (action_kind == AH_ACT_CONTINUOUS) {
+            const V2 v = reinterpret_cast<const V2*>(actions)[i];
+            move_robot<R>(e, true, -1, v.x, v.y);
+        } else {
+            const int ia = actions ? (int)reinterpret_cast<const int8_t*>(actions)[i] : -1;
+            move_robot<R>(e, false, ia, R(0), R(0));
+        }
+    } else if (agent == AH_AGENT_HUMAN) {                            // :102-105 teleport, then update()
+        const V2 v = reinterpret_cast<const V2*>(actions)[i];
+        e.ox = v.x; e.oy = v.y;
+        mallet_update<R>(e.ox, e.oy, e.odx, e.ody, K<R>::opp_lo, K<R>::opp_hi);
+    } else {                                                         // :106-107
+        computer_ai<R>(e);
+    }
+    physics_tail<R>(e, dot_fma != 0, friction != 0);
+    store_env<R>(st, i, e);
+}
+
+template <typename R>
+__global__ void get_state_kernel(StatePtrs<R> st, int64_t n, int robot, R* obs) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Env<R> e = load_env<R>(st, i);
+    store_obs<R>(obs, i, get_state<R>(e, robot != 0));
+}
+
+// AirHockey.update_score  airhockey.py:149-169
+template <typename R>
+__global__ void update_score_kernel(StatePtrs<R> st, int64_t n, const int8_t* score, ResetSrc rs, DevBlock* blk) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int sc = score[i];
+    if (sc == 0) return;
+    Env<R> e = load_env<R>(st, i);
+    unsigned overflow = 0;
+    if (sc > 0) e.robot_score += 1; else e.opp_score += 1;
+    env_reset<R>(e, false, rs, i, overflow);
+    store_env<R>(st, i, e);
+    if (overflow) atomicAdd(&blk->stats[13], 1ull);
+}
+
+// Rewards.__call__  lib/rewards.py:118-142
+template <typename R>
+__global__ void rewards_kernel(StatePtrs<R> st, int64_t n, int dot_fma, R* reward, int8_t* score, uint8_t* done) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Env<R> e = load_env<R>(st, i);
+    int rw, sc; bool dn;
+    rewards_call<R>(e, dot_fma != 0, rw, sc, dn);
+    st.prev_dist[i] = e.prev_dist;
+    if (reward) reward[i] = (R)rw;
+    if (score) score[i] = (int8_t)sc;
+    if (done) done[i] = dn ? 1 : 0;
+}
+
+__global__ void stats_copy_kernel(DevBlock* blk, int64_t* out, int clear) {
+    const int q = threadIdx.x;
+    if (q < AH_NSTATS) {
+        out[q] = (int64_t)blk->stats[q];
+        if (clear) blk->stats[q] = 0ull;
+    }
+}
+
+__global__ void counters_set_kernel(DevBlock* blk, unsigned long long frame, unsigned long long ring) {
+    blk->frame = frame; blk->ring_appended = ring;
+}
+__global__ void counters_get_kernel(const DevBlock* blk, unsigned long long* out2) {
+    out2[0] = blk->frame; out2[1] = blk->ring_appended;
+}
+
+// a*b+c must NOT be contracted in this translation unit (FP64 validation build): discriminating probe
+__global__ void nofma_probe_kernel(double a, double b, double c, double* out) { out[0] = a * b + c; }
+
+}  // namespace ah
+
+// ================================================================================================ C ABI
+struct ah_env {
+    int64_t n;
+    int dtype, device;
+    uint64_t seed, env_id0;
+    ah_config cfg;
+    void *puck, *robot, *opp, *prev_dist;
+    int32_t* meta;
+    ah::DevBlock* blk;
+    int sms, blocks_f32, blocks_f64;
+    int last_cuda;
+};
+
+namespace {
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+struct DeviceGuard {
+    int prev = -1; bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+inline int cuda_fail(ah_env* env, cudaError_t e) { if (env) env->last_cuda = (int)e; return AH_ECUDA; }
+
+template <typename R> ah::StatePtrs<R> state_ptrs(const ah_env* env) {
+    ah::StatePtrs<R> s;
+    using V = typename ah::Vec4T<R>::type;
+    s.puck = reinterpret_cast<V*>(env->puck); s.robot = reinterpret_cast<V*>(env->robot);
+    s.opp = reinterpret_cast<V*>(env->opp); s.prev_dist = reinterpret_cast<R*>(env->prev_dist);
+    s.meta = reinterpret_cast<int4*>(env->meta);
+    return s;
+}
+
+inline ah::ResetSrc reset_src(const ah_env* env, const double* table, int R) {
+    ah::ResetSrc rs; rs.table = table; rs.R = R; rs.seed = env->seed; rs.env_id0 = env->env_id0; return rs;
+}
+
+inline unsigned small_grid(int64_t n) { return (unsigned)((n + 255) / 256); }
+
+template <typename R>
+int launch_step(ah_env* env, const ah_step_io* io, int K, cudaStream_t s) {
+    ah::StepArgs<R> a;
+    memset(&a, 0, sizeof a);
+    a.st = state_ptrs<R>(env); a.n = env->n; a.K = K;
+    a.actions = io->actions; a.action_kind = io->action_kind;
+    a.rs = reset_src(env, io->reset_table, io->reset_table_len);
+    a.obs_state = (R*)io->obs_state; a.obs_new_state = (R*)io->obs_new_state; a.reward = (R*)io->reward;
+    a.done = io->done; a.score = io->score; a.game_over = io->game_over;
+    a.obs_next = (R*)io->obs_next; a.obs_next_per_frame = io->obs_next_per_frame;
+    a.collect_stats = io->collect_stats;
+    if (io->ring) {
+        a.ring_state = (R*)io->ring->state; a.ring_new_state = (R*)io->ring->new_state; a.ring_action = io->ring->action;
+        a.ring_reward = (R*)io->ring->reward; a.ring_done = io->ring->done; a.ring_capacity = io->ring->capacity;
+    }
+    a.dot_fma = env->cfg.dot_fma; a.friction = env->cfg.friction; a.blk = env->blk;
+    const int max_blocks = sizeof(R) == 4 ? env->blocks_f32 : env->blocks_f64;
+    int64_t want = (env->n + ah::kThreads - 1) / ah::kThreads;
+    const unsigned grid = (unsigned)(want < max_blocks ? want : max_blocks);
+    switch (io->action_kind) {
+        case AH_ACT_DISCRETE: case AH_ACT_DISCRETE_REPEAT:
+            ah::step_kernel<R, 1><<<grid, ah::kThreads, 0, s>>>(a); break;
+        case AH_ACT_CONTINUOUS: case AH_ACT_CONTINUOUS_REPEAT:
+            ah::step_kernel<R, 2><<<grid, ah::kThreads, 0, s>>>(a); break;
+        case AH_ACT_PHILOX:
+            ah::step_kernel<R, 3><<<grid, ah::kThreads, 0, s>>>(a); break;
+        default: return AH_EINVAL;
+    }
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? AH_OK : cuda_fail(env, e);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ah_strerror(int code) {
+    switch (code) {
+        case AH_OK: return "ok";
+        case AH_EINVAL: return "invalid argument";
+        case AH_ECUDA: return "CUDA runtime error";
+        case AH_ENOMEM: return "out of memory";
+        case AH_EAGENT: return "invalid agent";
+        case AH_ESTATE: return "state not bound";
+        default: return "unknown error";
+    }
+}
+
+int ah_abi_version(void) { return AH_ABI_VERSION; }
+
+int ah_last_cuda_error(const ah_env* env) { return env ? env->last_cuda : 0; }
+
+int ah_create(ah_env** out, int64_t n, int dtype, int device, uint64_t seed, uint64_t env_id0, const ah_config* cfg) {
+    if (!out || n <= 0 || (dtype != AH_F32 && dtype != AH_F64) || device < 0) return AH_EINVAL;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device >= count) return AH_ECUDA;   // no CPU fallback
+    ah_env* env = new (std::nothrow) ah_env();
+    if (!env) return AH_ENOMEM;
+    memset(env, 0, sizeof *env);
+    env->n = n; env->dtype = dtype; env->device = device; env->seed = seed; env->env_id0 = env_id0;
+    env->cfg.dot_fma = 1; env->cfg.friction = 0;
+    if (cfg) env->cfg = *cfg;
+    DeviceGuard g(device);
+    cudaError_t e = g.ok ? cudaSuccess : cudaErrorInvalidDevice;
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&env->sms, cudaDevAttrMultiProcessorCount, device);
+    int occ32 = 0, occ64 = 0;
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ32, ah::step_kernel<float, 1>, ah::kThreads, 0);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ64, ah::step_kernel<double, 1>, ah::kThreads, 0);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&env->blk), sizeof(ah::DevBlock));
+    if (e == cudaSuccess) e = cudaMemset(env->blk, 0, sizeof(ah::DevBlock));
+    if (e != cudaSuccess) { if (env->blk) cudaFree(env->blk); delete env; return AH_ECUDA; }
+    env->blocks_f32 = env->sms * (occ32 > 0 ? occ32 : 1);
+    env->blocks_f64 = env->sms * (occ64 > 0 ? occ64 : 1);
+    *out = env;
+    return AH_OK;
+}
+
+int ah_destroy(ah_env* env) {
+    if (!env) return AH_EINVAL;
+    DeviceGuard g(env->device);
+    if (env->blk) cudaFree(env->blk);
+    delete env;
+    return AH_OK;
+}
+
+int ah_bind_state(ah_env* env, void* d_puck, void* d_robot, void* d_opponent, void* d_prev_dist, int32_t* d_meta) {
+    if (!env || !d_puck || !d_robot || !d_opponent || !d_prev_dist || !d_meta) return AH_EINVAL;
+    if (!aligned16(d_puck) || !aligned16(d_robot) || !aligned16(d_opponent) || !aligned16(d_meta) ||
+        (reinterpret_cast<uintptr_t>(d_prev_dist) & 7u)) return AH_EINVAL;
+    env->puck = d_puck; env->robot = d_robot; env->opp = d_opponent; env->prev_dist = d_prev_dist; env->meta = d_meta;
+    return AH_OK;
+}
+
+#define AH_CHECK_BOUND(env) do { if (!(env)) return AH_EINVAL; if (!(env)->puck) return AH_ESTATE; } while (0)
+#define AH_DISPATCH(env, call_f32, call_f64) do { if ((env)->dtype == AH_F32) { call_f32; } else { call_f64; } } while (0)
+#define AH_LAUNCH_RC(env) do { const cudaError_t e_ = cudaGetLastError(); return e_ == cudaSuccess ? AH_OK : cuda_fail((env), e_); } while (0)
+
+int ah_init_state(ah_env* env, void* stream) {
+    AH_CHECK_BOUND(env);
+    DeviceGuard g(env->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    AH_DISPATCH(env, (ah::init_state_kernel<float><<<small_grid(env->n), 256, 0, s>>>(state_ptrs<float>(env), env->n)),
+                (ah::init_state_kernel<double><<<small_grid(env->n), 256, 0, s>>>(state_ptrs<double>(env), env->n)));
+    AH_LAUNCH_RC(env);
+}
+
+int ah_reset(ah_env* env, int total, const uint8_t* d_mask, const double* d_reset_table, int reset_table_len, void* stream) {
+    AH_CHECK_BOUND(env);
+    if (d_reset_table && (reset_table_len <= 0 || !aligned16(d_reset_table))) return AH_EINVAL;
+    DeviceGuard g(env->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const ah::ResetSrc rs = reset_src(env, d_reset_table, reset_table_len);
+    AH_DISPATCH(env, (ah::reset_kernel<float><<<small_grid(env->n), 256, 0, s>>>(state_ptrs<float>(env), env->n, total, d_mask, rs, env->blk)),
+                (ah::reset_kernel<double><<<small_grid(env->n), 256, 0, s>>>(state_ptrs<double>(env), env->n, total, d_mask, rs, env->blk)));
+    AH_LAUNCH_RC(env);
+}
+
+int ah_update_state(ah_env* env, const void* d_actions, int action_kind, int agent, void* stream) {
+    AH_CHECK_BOUND(env);
+    if (agent != AH_AGENT_ROBOT && agent != AH_AGENT_HUMAN && agent != AH_AGENT_COMPUTER) return AH_EAGENT;
+    if (agent == AH_AGENT_HUMAN && (!d_actions || action_kind != AH_ACT_CONTINUOUS)) return AH_EINVAL;
+    if (agent == AH_AGENT_ROBOT) {
+        if (action_kind == AH_ACT_CONTINUOUS) { if (!d_actions || (reinterpret_cast<uintptr_t>(d_actions) & (env->dtype == AH_F32 ? 7u : 15u))) return AH_EINVAL; }
+        else if (action_kind == AH_ACT_DISCRETE) { if (!d_actions) return AH_EINVAL; }
+        else if (action_kind != AH_ACT_NONE) return AH_EINVAL;   // AH_ACT_NONE: `update_state("", "robot")`, no nudge
+    }
+    DeviceGuard g(env->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    AH_DISPATCH(env, (ah::update_state_kernel<float><<<small_grid(env->n), 256, 0, s>>>(state_ptrs<float>(env), env->n, d_actions, action_kind, agent, env->cfg.dot_fma, env->cfg.friction)),
+                (ah::update_state_kernel<double><<<small_grid(env->n), 256, 0, s>>>(state_ptrs<double>(env), env->n, d_actions, action_kind, agent, env->cfg.dot_fma, env->cfg.friction)));
+    AH_LAUNCH_RC(env);
+}
+
+int ah_get_state(ah_env* env, int agent, void* d_obs, void* stream) {
+    AH_CHECK_BOUND(env);
+    if (!d_obs || !aligned16(d_obs)) return AH_EINVAL;
+    // get_state: any name other than "robot" selects the opponent's mallet (airhockey.py:139)
+    const int robot = agent == AH_AGENT_ROBOT;
+    DeviceGuard g(env->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    AH_DISPATCH(env, (ah::get_state_kernel<float><<<small_grid(env->n), 256, 0, s>>>(state_ptrs<float>(env), env->n, robot, (float*)d_obs)),
+                (ah::get_state_kernel<double><<<small_grid(env->n), 256, 0, s>>>(state_ptrs<double>(env), env->n, robot, (double*)d_obs)));
+    AH_LAUNCH_RC(env);
+}
+
+int ah_update_score(ah_env* env, const int8_t* d_score, const double* d_reset_table, int reset_table_len, void* stream) {
+    AH_CHECK_BOUND(env);
+    if (!d_score) return AH_EINVAL;
+    if (d_reset_table && (reset_table_len <= 0 || !aligned16(d_reset_table))) return AH_EINVAL;
+    DeviceGuard g(env->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const ah::ResetSrc rs = reset_src(env, d_reset_table, reset_table_len);
+    AH_DISPATCH(env, (ah::update_score_kernel<float><<<small_grid(env->n), 256, 0, s>>>(state_ptrs<float>(env), env->n, d_score, rs, env->blk)),
+                (ah::update_score_kernel<double><<<small_grid(env->n), 256, 0, s>>>(state_ptrs<double>(env), env->n, d_score, rs, env->blk)));
+    AH_LAUNCH_RC(env);
+}
+
+int ah_rewards(ah_env* env, void* d_reward, int8_t* d_score, uint8_t* d_done, void* stream) {
+    AH_CHECK_BOUND(env);
+    DeviceGuard g(env->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    AH_DISPATCH(env, (ah::rewards_kernel<float><<<small_grid(env->n), 256, 0, s>>>(state_ptrs<float>(env), env->n, env->cfg.dot_fma, (float*)d_reward, d_score, d_done)),
+                (ah::rewards_kernel<double><<<small_grid(env->n), 256, 0, s>>>(state_ptrs<double>(env), env->n, env->cfg.dot_fma, (double*)d_reward, d_score, d_done)));
+    AH_LAUNCH_RC(env);
+}
+
+int ah_step(ah_env* env, const ah_step_io* io, int K, void* stream) {
+    AH_CHECK_BOUND(env);
+    if (!io || K < 1 || K > 4096) return AH_EINVAL;
+    const int kind = io->action_kind;
+    if (kind != AH_ACT_DISCRETE && kind != AH_ACT_CONTINUOUS && kind != AH_ACT_PHILOX &&
+        kind != AH_ACT_DISCRETE_REPEAT && kind != AH_ACT_CONTINUOUS_REPEAT) return AH_EINVAL;
+    if (kind != AH_ACT_PHILOX && !io->actions) return AH_EINVAL;
+    if ((kind == AH_ACT_CONTINUOUS || kind == AH_ACT_CONTINUOUS_REPEAT) &&
+        (reinterpret_cast<uintptr_t>(io->actions) & (env->dtype == AH_F32 ? 7u : 15u))) return AH_EINVAL;
+    if (io->reset_table && (io->reset_table_len <= 0 || !aligned16(io->reset_table))) return AH_EINVAL;
+    if (!aligned16(io->obs_state) || !aligned16(io->obs_new_state) || !aligned16(io->obs_next)) return AH_EINVAL;
+    if (io->ring) {
+        const ah_ring* r = io->ring;
+        if (r->capacity <= 0 || !r->state || !r->new_state || !r->action || !r->reward || !r->done) return AH_EINVAL;
+        if (!aligned16(r->state) || !aligned16(r->new_state)) return AH_EINVAL;
+    }
+    DeviceGuard g(env->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (env->dtype == AH_F32) return launch_step<float>(env, io, K, s);
+    return launch_step<double>(env, io, K, s);
+}
+
+int ah_stats(ah_env* env, int64_t* d_out, int clear, void* stream) {
+    if (!env || !d_out) return AH_EINVAL;
+    DeviceGuard g(env->device);
+    ah::stats_copy_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(env->blk, d_out, clear);
+    AH_LAUNCH_RC(env);
+}
+
+int ah_set_counters(ah_env* env, uint64_t frame, uint64_t ring_appended, void* stream) {
+    if (!env) return AH_EINVAL;
+    DeviceGuard g(env->device);
+    ah::counters_set_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(env->blk, frame, ring_appended);
+    AH_LAUNCH_RC(env);
+}
+
+int ah_get_counters(ah_env* env, uint64_t* d_out2, void* stream) {
+    if (!env || !d_out2) return AH_EINVAL;
+    DeviceGuard g(env->device);
+    ah::counters_get_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(env->blk, reinterpret_cast<unsigned long long*>(d_out2));
+    AH_LAUNCH_RC(env);
+}
+
+int ah_launch_info(const ah_env* env, int* blocks, int* threads, int* sms) {
+    if (!env) return AH_EINVAL;
+    int64_t want = (env->n + ah::kThreads - 1) / ah::kThreads;
+    const int max_blocks = env->dtype == AH_F32 ? env->blocks_f32 : env->blocks_f64;
+    if (blocks) *blocks = (int)(want < max_blocks ? want : max_blocks);
+    if (threads) *threads = ah::kThreads;
+    if (sms) *sms = env->sms;
+    return AH_OK;
+}
+
+/* Self-test: AH_OK when this library was compiled without multiply-add contraction (required by the FP64
+ * validation build).  d_scratch: device double[1]. */
+int ah_selftest_nofma(ah_env* env, double* d_scratch, void* stream) {
+    if (!env || !d_scratch) return AH_EINVAL;
+    DeviceGuard g(env->device);
+    // a*b + c with a = 1 + 2^-30, b = 1 - 2^-30, c = -1: exact product 1 - 2^-60 rounds to 1.0, so the
+    // unfused result is 0.0 while a fused multiply-add returns -2^-60.
+    ah::nofma_probe_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(1.0 + 9.313225746154785e-10, 1.0 - 9.313225746154785e-10, -1.0, d_scratch);
+    AH_LAUNCH_RC(env);
+}
+
+}  // extern "C"

@@ -1,0 +1,262 @@
+// Device-side rules of one air-hockey game, one environment per thread, state in registers.
+//
+// Two arithmetic policies share this source:
+//   Math<double>  VALIDATION build: every operation is the reference's IEEE binary64 operation in the
+//                 reference's order.  The translation unit is compiled with -fmad=false, so the only fused
+//                 multiply-adds are the explicit ones that reproduce numpy/OpenBLAS' 2-vector dot
+//                 (np.dot([a,b],[c,d]) == fma(b, d, fl(a*c))), switchable at run time.
+//   Math<float>   THROUGHPUT build: same rules and branch structure in binary32; min/max for clamps,
+//                 MUFU rsqrt/sqrt on the (rare) contact path and for the reward distance.
+//
+// Each function cites the reference file:line it implements (paths relative to the reference root).
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+namespace ah {
+
+// ---- constants: environment/config.py:4-13, table.py:8-15, mallet.py:33-44, airhockey.py:35-49,63 ----
+template <typename R> struct K {
+    static constexpr R table_w = R(900), table_h = R(480);
+    static constexpr R puck_r = R(15), mallet_r = R(20);
+    static constexpr R radius = R(35);            // mallet.radius + puck.radius   airhockey.py:206
+    static constexpr R radius_sq = R(1225);       //                               airhockey.py:207
+    static constexpr R puck_imass = R(10);        // 1.0 / 0.1 == 10.0 in binary64 puck.py:36
+    static constexpr R mallet_imass = R(2);       // 1.0 / 0.5                     mallet.py:27
+    static constexpr R imass_sum = R(12);         //                               airhockey.py:223
+    static constexpr R speed = R(10);             // config.puck["default_speed"]
+    static constexpr R step = R(10);              // airhockey.py:63
+    static constexpr R left_wall = R(13), right_wall = R(882);           // table.py:14-15
+    static constexpr R mid_x = R(450), mid_y = R(240);                   // table.py:11
+    static constexpr R robot_lo = R(20), robot_hi = R(430);              // mallet.py:36-38
+    static constexpr R opp_lo = R(470), opp_hi = R(880);                 // mallet.py:39-41
+    static constexpr R y_lo = R(20), y_hi = R(460);                      // mallet.py:33-34
+    static constexpr R puck_x_lo = R(15), puck_x_hi = R(885);            // puck.py:49-54
+    static constexpr R puck_y_lo = R(15), puck_y_hi = R(465);            // puck.py:56-61
+};
+
+template <typename R> struct Math;
+
+template <> struct Math<double> {
+    static constexpr bool exact = true;
+    // np.dot on two 2-vectors (airhockey.py:203,246; rewards.py:94 through np.linalg.norm)
+    static __device__ __forceinline__ double dot2(double a0, double a1, double b0, double b1, bool dot_fma) {
+        const double p = __dmul_rn(a0, b0);
+        return dot_fma ? __fma_rn(a1, b1, p) : __dadd_rn(p, __dmul_rn(a1, b1));
+    }
+    static __device__ __forceinline__ double sqrt_(double v) { return __dsqrt_rn(v); }
+    static __device__ __forceinline__ double trunc_(double v) { return trunc(v); }
+    // `if x < lo: x = lo elif x > hi: x = hi`   (mallet.py:65-74)
+    static __device__ __forceinline__ double clamp(double x, double lo, double hi) {
+        return (x < lo) ? lo : ((x > hi) ? hi : x);
+    }
+    static __device__ __forceinline__ double abs_(double v) { return fabs(v); }
+};
+
+template <> struct Math<float> {
+    static constexpr bool exact = false;
+    static __device__ __forceinline__ float dot2(float a0, float a1, float b0, float b1, bool) {
+        return fmaf(a1, b1, a0 * b0);
+    }
+    static __device__ __forceinline__ float sqrt_(float v) {
+        float r;
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+        return r;
+    }
+    static __device__ __forceinline__ float trunc_(float v) { return truncf(v); }
+    static __device__ __forceinline__ float clamp(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+    static __device__ __forceinline__ float abs_(float v) { return fabsf(v); }
+};
+
+// All state of one game, in registers.
+template <typename R> struct Env {
+    R px, py, pdx, pdy;      // puck       environment/puck.py:16-43
+    R rx, ry, rdx, rdy;      // robot      environment/mallet.py:11-48 (name "robot": left half)
+    R ox, oy, odx, ody;      // opponent   (name "opponent": right half)
+    R prev_dist;             // Rewards.prev_mallet_to_puck_distance   lib/rewards.py:31
+    int robot_score, opp_score;                                     // airhockey.py:52
+    uint32_t resets;         // reset draws consumed
+    int game_frames, game_return;
+};
+
+// ---- Mallet.update  environment/mallet.py:54-76 ----
+template <typename R>
+__device__ __forceinline__ void mallet_update(R& x, R& y, R dx, R dy, R lo, R hi) {
+    x = Math<R>::clamp(x + dx, lo, hi);
+    y = Math<R>::clamp(y + dy, K<R>::y_lo, K<R>::y_hi);
+}
+
+// ---- AirHockey._move  environment/airhockey.py:65-94 ----
+// The nudge never enters the velocity: after the first update() the velocity is recomputed as the
+// displacement actually made (== the old velocity unless a limit shortened it).
+template <typename R>
+__device__ __forceinline__ void move_robot(Env<R>& e, bool continuous, int ia, R ax, R ay) {
+    if (continuous) {                              // :69-71
+        e.rdx += ax;
+        e.rdy += ay;
+    } else {                                       // :74-84 ; other ints: no nudge
+        const R ny = (ia == 0) ? K<R>::step : (ia == 1) ? -K<R>::step : R(0);
+        const R nx = (ia == 3) ? K<R>::step : (ia == 2) ? -K<R>::step : R(0);
+        e.ry += ny;
+        e.rx += nx;
+    }
+    const R lx = e.rx, ly = e.ry;                  // mallet.py:57-58 (last_x, last_y)
+    mallet_update<R>(e.rx, e.ry, e.rdx, e.rdy, K<R>::robot_lo, K<R>::robot_hi);   // :87
+    e.rdx = e.rx - lx;                             // :90
+    e.rdy = e.ry - ly;                             // :91
+    mallet_update<R>(e.rx, e.ry, e.rdx, e.rdy, K<R>::robot_lo, K<R>::robot_hi);   // :92
+}
+
+// ---- AirHockey.collision  environment/airhockey.py:189-268 (correction=True) ----
+template <typename R>
+__device__ __forceinline__ bool collision(R& px, R& py, R& pdx, R& pdy, R& mx, R& my, R& mdx, R& mdy, bool dot_fma) {
+    using M = Math<R>;
+    const R d_x = mx - px;                                         // :198
+    const R d_y = my - py;                                         // :199
+    const R dist_sq = M::dot2(d_x, d_y, d_x, d_y, dot_fma);        // :203
+    if (dist_sq > K<R>::radius_sq) return false;                   // :210 (touching counts as contact)
+    R n_x, n_y;
+    if (M::exact) {
+        const R distance = M::sqrt_(dist_sq);                      // :214
+        if (distance > R(0)) { n_x = d_x / distance; n_y = d_y / distance; }   // :217
+        else { n_x = d_x; n_y = d_y; }
+    } else {
+        const R inv = dist_sq > R(0) ? rsqrtf((float)dist_sq) : R(1);
+        n_x = d_x * inv; n_y = d_y * inv;
+    }
+    // :220 `dcoll = radius - d` is a 2-VECTOR in the reference and :230 `np.max(dcoll - slop, 0)` is the
+    // axis-0 maximum of its two components (not a clamp at zero).  Reproduced as written.
+    const R a = (K<R>::radius - d_x) - R(0.01);
+    const R b = (K<R>::radius - d_y) - R(0.01);
+    const R m = (a >= b) ? a : b;
+    R s;
+    if (M::exact) s = (m / K<R>::imass_sum) * R(0.2);              // :230 ((max / imass_sum) * percent)
+    else s = m * R(0.2 / 12.0);
+    const R sep_x = s * n_x, sep_y = s * n_y;
+    px -= sep_x * K<R>::puck_imass;                                // :235
+    py -= sep_y * K<R>::puck_imass;                                // :236
+    mx += sep_x * K<R>::mallet_imass;                              // :237
+    my += sep_y * K<R>::mallet_imass;                              // :238
+    const R v_x = mdx - pdx;                                       // :241
+    const R v_y = mdy - pdy;                                       // :242
+    const R vn = M::dot2(v_x, v_y, n_x, n_y, dot_fma);             // :246
+    if (vn > R(0)) return true;                                    // :249 moving apart
+    R j;
+    if (M::exact) j = -(R(1.0) + R(0.9)) * (vn / K<R>::imass_sum); // :256
+    else j = vn * R(-1.9 / 12.0);
+    const R i_x = j * n_x, i_y = j * n_y;                          // :259
+    pdx -= i_x * K<R>::puck_imass;                                 // :262
+    pdy -= i_y * K<R>::puck_imass;                                 // :263
+    mdx += i_x * K<R>::mallet_imass;                               // :265
+    mdy += i_y * K<R>::mallet_imass;                               // :266
+    return true;
+}
+
+// ---- Puck.friction_on_puck  environment/puck.py:73-88 (dead code in the reference; opt-in flag) ----
+template <typename R>
+__device__ __forceinline__ void friction_on_puck(R& pdx, R& pdy) {
+    if (pdx > R(1)) pdx -= R(0.5);
+    if (pdx < R(-1)) pdx += R(0.5);
+    if (pdy > R(1)) pdy -= R(0.5);
+    else if (pdy < R(-1)) pdy += R(0.5);
+}
+
+// ---- Puck.limit_puck_speed  environment/puck.py:90-109 ----
+template <typename R>
+__device__ __forceinline__ void limit_puck_speed(R& pdx, R& pdy) {
+    pdx = (pdx > K<R>::speed) ? K<R>::speed : pdx;                 // :94-95
+    pdx = (pdx < -K<R>::speed) ? -K<R>::speed : pdx;               // :96-97
+    pdy = (pdy > K<R>::speed) ? K<R>::speed : pdy;                 // :100-101
+    pdy = (pdy < -K<R>::speed) ? K<R>::speed : pdy;                // :102-103: -> +speed, as in the reference
+}
+
+// ---- Puck.update  environment/puck.py:45-71: clamp + reflect FIRST, then advance ----
+template <typename R>
+__device__ __forceinline__ void puck_update(R& px, R& py, R& pdx, R& pdy) {
+    const bool fx = (px <= K<R>::puck_x_lo) || (px >= K<R>::puck_x_hi);
+    px = (px <= K<R>::puck_x_lo) ? K<R>::puck_x_lo : ((px >= K<R>::puck_x_hi) ? K<R>::puck_x_hi : px);
+    pdx = fx ? -pdx : pdx;                                         // `dx *= -1`
+    const bool fy = (py <= K<R>::puck_y_lo) || (py >= K<R>::puck_y_hi);
+    py = (py <= K<R>::puck_y_lo) ? K<R>::puck_y_lo : ((py >= K<R>::puck_y_hi) ? K<R>::puck_y_hi : py);
+    pdy = fy ? -pdy : pdy;
+    px += pdx;                                                     // :68
+    py += pdy;                                                     // :69
+}
+
+// ---- AirHockey.computerAI  environment/airhockey.py:270-308 ----
+template <typename R>
+__device__ __forceinline__ void computer_ai(Env<R>& e) {
+    using M = Math<R>;
+    if (e.px < e.ox) e.odx = (e.px < K<R>::opp_lo) ? R(1) : R(-2);             // :273-277
+    if (e.px > e.ox) e.odx = (e.px > K<R>::opp_hi) ? R(-1) : R(2);             // :279-283
+    if (e.py < e.oy) e.ody = (e.py < K<R>::y_lo) ? R(1) : R(-6);               // :285-289
+    if (e.py > e.oy) {                                                         // :291
+        e.ody = (e.py <= R(360)) ? R(6) : ((e.oy > R(200)) ? R(-2) : R(0));    // :292-300
+        if (M::abs_(e.py - e.oy) < R(40) && M::abs_(e.px - e.ox) < R(40)) {    // :303
+            e.pdx += R(2);                                                     // :304
+            e.pdy += R(2);                                                     // :305
+        }
+    }
+    mallet_update<R>(e.ox, e.oy, e.odx, e.ody, K<R>::opp_lo, K<R>::opp_hi);    // :307
+}
+
+// ---- the common tail of AirHockey.update_state  environment/airhockey.py:112-122 ----
+template <typename R>
+__device__ __forceinline__ void physics_tail(Env<R>& e, bool dot_fma, bool friction) {
+    collision<R>(e.px, e.py, e.pdx, e.pdy, e.rx, e.ry, e.rdx, e.rdy, dot_fma);   // :113-114 robot first
+    collision<R>(e.px, e.py, e.pdx, e.pdy, e.ox, e.oy, e.odx, e.ody, dot_fma);
+    if (friction) friction_on_puck<R>(e.pdx, e.pdy);
+    limit_puck_speed<R>(e.pdx, e.pdy);                                           // :117
+    puck_update<R>(e.px, e.py, e.pdx, e.pdy);                                    // :118
+    mallet_update<R>(e.rx, e.ry, e.rdx, e.rdy, K<R>::robot_lo, K<R>::robot_hi);  // :121-122
+    mallet_update<R>(e.ox, e.oy, e.odx, e.ody, K<R>::opp_lo, K<R>::opp_hi);
+}
+
+// ---- AirHockey.get_state + serialize_state  airhockey.py:136-147, puck.py:120-133, helpers.py:72-81 ----
+// obs = [int(agent.x), int(agent.y), int(puck.x), int(puck.y), agent.dx, agent.dy, puck.dx, puck.dy]
+template <typename R> struct Obs { R v[8]; };
+template <typename R>
+__device__ __forceinline__ Obs<R> get_state(const Env<R>& e, bool robot) {
+    using M = Math<R>;
+    Obs<R> o;
+    o.v[0] = M::trunc_(robot ? e.rx : e.ox); o.v[1] = M::trunc_(robot ? e.ry : e.oy);
+    o.v[2] = M::trunc_(e.px); o.v[3] = M::trunc_(e.py);
+    o.v[4] = robot ? e.rdx : e.odx; o.v[5] = robot ? e.rdy : e.ody;
+    o.v[6] = e.pdx; o.v[7] = e.pdy;
+    return o;
+}
+
+// ---- Rewards.__call__ for agent "robot"  lib/rewards.py:118-142 ----
+template <typename R>
+__device__ __forceinline__ void rewards_call(Env<R>& e, bool dot_fma, int& reward, int& score, bool& done) {
+    using M = Math<R>;
+    // compute_score_reward  rewards.py:64-81 with Goal.__contains__  goal.py:13-18; its reward and its own
+    // `done` are discarded by the caller (rewards.py:122).  The left-goal test comes second and wins ties.
+    const bool in_y = M::abs_(K<R>::mid_y - e.py) < R(95);
+    score = 0;
+    if (M::abs_(K<R>::table_w - e.px) < R(30) && in_y) score = 1;
+    if (M::abs_(R(0) - e.px) < R(30) && in_y) score = -1;
+    // compute_mallet_hit_puck  rewards.py:83-89 with Puck.__and__  puck.py:135-146
+    const R ex = e.px - e.rx, ey = e.py - e.ry;
+    const R dsq = M::dot2(ex, ey, ex, ey, dot_fma);
+    if (M::exact) {
+        // sqrt((px-mx)**2 + (py-my)**2) < 35 : plain (non-fused) sum of squares; `** 2` is libm pow() in the
+        // reference, evaluated here as x*x (they differ only within an ulp of the threshold)
+        done = M::sqrt_(ex * ex + ey * ey) < K<R>::radius;
+    } else {
+        done = dsq < K<R>::radius_sq;
+    }
+    int rw = done ? 3 : -1;
+    // compute_wall_reward  rewards.py:45-62 with Puck.__lshift__/__rshift__  puck.py:148-164
+    int wall = 0;
+    if (M::abs_(e.px - K<R>::left_wall) < K<R>::puck_r) wall = -2;
+    if (M::abs_(e.px - K<R>::right_wall) < K<R>::puck_r) wall = 2;
+    rw += wall;
+    // compute_mallet_to_puck_distance  rewards.py:91-101 (np.linalg.norm == sqrt(np.dot))
+    const R nd = M::sqrt_(dsq);
+    rw += (nd < e.prev_dist) ? 1 : -1;
+    e.prev_dist = nd;
+    reward = rw;
+}
+
+}  // namespace ah

@@ -1,0 +1,364 @@
+"""Host side of the batched environment: the reference's ``AirHockey`` verbs, vectorised over N games.
+
+``BatchedAirHockey`` owns the state as torch CUDA tensors (structure of arrays, see include/ah_b200.h) and
+forwards every verb to the C ABI with raw device pointers and the current CUDA stream.  PyTorch is used for
+device memory and streams only; all arithmetic happens in the sm_100a kernels of ``csrc/ah_b200.cu``.
+
+Reference interface mirrored here (paths relative to the reference root):
+    AirHockey.__init__        environment/airhockey.py:25-63
+    AirHockey.update_state    environment/airhockey.py:96-134   (InvalidAgentError for unknown agent names)
+    AirHockey.get_state       environment/airhockey.py:136-147  (+ serialize_state, lib/utils/helpers.py:72-81)
+    AirHockey.update_score    environment/airhockey.py:149-169
+    AirHockey.reset           environment/airhockey.py:171-187
+    Rewards.__call__          lib/rewards.py:118-142
+    one frame of Game.play    game.py:133-177 + lib/agents/agent.py:57-78          -> ``step``
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, Optional, Sequence, Union
+
+import torch
+
+from . import _capi
+from .exceptions import InvalidAgentError
+
+_AGENTS = {"robot": _capi.AH_AGENT_ROBOT, "human": _capi.AH_AGENT_HUMAN, "computer": _capi.AH_AGENT_COMPUTER}
+
+STEP_FIELDS = ("obs_state", "obs_new_state", "reward", "done", "score", "game_over", "obs_next")
+
+
+@dataclass
+class StepOutputs:
+    """Per-frame outputs of ``BatchedAirHockey.step``; any field may be None (not produced)."""
+    obs_state: Optional[torch.Tensor] = None       # real [K,N,8]  Observation.state      (agent.py:61)
+    obs_new_state: Optional[torch.Tensor] = None   # real [K,N,8]  Observation.new_state  (agent.py:67)
+    reward: Optional[torch.Tensor] = None          # real [K,N]
+    done: Optional[torch.Tensor] = None            # u8   [K,N]
+    score: Optional[torch.Tensor] = None           # i8   [K,N]
+    game_over: Optional[torch.Tensor] = None       # u8   [K,N]    0 / 1 robot won / 2 opponent won
+    obs_next: Optional[torch.Tensor] = None        # real [N,8] or [K,N,8]: the next frame's policy input
+
+
+class ReplayRing:
+    """Device-resident replacement of ``MemoryBuffer`` (lib/buffer.py:11-66) for ``Observation`` tuples
+    (lib/types.py:7), filled from inside the step kernel.  Layout ``[capacity, N, ...]``; like the reference's
+    ``appendleft`` + ``retreive`` the newest entry comes first when read back."""
+
+    def __init__(self, capacity: int, n_envs: int, dtype: torch.dtype, device, continuous: bool = False):
+        self.capacity, self.n = int(capacity), int(n_envs)
+        self.continuous = continuous
+        self.state = torch.zeros(capacity, n_envs, 8, dtype=dtype, device=device)
+        self.new_state = torch.zeros(capacity, n_envs, 8, dtype=dtype, device=device)
+        self.action = (torch.zeros(capacity, n_envs, 2, dtype=dtype, device=device) if continuous
+                       else torch.zeros(capacity, n_envs, dtype=torch.int8, device=device))
+        self.reward = torch.zeros(capacity, n_envs, dtype=dtype, device=device)
+        self.done = torch.zeros(capacity, n_envs, dtype=torch.uint8, device=device)
+        self._c = _capi.AhRing(self.state.data_ptr(), self.new_state.data_ptr(), self.action.data_ptr(),
+                               self.reward.data_ptr(), self.done.data_ptr(), self.capacity)
+        self.appended = 0          # host mirror of the device counter (valid when steps are not graph-replayed)
+
+    def __len__(self) -> int:      # lib/buffer.py:63-66
+        return min(self.appended, self.capacity)
+
+    def order(self) -> torch.Tensor:
+        """Slot indices newest-first, the order of ``MemoryBuffer.retreive`` (lib/buffer.py:34-45)."""
+        n = len(self)
+        newest = (self.appended - 1) % self.capacity
+        return (newest - torch.arange(n, device=self.state.device)) % self.capacity
+
+    def retreive(self) -> Dict[str, torch.Tensor]:
+        idx = self.order()
+        return {"state": self.state[idx], "action": self.action[idx], "reward": self.reward[idx],
+                "done": self.done[idx], "new_state": self.new_state[idx]}
+
+    def sample(self, batch_size: int, generator: Optional[torch.Generator] = None) -> Dict[str, torch.Tensor]:
+        """Uniform sample without replacement over (slot, env) pairs (lib/buffer.py:47-50), on device."""
+        total = len(self) * self.n
+        if batch_size > total:
+            raise ValueError("Sample larger than population")        # what random.sample raises
+        flat = torch.randperm(total, device=self.state.device, generator=generator)[:batch_size]
+        slot, env = self.order()[flat // self.n], flat % self.n
+        return {"state": self.state[slot, env], "action": self.action[slot, env], "reward": self.reward[slot, env],
+                "done": self.done[slot, env], "new_state": self.new_state[slot, env]}
+
+    def purge(self) -> None:       # lib/buffer.py:52-61
+        self.appended = 0
+
+
+class BatchedAirHockey:
+    """N independent air-hockey games stepped on one GPU."""
+
+    def __init__(self, n_envs: int, dtype: torch.dtype = torch.float32, device: Union[str, torch.device] = "cuda",
+                 seed: int = 0, env_id0: int = 0, dot_fma: bool = True, friction: bool = False):
+        if dtype not in (torch.float32, torch.float64):
+            raise ValueError("dtype must be torch.float32 (throughput build) or torch.float64 (validation build)")
+        self._lib = _capi.lib()                       # raises ImportError when the CUDA library is missing
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("BatchedAirHockey runs on CUDA devices only (no CPU fallback)")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.n, self.dtype, self.seed, self.env_id0 = int(n_envs), dtype, int(seed), int(env_id0)
+        self._h = C.c_void_p()
+        cfg = _capi.AhConfig(int(dot_fma), int(friction))
+        _capi.check(self._lib.ah_create(C.byref(self._h), self.n, _capi.AH_F32 if dtype == torch.float32 else _capi.AH_F64,
+                                        self.device.index, self.seed, self.env_id0, C.byref(cfg)), "ah_create")
+        kw = dict(dtype=dtype, device=self.device)
+        self.puck = torch.empty(self.n, 4, **kw)          # x, y, dx, dy
+        self.robot = torch.empty(self.n, 4, **kw)
+        self.opponent = torch.empty(self.n, 4, **kw)
+        self.prev_dist = torch.empty(self.n, **kw)
+        self.meta = torch.zeros(self.n, 4, dtype=torch.int32, device=self.device)
+        self._bind()
+        self._stats_buf = torch.zeros(_capi.AH_NSTATS, dtype=torch.int64, device=self.device)
+        self._io_keepalive = None
+        self.step_size = 10                               # airhockey.py:63
+        _capi.check(self._lib.ah_init_state(self._h, self._stream()), "ah_init_state", self._h)
+
+    # ------------------------------------------------------------------ plumbing
+    def _bind(self) -> None:
+        _capi.check(self._lib.ah_bind_state(self._h, self.puck.data_ptr(), self.robot.data_ptr(), self.opponent.data_ptr(),
+                                            self.prev_dist.data_ptr(), self.meta.data_ptr()), "ah_bind_state", self._h)
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.ah_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check_tensor(self, t: torch.Tensor, shape: Sequence[int], dtype: torch.dtype, name: str) -> torch.Tensor:
+        if t.device != self.device or t.dtype != dtype or tuple(t.shape) != tuple(shape) or not t.is_contiguous():
+            raise ValueError(f"{name}: expected contiguous {dtype} {tuple(shape)} on {self.device}, "
+                             f"got {t.dtype} {tuple(t.shape)} on {t.device}")
+        return t
+
+    def _table(self, reset_table: Optional[torch.Tensor]):
+        if reset_table is None:
+            return None, 0
+        if (reset_table.device != self.device or reset_table.dtype != torch.float64 or reset_table.dim() != 3
+                or reset_table.shape[0] != self.n or reset_table.shape[2] != 2 or not reset_table.is_contiguous()):
+            raise ValueError("reset_table must be a contiguous float64 [N, R, 2] tensor on the env's device")
+        return reset_table.data_ptr(), int(reset_table.shape[1])
+
+    # ------------------------------------------------------------------ views
+    @property
+    def scores(self) -> torch.Tensor:
+        """int16 [N,2] view: (robot_score, opponent_score)  (airhockey.py:52)."""
+        return self.meta.view(torch.int16)[:, 0:2]
+
+    @property
+    def robot_score(self) -> torch.Tensor:
+        return self.scores[:, 0]
+
+    @property
+    def opponent_score(self) -> torch.Tensor:
+        return self.scores[:, 1]
+
+    @property
+    def reset_count(self) -> torch.Tensor:
+        return self.meta[:, 1]
+
+    # ------------------------------------------------------------------ reference verbs
+    def init_state(self) -> None:
+        """Back to the constructor state (airhockey.py:25-63)."""
+        _capi.check(self._lib.ah_init_state(self._h, self._stream()), "ah_init_state", self._h)
+
+    def reset(self, total: bool = False, mask: Optional[torch.Tensor] = None,
+              reset_table: Optional[torch.Tensor] = None) -> None:
+        """``AirHockey.reset(total)``: puck to the centre with a fresh U(-10,10) velocity, mallet velocities
+        zeroed (positions kept); ``total`` also clears both scores.  ``mask`` (uint8/bool [N]) selects envs."""
+        mp = None
+        if mask is not None:
+            mask = self._check_tensor(mask.to(torch.uint8) if mask.dtype == torch.bool else mask, (self.n,), torch.uint8, "mask")
+            mp = mask.data_ptr()
+        tp, R = self._table(reset_table)
+        _capi.check(self._lib.ah_reset(self._h, int(total), mp, tp, R, self._stream()), "ah_reset", self._h)
+
+    def update_state(self, action: Optional[torch.Tensor] = None, agent_name: str = "") -> None:
+        """``AirHockey.update_state(action, agent_name)``: one physics sub-update for every env.
+
+        robot:    ``action`` int8/int64 [N] (discrete) or real [N,2] (continuous, added to the velocity)
+        human:    ``action`` real [N,2] = new location of the opponent's mallet
+        computer: no action (the heuristic opponent moves)
+        """
+        if agent_name not in _AGENTS:
+            raise InvalidAgentError(agent_name)          # airhockey.py:108-110
+        agent = _AGENTS[agent_name]
+        ap, kind = None, _capi.AH_ACT_NONE
+        if agent != _capi.AH_AGENT_COMPUTER and action is not None:
+            if action.dim() == 2:
+                action = self._check_tensor(action, (self.n, 2), self.dtype, "action")
+                kind = _capi.AH_ACT_CONTINUOUS
+            else:
+                if action.dtype != torch.int8:
+                    action = action.to(torch.int8)
+                action = self._check_tensor(action, (self.n,), torch.int8, "action")
+                kind = _capi.AH_ACT_DISCRETE
+            ap = action.data_ptr()
+        _capi.check(self._lib.ah_update_state(self._h, ap, kind, agent, self._stream()), "ah_update_state", self._h)
+
+    def get_state(self, agent_name: str = "robot", out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``serialize_state(AirHockey.get_state(agent_name))`` for every env: real [N,8] =
+        int(agent.x), int(agent.y), int(puck.x), int(puck.y), agent.dx, agent.dy, puck.dx, puck.dy."""
+        if out is None:
+            out = torch.empty(self.n, 8, dtype=self.dtype, device=self.device)
+        self._check_tensor(out, (self.n, 8), self.dtype, "out")
+        agent = _capi.AH_AGENT_ROBOT if agent_name == "robot" else _capi.AH_AGENT_COMPUTER   # airhockey.py:139
+        _capi.check(self._lib.ah_get_state(self._h, agent, out.data_ptr(), self._stream()), "ah_get_state", self._h)
+        return out
+
+    def update_score(self, score: torch.Tensor, reset_table: Optional[torch.Tensor] = None) -> None:
+        """``AirHockey.update_score(score)``: +1 -> robot_score++, -1 -> opponent_score++, then ``reset()``."""
+        if score.dtype != torch.int8:
+            score = score.to(torch.int8)
+        self._check_tensor(score, (self.n,), torch.int8, "score")
+        tp, R = self._table(reset_table)
+        _capi.check(self._lib.ah_update_score(self._h, score.data_ptr(), tp, R, self._stream()), "ah_update_score", self._h)
+
+    def rewards(self):
+        """``Rewards.__call__(puck, robot)`` on the current state -> (reward real [N], score i8 [N], done u8 [N])."""
+        reward = torch.empty(self.n, dtype=self.dtype, device=self.device)
+        score = torch.empty(self.n, dtype=torch.int8, device=self.device)
+        done = torch.empty(self.n, dtype=torch.uint8, device=self.device)
+        _capi.check(self._lib.ah_rewards(self._h, reward.data_ptr(), score.data_ptr(), done.data_ptr(), self._stream()),
+                    "ah_rewards", self._h)
+        return reward, score, done
+
+    # ------------------------------------------------------------------ the fused frame
+    def make_outputs(self, K: int = 1, fields: Sequence[str] = ("reward", "done", "score", "game_over", "obs_next"),
+                     obs_next_per_frame: bool = False) -> StepOutputs:
+        """Preallocate output tensors for ``step`` (reuse them across steps: nothing is allocated per step)."""
+        o = StepOutputs()
+        for f in fields:
+            if f not in STEP_FIELDS:
+                raise ValueError(f"unknown output field {f!r}")
+        r = dict(dtype=self.dtype, device=self.device)
+        if "obs_state" in fields:
+            o.obs_state = torch.empty(K, self.n, 8, **r)
+        if "obs_new_state" in fields:
+            o.obs_new_state = torch.empty(K, self.n, 8, **r)
+        if "reward" in fields:
+            o.reward = torch.empty(K, self.n, **r)
+        if "done" in fields:
+            o.done = torch.empty(K, self.n, dtype=torch.uint8, device=self.device)
+        if "score" in fields:
+            o.score = torch.empty(K, self.n, dtype=torch.int8, device=self.device)
+        if "game_over" in fields:
+            o.game_over = torch.empty(K, self.n, dtype=torch.uint8, device=self.device)
+        if "obs_next" in fields:
+            o.obs_next = torch.empty((K, self.n, 8) if obs_next_per_frame else (self.n, 8), **r)
+        return o
+
+    def step(self, actions: Optional[torch.Tensor] = None, K: int = 1, *, repeat: bool = False,
+             out: Optional[StepOutputs] = None, reset_table: Optional[torch.Tensor] = None,
+             ring: Optional[ReplayRing] = None, collect_stats: bool = True) -> StepOutputs:
+        """K fused frames of ``Game.play`` for every env, in ONE kernel launch (state stays in registers).
+
+        actions: None                -> uniform random {0,1,2,3} drawn in-kernel (Philox)
+                 int8 [K,N]          -> one discrete action per frame   ([N] when K == 1 or ``repeat``)
+                 real [K,N,2]        -> one continuous action per frame ([N,2] when K == 1 or ``repeat``)
+        repeat:  apply the single given action to all K frames (frame-skip)
+        out:     preallocated ``StepOutputs`` (see ``make_outputs``); default: reward/done/score/game_over/obs_next
+        """
+        if out is None:
+            out = self.make_outputs(K)
+        io = _capi.AhStepIO()
+        if actions is None:
+            io.action_kind = _capi.AH_ACT_PHILOX
+        else:
+            per_env = repeat or K == 1
+            if actions.dtype in (torch.float32, torch.float64):
+                shape = (self.n, 2) if (per_env and actions.dim() == 2) else (K, self.n, 2)
+                self._check_tensor(actions, shape, self.dtype, "actions")
+                io.action_kind = _capi.AH_ACT_CONTINUOUS_REPEAT if repeat else _capi.AH_ACT_CONTINUOUS
+            else:
+                if actions.dtype != torch.int8:
+                    actions = actions.to(torch.int8)
+                shape = (self.n,) if (per_env and actions.dim() == 1) else (K, self.n)
+                self._check_tensor(actions, shape, torch.int8, "actions")
+                io.action_kind = _capi.AH_ACT_DISCRETE_REPEAT if repeat else _capi.AH_ACT_DISCRETE
+            io.actions = actions.data_ptr()
+        tp, R = self._table(reset_table)
+        io.reset_table, io.reset_table_len = tp, R
+        r = self.dtype
+        if out.obs_state is not None:
+            io.obs_state = self._check_tensor(out.obs_state, (K, self.n, 8), r, "obs_state").data_ptr()
+        if out.obs_new_state is not None:
+            io.obs_new_state = self._check_tensor(out.obs_new_state, (K, self.n, 8), r, "obs_new_state").data_ptr()
+        if out.reward is not None:
+            io.reward = self._check_tensor(out.reward, (K, self.n), r, "reward").data_ptr()
+        if out.done is not None:
+            io.done = self._check_tensor(out.done, (K, self.n), torch.uint8, "done").data_ptr()
+        if out.score is not None:
+            io.score = self._check_tensor(out.score, (K, self.n), torch.int8, "score").data_ptr()
+        if out.game_over is not None:
+            io.game_over = self._check_tensor(out.game_over, (K, self.n), torch.uint8, "game_over").data_ptr()
+        if out.obs_next is not None:
+            per_frame = out.obs_next.dim() == 3
+            io.obs_next = self._check_tensor(out.obs_next, (K, self.n, 8) if per_frame else (self.n, 8), r, "obs_next").data_ptr()
+            io.obs_next_per_frame = int(per_frame)
+        io.collect_stats = int(collect_stats)
+        if ring is not None:
+            if ring.n != self.n or ring.state.dtype != self.dtype or ring.state.device != self.device:
+                raise ValueError("ring does not match this environment")
+            if ring.continuous != (io.action_kind in (_capi.AH_ACT_CONTINUOUS, _capi.AH_ACT_CONTINUOUS_REPEAT)):
+                raise ValueError("ring action layout (discrete/continuous) does not match the actions given")
+            io.ring = C.pointer(ring._c)
+            ring.appended += K
+        self._io_keepalive = (io, actions)
+        _capi.check(self._lib.ah_step(self._h, C.byref(io), int(K), self._stream()), "ah_step", self._h)
+        return out
+
+    # ------------------------------------------------------------------ statistics, counters, checkpoints
+    def stats_tensor(self, clear: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """int64 [16] device tensor of the AH_STAT_* counters accumulated by ``step`` (no host sync)."""
+        out = self._stats_buf if out is None else out
+        _capi.check(self._lib.ah_stats(self._h, out.data_ptr(), int(clear), self._stream()), "ah_stats", self._h)
+        return out
+
+    def stats(self, clear: bool = False) -> Dict[str, int]:
+        v = self.stats_tensor(clear).tolist()
+        return dict(zip(_capi.STAT_NAMES, v))
+
+    def set_counters(self, frame: int = 0, ring_appended: int = 0) -> None:
+        _capi.check(self._lib.ah_set_counters(self._h, frame, ring_appended, self._stream()), "ah_set_counters", self._h)
+
+    def counters(self) -> Dict[str, int]:
+        buf = torch.zeros(2, dtype=torch.int64, device=self.device)
+        _capi.check(self._lib.ah_get_counters(self._h, buf.data_ptr(), self._stream()), "ah_get_counters", self._h)
+        f, r = buf.tolist()
+        return {"frame": f, "ring_appended": r}
+
+    def launch_info(self) -> Dict[str, int]:
+        b, t, s = C.c_int(), C.c_int(), C.c_int()
+        _capi.check(self._lib.ah_launch_info(self._h, C.byref(b), C.byref(t), C.byref(s)), "ah_launch_info", self._h)
+        return {"blocks": b.value, "threads": t.value, "sms": s.value}
+
+    def compiled_without_fma_contraction(self) -> bool:
+        buf = torch.ones(1, dtype=torch.float64, device=self.device)
+        _capi.check(self._lib.ah_selftest_nofma(self._h, buf.data_ptr(), self._stream()), "ah_selftest_nofma", self._h)
+        return float(buf.item()) == 0.0
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        """Exact checkpoint of the environment (the reference never checkpoints env state)."""
+        c = self.counters()
+        return {"puck": self.puck.clone(), "robot": self.robot.clone(), "opponent": self.opponent.clone(),
+                "prev_dist": self.prev_dist.clone(), "meta": self.meta.clone(),
+                "counters": torch.tensor([c["frame"], c["ring_appended"]], dtype=torch.int64),
+                "seed": torch.tensor([self.seed, self.env_id0], dtype=torch.int64)}
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
+        for k in ("puck", "robot", "opponent", "prev_dist", "meta"):
+            getattr(self, k).copy_(sd[k])
+        f, r = sd["counters"].tolist()
+        self.set_counters(int(f), int(r))

@@ -1,0 +1,191 @@
+/*
+ * include/ah_b200.h -- C ABI of the B200-native batched air-hockey environment step.
+ *
+ * This is the drop-in boundary for the ONE hot path this project accelerates: the environment step of
+ * Positronic-IO/air-hockey-training-environment (`AirHockey` reset / update_state / get_state, the
+ * `Rewards` reward and the `computerAI` heuristic opponent, looped as game.py does), for N independent
+ * games resident in HBM.  The reference has no FFI for this path (it is pure Python); the entry points
+ * below are what a ctypes binding of the reference's environment API would bind -- each one cites the
+ * reference interface it replaces (paths relative to the reference root).  INTEGRATION.md shows the
+ * reference-side stub.
+ *
+ * Conventions
+ *   - plain C: opaque handle, raw pointers and sizes; no torch / C++ types cross this boundary;
+ *   - every pointer named `d_*` or documented "device" is a CUDA device address owned by the CALLER
+ *     (e.g. torch tensors).  The library never allocates state or outputs: its only allocations are the
+ *     host handle and one 256-byte device block (statistics + counters);
+ *   - every call enqueues on the caller's stream (`void* stream` is a cudaStream_t; NULL = legacy default
+ *     stream), never synchronises and never allocates, so all of them can be captured in a CUDA graph;
+ *   - return value: AH_OK (0) or a negative AH_E* code; ah_strerror() names it.  No exception or signal
+ *     crosses the boundary.  There is NO CPU fallback: without a CUDA device every compute call fails with
+ *     AH_ECUDA.
+ *   - a handle is not thread-safe; distinct handles (one per GPU) are independent.
+ *
+ * State layout in HBM (structure of arrays, one row per environment, all rows 16-byte aligned):
+ *   puck      real[n][4]   x, y, dx, dy                          environment/puck.py:16-43
+ *   robot     real[n][4]   x, y, dx, dy   (left mallet)           environment/mallet.py:11-48, airhockey.py:46
+ *   opponent  real[n][4]   x, y, dx, dy   (right mallet)          airhockey.py:49
+ *   prev_dist real[n]      Rewards.prev_mallet_to_puck_distance   lib/rewards.py:31,96-100
+ *   meta      int32[n][4]  [0] robot_score | opponent_score<<16   airhockey.py:52
+ *                          [1] resets consumed (RNG counter / reset-table cursor)
+ *                          [2] frames played in the current game, [3] reward summed over the current game
+ *   `real` is float (AH_F32, throughput build) or double (AH_F64, validation build that preserves the
+ *   reference's operation order and numpy's FMA-contracted dot products).
+ */
+#ifndef AH_B200_H
+#define AH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AH_ABI_VERSION 1
+
+typedef struct ah_env ah_env;
+
+/* ---- error codes ---- */
+enum {
+    AH_OK = 0,
+    AH_EINVAL = -1,   /* NULL / misaligned pointer, n <= 0, K out of range, bad enum */
+    AH_ECUDA = -2,    /* a CUDA runtime call failed; ah_last_cuda_error() has the cudaError_t */
+    AH_ENOMEM = -3,
+    AH_EAGENT = -4,   /* unknown agent: the reference's InvalidAgentError (airhockey.py:108-110) */
+    AH_ESTATE = -5    /* state not bound yet */
+};
+
+/* ---- enums ---- */
+enum { AH_F32 = 0, AH_F64 = 1 };
+/* agent_name of AirHockey.update_state / get_state (airhockey.py:100-110, :139) */
+enum { AH_AGENT_ROBOT = 0, AH_AGENT_HUMAN = 1, AH_AGENT_COMPUTER = 2 };
+/* where the robot's actions come from (Action = Union[int, Tuple], lib/types.py:5; airhockey.py:65-84) */
+enum {
+    AH_ACT_NONE = 0,         /* no action argument (agent "computer")                                   */
+    AH_ACT_DISCRETE = 1,     /* int8 [K][n]: 0 y+=10, 1 y-=10, 2 x-=10, 3 x+=10, anything else no nudge  */
+    AH_ACT_CONTINUOUS = 2,   /* real [K][n][2]: added to the mallet velocity (airhockey.py:69-71); for     */
+                             /* agent "human": real [n][2] = the new mallet location (airhockey.py:104)   */
+    AH_ACT_PHILOX = 3,       /* uniform {0,1,2,3} drawn in-kernel (synthetic random-action workload)     */
+    AH_ACT_DISCRETE_REPEAT = 4,   /* int8 [n]: one action applied to all K frames (frame-skip)            */
+    AH_ACT_CONTINUOUS_REPEAT = 5  /* real [n][2]: one action applied to all K frames                      */
+};
+
+/* indices into the statistics vector (int64[AH_NSTATS]); the device-side equivalent of the per-frame
+ * scores.csv row (game.py:82-112) and of the rewards CSV (lib/rewards.py:129-140) */
+enum {
+    AH_STAT_FRAMES = 0,
+    AH_STAT_ROBOT_GOALS = 1,
+    AH_STAT_OPPONENT_GOALS = 2,
+    AH_STAT_ROBOT_WINS = 3,
+    AH_STAT_OPPONENT_WINS = 4,
+    AH_STAT_DONES = 5,
+    AH_STAT_REWARD_SUM = 6,
+    AH_STAT_REWARD_SQ_SUM = 7,
+    AH_STAT_GAMES = 8,            /* games finished (robot_wins + opponent_wins) */
+    AH_STAT_GAME_LEN_SUM = 9,     /* frames of the finished games */
+    AH_STAT_GAME_LEN_SQ_SUM = 10,
+    AH_STAT_GAME_RETURN_SUM = 11, /* reward summed over the finished games */
+    AH_STAT_NONFINITE = 12,       /* envs whose puck state was non-finite at the end of a launch */
+    AH_NSTATS = 16
+};
+
+/* ---- configuration (flags only; the physical constants of environment/config.py are compile-time) ---- */
+typedef struct ah_config {
+    int32_t dot_fma;    /* 1: the 2-vector dot products are fma(b,d,fl(a*c)) like numpy/OpenBLAS (default) */
+    int32_t friction;   /* 1: apply Puck.friction_on_puck (puck.py:73-88) before the speed clamp; the      */
+                        /*    reference never calls it (dead code), so the default is 0                    */
+    int32_t reserved[6];
+} ah_config;
+
+/* ---- optional fused replay/rollout ring (replaces MemoryBuffer.append, lib/buffer.py:24-32, fed with the
+ *      Observation tuple of lib/agents/agent.py:74).  Slot = (appended so far) mod capacity; the newest
+ *      entry is read first, as `appendleft` + `retreive` do (lib/buffer.py:27,45). ---- */
+typedef struct ah_ring {
+    void* state;        /* real   [capacity][n][8]  Observation.state     */
+    void* new_state;    /* real   [capacity][n][8]  Observation.new_state */
+    void* action;       /* int8   [capacity][n]     (discrete) or real [capacity][n][2] (continuous) */
+    void* reward;       /* real   [capacity][n] */
+    uint8_t* done;      /* uint8  [capacity][n] */
+    int64_t capacity;
+} ah_ring;
+
+/* ---- inputs / outputs of the fused step ---- */
+typedef struct ah_step_io {
+    /* inputs */
+    const void* actions;          /* device; see AH_ACT_* (NULL for AH_ACT_PHILOX) */
+    int32_t action_kind;
+    int32_t reset_table_len;      /* R */
+    const double* reset_table;    /* device double [n][R][2] (dx, dy) per reset, or NULL => in-kernel Philox.    */
+                                  /* Stands in for the global np.random.uniform draws of puck.py:115-116.       */
+    /* per-frame outputs, each nullable; [K][n]... */
+    void* obs_state;              /* real [K][n][8]  Observation.state     (agent.py:61)  */
+    void* obs_new_state;          /* real [K][n][8]  Observation.new_state (agent.py:67)  */
+    void* reward;                 /* real [K][n]     lib/rewards.py:118-142               */
+    uint8_t* done;                /* u8   [K][n]     "mallet overlaps puck" (rewards.py:86-89,124) */
+    int8_t* score;                /* i8   [K][n]     +1 robot scored, -1 opponent scored (rewards.py:64-81) */
+    uint8_t* game_over;           /* u8   [K][n]     0, 1 robot reached 10, 2 opponent reached 10 (game.py:101-109,169-177) */
+    /* observation at the end of the frame = the policy input of the next frame (agent.py:46) */
+    void* obs_next;               /* real [n][8] (last frame only) or [K][n][8] when obs_next_per_frame */
+    int32_t obs_next_per_frame;
+    int32_t collect_stats;        /* accumulate the AH_STAT_* vector (warp-reduced, one atomic set per block) */
+    const ah_ring* ring;          /* NULL => no append */
+} ah_step_io;
+
+const char* ah_strerror(int code);
+int ah_abi_version(void);
+int ah_last_cuda_error(const ah_env* env);
+
+/* AirHockey() for n games (airhockey.py:25-63).  `env_id0` is the global id of local env 0: the RNG is
+ * keyed on (seed, env_id0 + i) so results do not depend on how the envs are sharded over GPUs. */
+int ah_create(ah_env** out, int64_t n, int dtype, int device, uint64_t seed, uint64_t env_id0, const ah_config* cfg);
+int ah_destroy(ah_env* env);
+
+/* Attach caller-owned device state (layout above). */
+int ah_bind_state(ah_env* env, void* d_puck, void* d_robot, void* d_opponent, void* d_prev_dist, int32_t* d_meta);
+
+/* Write the constructor state (airhockey.py:39-52, puck.py:16, rewards.py:31) into the bound arrays. */
+int ah_init_state(ah_env* env, void* stream);
+
+/* AirHockey.reset(total) (airhockey.py:171-187) for the envs whose mask byte is non-zero (NULL = all). */
+int ah_reset(ah_env* env, int total, const uint8_t* d_mask, const double* d_reset_table, int reset_table_len,
+             void* stream);
+
+/* AirHockey.update_state(action, agent_name) (airhockey.py:96-134): ONE physics sub-update. */
+int ah_update_state(ah_env* env, const void* d_actions, int action_kind, int agent, void* stream);
+
+/* AirHockey.get_state(agent_name) flattened by serialize_state (airhockey.py:136-147, helpers.py:72-81):
+ * real [n][8] = int(agent.x), int(agent.y), int(puck.x), int(puck.y), agent.dx, agent.dy, puck.dx, puck.dy */
+int ah_get_state(ah_env* env, int agent, void* d_obs, void* stream);
+
+/* AirHockey.update_score(score) (airhockey.py:149-169): score int8 [n]. */
+int ah_update_score(ah_env* env, const int8_t* d_score, const double* d_reset_table, int reset_table_len,
+                    void* stream);
+
+/* Rewards.__call__(puck, robot_mallet) (lib/rewards.py:118-142) on the current state: reward real [n],
+ * score int8 [n] (+1 / -1 / 0), done uint8 [n]; updates prev_dist.  Outputs are nullable. */
+int ah_rewards(ah_env* env, void* d_reward, int8_t* d_score, uint8_t* d_done, void* stream);
+
+/* K fused frames of Game.play (game.py:133-177 + agent.py:57-78): per frame
+ *   update_state(a,"robot"); state; update_state(a,"robot"); new_state; Rewards; update_score;
+ *   update_state("computer"); 10-goal game over.            1 <= K <= 4096 */
+int ah_step(ah_env* env, const ah_step_io* io, int K, void* stream);
+
+/* Copy the int64[AH_NSTATS] statistics block to a caller device buffer, optionally clearing it. */
+int ah_stats(ah_env* env, int64_t* d_out, int clear, void* stream);
+
+/* Global frame counter (Philox action index) and ring append counter, kept on the device so that captured
+ * graphs advance them; get copies {frame, ring_appended} (uint64[2]) to a caller device buffer. */
+int ah_set_counters(ah_env* env, uint64_t frame, uint64_t ring_appended, void* stream);
+int ah_get_counters(ah_env* env, uint64_t* d_out2, void* stream);
+
+/* Launch geometry actually used by ah_step (for reports): blocks, threads per block, SM count. */
+int ah_launch_info(const ah_env* env, int* blocks, int* threads, int* sms);
+
+/* Build self-test: writes a*b+c of a discriminating triple to d_scratch (device double[1]); the value is 0.0
+ * iff the library was compiled WITHOUT multiply-add contraction, which the AH_F64 build relies on. */
+int ah_selftest_nofma(ah_env* env, double* d_scratch, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AH_B200_H */

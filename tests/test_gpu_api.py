@@ -1,0 +1,262 @@
+"""GPU tests of the drop-in API surface: the reference's own unit-test pins re-expressed against the CUDA
+path, error behaviour, K-fusion / sharding / replay invariance, the fused ring buffer, CUDA-graph capture,
+and size-independent properties at BASELINE's full sizes (1M envs FP32, K=8)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def make_env(n, dtype=torch.float32, **kw):
+    from air_hockey_training_environment_b200 import BatchedAirHockey
+    return BatchedAirHockey(n, dtype=dtype, device="cuda", **kw)
+
+
+def snapshot(env):
+    return [t.clone() for t in (env.puck, env.robot, env.opponent, env.prev_dist, env.meta)]
+
+
+def same(a, b):
+    return all(torch.equal(x.view(torch.uint8), y.view(torch.uint8)) for x, y in zip(a, b))
+
+
+# ---------------------------------------------------------------- the reference's unit pins, on the GPU
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_initial_state_and_observation(dtype):
+    env = make_env(8, dtype)
+    assert env.get_state("robot")[0].tolist() == [350, 240, 450, 240, 0, 0, -3, 0]
+    assert env.get_state("opponent")[0].tolist() == [550, 240, 450, 240, 0, 0, -3, 0]
+    assert env.scores.sum().item() == 0 and torch.isinf(env.prev_dist).all()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_environment_pin(dtype):
+    # reference tests/test_environment.py:9-16 (with "computer" for the stale "opponent"): puck at (438, 240)
+    env = make_env(4, dtype)
+    d = env.device
+    env.update_state(torch.tensor([[80.0, 100.0]] * 4, dtype=dtype, device=d), "robot")
+    env.update_state(agent_name="computer")
+    env.update_state(torch.tensor([[200.0, 234.0]] * 4, dtype=dtype, device=d), "robot")
+    env.update_state(agent_name="computer")
+    assert env.get_state()[0, 2:4].tolist() == [438, 240]
+
+
+def test_invalid_agent_raises():
+    from air_hockey_training_environment_b200 import InvalidAgentError
+    env = make_env(4)
+    with pytest.raises(InvalidAgentError):       # airhockey.py:108-110 ; tests/test_environment.py uses "opponent"
+        env.update_state(torch.zeros(4, 2, device=env.device), "opponent")
+    with pytest.raises(InvalidAgentError):
+        env.update_state()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_mallet_limits(dtype):
+    # reference tests/test_mallet.py:31-63: robot x in [20,430], opponent x in [470,880], y in [20,460]
+    env = make_env(2, dtype)
+    env.robot[:, 0:2] = torch.tensor([[-1.0, -1.0], [1000.0, 1000.0]], dtype=dtype)
+    env.update_state(agent_name="computer")      # tail of update_state runs Mallet.update on both mallets
+    assert env.robot[:, 0:2].tolist() == [[20, 20], [430, 460]]
+    env.update_state(torch.tensor([[-1.0, -1.0], [1000.0, 1000.0]], dtype=dtype, device=env.device), "human")
+    assert env.opponent[:, 0:2].tolist() == [[470, 20], [880, 460]]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_reward_predicates(dtype):
+    # reference tests/test_puck.py:18-63 and tests/test_goal.py:14-40 through Rewards.__call__
+    env = make_env(8, dtype)
+    P = torch.tensor([[340, 230], [300, 190],        # overlap robot mallet at (350,240): yes / no
+                      [10, 300], [100, 300],         # left wall: yes / no
+                      [890, 300], [800, 300],        # right wall: yes / no
+                      [10, 240], [900, 240]],        # in left goal / in right goal
+                     dtype=dtype)
+    env.puck[:, 0:2] = P.to(env.device)
+    reward, score, done = env.rewards()
+    assert done.tolist() == [1, 0, 0, 0, 0, 0, 0, 0]
+    assert score.tolist() == [0, 0, 0, 0, 0, 0, -1, 1]
+    # reward = (3 | -1) + wall(-2 | +2 | 0) + (+1: closer than prev (inf))
+    assert reward.tolist() == [4, 0, -2, 0, 2, 0, -2, 2]
+    assert not torch.isinf(env.prev_dist).any()
+    # goal test fails away from the mouth: (10, 30) and (900, 30)   (tests/test_goal.py:25,39)
+    env.puck[0:2, 0:2] = torch.tensor([[10, 30], [900, 30]], dtype=dtype).to(env.device)
+    assert env.rewards()[1][0:2].tolist() == [0, 0]
+
+
+def test_update_score_and_reset():
+    env = make_env(6, torch.float64, seed=5)
+    env.robot[:, 2:4] = 3.0
+    rob = env.robot.clone()
+    env.update_score(torch.tensor([1, -1, 0, 1, 0, -1], dtype=torch.int8, device=env.device))
+    assert env.scores.tolist() == [[1, 0], [0, 1], [0, 0], [1, 0], [0, 0], [0, 1]]
+    hit = torch.tensor([1, 1, 0, 1, 0, 1], dtype=torch.bool, device=env.device)
+    assert (env.puck[hit, 0:2] == torch.tensor([450.0, 240.0], device=env.device, dtype=torch.float64)).all()
+    assert (env.puck[hit, 2:4].abs() <= 10).all() and (env.puck[~hit, 2] == -3).all()
+    assert (env.robot[hit, 2:4] == 0).all() and torch.equal(env.robot[:, 0:2], rob[:, 0:2])   # positions kept
+    assert (env.robot[~hit, 2:4] == 3).all()
+    assert env.reset_count.tolist() == [1, 1, 0, 1, 0, 1]
+    env.reset(total=True)
+    assert env.scores.sum().item() == 0 and env.reset_count.tolist() == [2, 2, 1, 2, 1, 2]
+    # Philox draws equal the oracle's restatement
+    from oracle import oracle
+    want = oracle.rng_reset_pair(5, 0, 1)
+    assert env.puck[0, 2:4].tolist() == want.tolist()
+
+
+def test_bad_shapes_are_rejected():
+    env = make_env(16)
+    with pytest.raises(ValueError):
+        env.step(torch.zeros(3, 16, dtype=torch.int8, device=env.device), K=8)
+    with pytest.raises(ValueError):
+        env.step(torch.zeros(8, 16, dtype=torch.int8), K=8)          # CPU tensor
+    with pytest.raises(ValueError):
+        env.get_state(out=torch.zeros(16, 8, dtype=torch.float64, device=env.device))
+
+
+# ---------------------------------------------------------------- invariances (bit-exact, both builds)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_k_fusion_invariance(dtype):
+    """K fused frames in one launch == K launches of one frame."""
+    n, K = 4096, 8
+    a = make_env(n, dtype, seed=11)
+    b = make_env(n, dtype, seed=11)
+    for e in (a, b):
+        e.step(None, K=200, out=e.make_outputs(200, ()))          # decorrelate
+    acts = torch.randint(0, 4, (K, n), dtype=torch.int8, device=a.device)
+    oa = a.step(acts, K=K, out=a.make_outputs(K, ("reward", "done", "score", "game_over", "obs_next"), True))
+    rs = []
+    for k in range(K):
+        ob = b.step(acts[k], K=1, out=b.make_outputs(1, ("reward", "done", "score", "game_over", "obs_next"), True))
+        rs.append(ob)
+    assert same(snapshot(a), snapshot(b))
+    for f in ("reward", "done", "score", "game_over", "obs_next"):
+        assert torch.equal(getattr(oa, f), torch.cat([getattr(o, f) for o in rs]))
+    assert a.stats() == b.stats()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_sharding_invariance(dtype):
+    """Results are keyed on the GLOBAL env id: one env of N == two shards of N/2 with env_id0 offsets."""
+    n = 2048
+    full = make_env(n, dtype, seed=21)
+    lo = make_env(n // 2, dtype, seed=21, env_id0=0)
+    hi = make_env(n // 2, dtype, seed=21, env_id0=n // 2)
+    for e in (full, lo, hi):
+        for _ in range(6):
+            e.step(None, K=64, out=e.make_outputs(64, ()))
+    for name in ("puck", "robot", "opponent", "prev_dist", "meta"):
+        assert torch.equal(getattr(full, name), torch.cat([getattr(lo, name), getattr(hi, name)]))
+    sf, sl, sh = full.stats(), lo.stats(), hi.stats()
+    assert all(sf[k] == sl[k] + sh[k] for k in sf)
+    assert sf["robot_goals"] + sf["opponent_goals"] > 100
+
+
+def test_checkpoint_resume_is_exact():
+    n = 1024
+    a = make_env(n, seed=3)
+    a.step(None, K=100, out=a.make_outputs(100, ()))
+    sd = a.state_dict()
+    a.step(None, K=100, out=a.make_outputs(100, ()))
+    b = make_env(n, seed=3)
+    b.load_state_dict(sd)
+    b.step(None, K=100, out=b.make_outputs(100, ()))
+    assert same(snapshot(a), snapshot(b))
+
+
+def test_repeat_action_equals_tiled_actions():
+    n, K = 512, 4
+    a, b = make_env(n, seed=9), make_env(n, seed=9)
+    act = torch.randint(0, 4, (n,), dtype=torch.int8, device=a.device)
+    a.step(act, K=K, repeat=True)
+    b.step(act[None].repeat(K, 1).contiguous(), K=K)
+    assert same(snapshot(a), snapshot(b))
+
+
+def test_friction_flag_changes_trajectories_only_when_enabled():
+    a, b, c = make_env(64, seed=1), make_env(64, seed=1), make_env(64, seed=1, friction=True)
+    for e in (a, b, c):
+        e.step(None, K=50)
+    assert same(snapshot(a), snapshot(b)) and not same(snapshot(a), snapshot(c))
+
+
+# ---------------------------------------------------------------- fused ring buffer (lib/buffer.py)
+def test_ring_append_matches_step_outputs_and_wraps():
+    from air_hockey_training_environment_b200 import ReplayRing
+    n, cap = 256, 6
+    env = make_env(n, seed=4)
+    ring = ReplayRing(cap, n, env.dtype, env.device)
+    assert len(ring) == 0
+    hist = []
+    for _ in range(4):                                   # 4 launches x 2 frames = 8 appends into 6 slots
+        acts = torch.randint(0, 4, (2, n), dtype=torch.int8, device=env.device)
+        out = env.step(acts, K=2, out=env.make_outputs(2, ("obs_state", "obs_new_state", "reward", "done")), ring=ring)
+        for k in range(2):
+            hist.append((out.obs_state[k].clone(), acts[k].clone(), out.reward[k].clone(), out.done[k].clone(),
+                         out.obs_new_state[k].clone()))
+    assert len(ring) == cap and ring.appended == 8 and env.counters()["ring_appended"] == 8
+    got = ring.retreive()                                # newest first, like MemoryBuffer.retreive()
+    for j in range(cap):
+        s, a, r, d, s2 = hist[-1 - j]
+        assert torch.equal(got["state"][j], s) and torch.equal(got["new_state"][j], s2)
+        assert torch.equal(got["action"][j], a) and torch.equal(got["reward"][j], r) and torch.equal(got["done"][j], d)
+    batch = ring.sample(100)
+    assert batch["state"].shape == (100, 8) and batch["action"].shape == (100,)
+    with pytest.raises(ValueError):
+        ring.sample(cap * n + 1)                         # random.sample raises ValueError too
+    ring.purge()
+    assert len(ring) == 0
+
+
+# ---------------------------------------------------------------- CUDA graph capture
+def test_step_is_graph_capturable_and_counters_advance_on_device():
+    n, K = 8192, 8
+    a, b = make_env(n, seed=13), make_env(n, seed=13)
+    out = a.make_outputs(K, ("reward",))
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        a.step(None, K=K, out=out)                       # warm-up on the side stream
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        a.step(None, K=K, out=out)
+    for _ in range(5):
+        g.replay()
+    for _ in range(6):
+        b.step(None, K=K)
+    torch.cuda.synchronize()
+    assert same(snapshot(a), snapshot(b))                # Philox frame counter advanced inside the graph
+    assert a.counters()["frame"] == 6 * K
+
+
+# ---------------------------------------------------------------- properties at BASELINE's full size
+def test_full_size_properties_1m_envs_fp32_k8():
+    n, K = 1 << 20, 8
+    env = make_env(n, seed=1234)
+    twin = make_env(n, seed=1234)
+    out = env.make_outputs(K, ("reward", "done", "score", "game_over", "obs_next"))
+    tot = {"robot_goals": 0, "opponent_goals": 0, "dones": 0, "reward_sum": 0, "games": 0}
+    for it in range(40):
+        env.step(None, K=K, out=out)
+        twin.step(None, K=K, out=twin.make_outputs(K, ()))
+        tot["robot_goals"] += int((out.score > 0).sum()); tot["opponent_goals"] += int((out.score < 0).sum())
+        tot["dones"] += int(out.done.sum()); tot["reward_sum"] += int(out.reward.sum().item())
+        tot["games"] += int((out.game_over != 0).sum())
+    st = env.stats()
+    assert st["frames"] == 40 * K * n and st["nonfinite"] == 0
+    for k, v in tot.items():                             # checksum of checksums: device tallies == output sums
+        assert st[k] == v, (k, st[k], v)
+    assert same(snapshot(env), snapshot(twin))           # determinism, independent of which outputs are written
+    # table / limit invariants after any frame
+    assert env.robot[:, 0].min() >= 20 and env.robot[:, 0].max() <= 430
+    assert env.opponent[:, 0].min() >= 470 and env.opponent[:, 0].max() <= 880
+    for m in (env.robot, env.opponent):
+        assert m[:, 1].min() >= 20 and m[:, 1].max() <= 460
+    assert env.puck[:, 2:4].abs().max() <= 10            # speed clamp precedes every advance
+    assert env.puck[:, 0].min() >= 15 - 10 and env.puck[:, 0].max() <= 885 + 10
+    assert env.scores.min() >= 0 and env.scores.max() <= 9
+    assert set(torch.unique(out.reward).tolist()) <= {-4.0, -2.0, 0.0, 2.0, 4.0, 6.0}
+    o = out.obs_next
+    assert torch.equal(o[:, 0:4], o[:, 0:4].trunc())     # positions are int()-truncated in the observation
+    rate = (st["robot_goals"] + st["opponent_goals"]) / st["frames"]
+    assert 0.004 < rate < 0.012                          # reference: 7.9 goals per 1,000 frames
