@@ -17,7 +17,7 @@ AH_ACT_NONE, AH_ACT_DISCRETE, AH_ACT_CONTINUOUS, AH_ACT_PHILOX, AH_ACT_DISCRETE_
 AH_NSTATS = 16
 STAT_NAMES = ("frames", "robot_goals", "opponent_goals", "robot_wins", "opponent_wins", "dones", "reward_sum",
               "reward_sq_sum", "games", "game_len_sum", "game_len_sq_sum", "game_return_sum", "nonfinite",
-              "reset_table_overflow", "reserved14", "reserved15")
+              "reset_table_overflow", "contacts_robot", "contacts_opponent")
 
 # every symbol include/ah_b200.h declares (tests/test_capi_symbols.py checks header <-> library <-> this list)
 SYMBOLS = ("ah_strerror", "ah_abi_version", "ah_last_cuda_error", "ah_create", "ah_destroy", "ah_bind_state",

@@ -126,6 +126,7 @@ struct StepArgs {
 
 struct Tally {   // per-thread event counters of one launch
     int frames, robot_goals, opp_goals, robot_wins, opp_wins, dones, reward_sum, reward_sq, games, nonfinite;
+    int c_robot, c_opp;
     long long len_sum, len_sq, ret_sum;
 };
 
@@ -169,11 +170,11 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const StepArgs<R> a) {
             }
             // ---- robot.move(a): sub-update #1                      game.py:136 -> agent.py:32-36
             move_robot<R>(e, ACT == 2, ia, ax, ay);
-            physics_tail<R>(e, dot_fma, friction);
+            physics_tail<R>(e, dot_fma, friction, t.c_robot, t.c_opp);
             const Obs<R> s0 = get_state<R>(e, true);                // Observation.state      agent.py:61
             // ---- robot.step(a) -> self.move(a): sub-update #2      agent.py:64
             move_robot<R>(e, ACT == 2, ia, ax, ay);
-            physics_tail<R>(e, dot_fma, friction);
+            physics_tail<R>(e, dot_fma, friction, t.c_robot, t.c_opp);
             const Obs<R> s1 = get_state<R>(e, true);                // Observation.new_state  agent.py:67
             // ---- Rewards                                           agent.py:70-71
             int rw, sc; bool dn;
@@ -190,7 +191,7 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const StepArgs<R> a) {
             if (e.opp_score == 10) go = 2;
             // ---- env.update_state(agent_name="computer"): sub-update #3   game.py:166
             computer_ai<R>(e);
-            physics_tail<R>(e, dot_fma, friction);
+            physics_tail<R>(e, dot_fma, friction, t.c_robot, t.c_opp);
             // ---- 10-goal game over                                 game.py:169-177
             if (go != 0) {
                 t.games += 1; t.robot_wins += (go == 1); t.opp_wins += (go == 2);
@@ -225,20 +226,21 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const StepArgs<R> a) {
     }
 
     // ---- statistics: warp shuffle reduction, then one atomic set per block
-    __shared__ long long red[kThreads / 32][14];
+    __shared__ long long red[kThreads / 32][AH_NSTATS];
     if (a.collect_stats) {
-        long long v[14] = {t.frames, t.robot_goals, t.opp_goals, t.robot_wins, t.opp_wins, t.dones, t.reward_sum,
-                           t.reward_sq, t.games, t.len_sum, t.len_sq, t.ret_sum, t.nonfinite, (long long)overflow};
+        long long v[AH_NSTATS] = {t.frames, t.robot_goals, t.opp_goals, t.robot_wins, t.opp_wins, t.dones, t.reward_sum,
+                                  t.reward_sq, t.games, t.len_sum, t.len_sq, t.ret_sum, t.nonfinite, (long long)overflow,
+                                  t.c_robot, t.c_opp};
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-        for (int q = 0; q < 14; ++q) {
+        for (int q = 0; q < AH_NSTATS; ++q) {
             // events are rare: skip the shuffle tree when no lane of the warp has anything to add
             const bool any = __any_sync(0xffffffffu, v[q] != 0);
             const long long s = any ? warp_sum(v[q]) : 0;
             if (lane == 0) red[warp][q] = s;
         }
         __syncthreads();
-        if (threadIdx.x < 14) {
+        if (threadIdx.x < AH_NSTATS) {
             long long s = 0;
 #pragma unroll
             for (int w = 0; w < kThreads / 32; ++w) s += red[w][threadIdx.x];
@@ -286,7 +288,7 @@ __global__ void reset_kernel(StatePtrs<R> st, int64_t n, int total, const uint8_
     env_reset<R>(e, total != 0, rs, i, overflow);
     if (total) { e.game_frames = 0; e.game_return = 0; }
     store_env<R>(st, i, e);
-    if (overflow) atomicAdd(&blk->stats[13], 1ull);
+    if (overflow) atomicAdd(&blk->stats[AH_STAT_RESET_TABLE_OVERFLOW], 1ull);
 }
 
 // AirHockey.update_state  airhockey.py:96-134 : one sub-update
@@ -312,7 +314,8 @@ __global__ void update_state_kernel(StatePtrs<R> st, int64_t n, const void* acti
     } else {                                                         // :106-107
         computer_ai<R>(e);
     }
-    physics_tail<R>(e, dot_fma != 0, friction != 0);
+    int c0 = 0, c1 = 0;
+    physics_tail<R>(e, dot_fma != 0, friction != 0, c0, c1);
     store_env<R>(st, i, e);
 }
 
@@ -336,7 +339,7 @@ __global__ void update_score_kernel(StatePtrs<R> st, int64_t n, const int8_t* sc
     if (sc > 0) e.robot_score += 1; else e.opp_score += 1;
     env_reset<R>(e, false, rs, i, overflow);
     store_env<R>(st, i, e);
-    if (overflow) atomicAdd(&blk->stats[13], 1ull);
+    if (overflow) atomicAdd(&blk->stats[AH_STAT_RESET_TABLE_OVERFLOW], 1ull);
 }
 
 // Rewards.__call__  lib/rewards.py:118-142

@@ -109,12 +109,14 @@ __device__ __forceinline__ void move_robot(Env<R>& e, bool continuous, int ia, R
 
 // ---- AirHockey.collision  environment/airhockey.py:189-268 (correction=True) ----
 template <typename R>
-__device__ __forceinline__ bool collision(R& px, R& py, R& pdx, R& pdy, R& mx, R& my, R& mdx, R& mdy, bool dot_fma) {
+__device__ __forceinline__ bool collision(R& px, R& py, R& pdx, R& pdy, R& mx, R& my, R& mdx, R& mdy, bool dot_fma,
+                                          int& contacts) {
     using M = Math<R>;
     const R d_x = mx - px;                                         // :198
     const R d_y = my - py;                                         // :199
     const R dist_sq = M::dot2(d_x, d_y, d_x, d_y, dot_fma);        // :203
     if (dist_sq > K<R>::radius_sq) return false;                   // :210 (touching counts as contact)
+    contacts += 1;
     R n_x, n_y;
     if (M::exact) {
         const R distance = M::sqrt_(dist_sq);                      // :214
@@ -202,9 +204,9 @@ __device__ __forceinline__ void computer_ai(Env<R>& e) {
 
 // ---- the common tail of AirHockey.update_state  environment/airhockey.py:112-122 ----
 template <typename R>
-__device__ __forceinline__ void physics_tail(Env<R>& e, bool dot_fma, bool friction) {
-    collision<R>(e.px, e.py, e.pdx, e.pdy, e.rx, e.ry, e.rdx, e.rdy, dot_fma);   // :113-114 robot first
-    collision<R>(e.px, e.py, e.pdx, e.pdy, e.ox, e.oy, e.odx, e.ody, dot_fma);
+__device__ __forceinline__ void physics_tail(Env<R>& e, bool dot_fma, bool friction, int& c_robot, int& c_opp) {
+    collision<R>(e.px, e.py, e.pdx, e.pdy, e.rx, e.ry, e.rdx, e.rdy, dot_fma, c_robot);   // :113-114 robot first
+    collision<R>(e.px, e.py, e.pdx, e.pdy, e.ox, e.oy, e.odx, e.ody, dot_fma, c_opp);
     if (friction) friction_on_puck<R>(e.pdx, e.pdy);
     limit_puck_speed<R>(e.pdx, e.pdy);                                           // :117
     puck_update<R>(e.px, e.py, e.pdx, e.pdy);                                    // :118

@@ -86,6 +86,9 @@ enum {
     AH_STAT_GAME_LEN_SQ_SUM = 10,
     AH_STAT_GAME_RETURN_SUM = 11, /* reward summed over the finished games */
     AH_STAT_NONFINITE = 12,       /* envs whose puck state was non-finite at the end of a launch */
+    AH_STAT_RESET_TABLE_OVERFLOW = 13, /* resets that found their reset table exhausted (velocity set to 0) */
+    AH_STAT_CONTACTS_ROBOT = 14,  /* AirHockey.collision() returned True, robot mallet (airhockey.py:189-268) */
+    AH_STAT_CONTACTS_OPPONENT = 15,
     AH_NSTATS = 16
 };
 

@@ -155,7 +155,7 @@ static void move_robot(env_t* e, int kind, int ia, double ax, double ay) {
 }
 
 /* ------------------------------------------------------------------ environment/airhockey.py:189-268 */
-static int collision(body_t* puck, body_t* mallet, int dot_fma) {
+static int collision(body_t* puck, body_t* mallet, int dot_fma, double* dmin) {
     double d_x = mallet->x - puck->x;                       /* :198 */
     double d_y = mallet->y - puck->y;                       /* :199 */
     double distance_squared = dot2(d_x, d_y, d_x, d_y, dot_fma);   /* :203 */
@@ -163,6 +163,7 @@ static int collision(body_t* puck, body_t* mallet, int dot_fma) {
     const double radius_squared = radius * radius;          /* :207 */
     if (distance_squared > radius_squared) return 0;        /* :210 */
     double distance = sqrt(distance_squared);               /* :214 */
+    if (dmin && distance < *dmin) *dmin = distance;         /* test diagnostics only */
     double n_x, n_y;
     if (distance > 0) { n_x = d_x / distance; n_y = d_y / distance; }   /* :217 */
     else { n_x = d_x; n_y = d_y; }
@@ -237,7 +238,8 @@ static void computer_ai(env_t* e) {
 
 /* ------------------------------------------------------------------ environment/airhockey.py:96-134 */
 /* agent: 0 robot, 1 human, 2 computer.  Returns 0, or -1 for an unknown agent (InvalidAgentError, :108-110). */
-static int update_state(env_t* e, int agent, int kind, int ia, double ax, double ay, int dot_fma, int friction) {
+static int update_state_c(env_t* e, int agent, int kind, int ia, double ax, double ay, int dot_fma, int friction,
+                          int* contacts, double* dmin) {
     double lx, ly;
     if (agent == 0) move_robot(e, kind, ia, ax, ay);                               /* :100-101 */
     else if (agent == 1) {                                                         /* :102-105 */
@@ -245,14 +247,19 @@ static int update_state(env_t* e, int agent, int kind, int ia, double ax, double
         mallet_update(&e->opp, OPP_LEFT, OPP_RIGHT, &lx, &ly);
     } else if (agent == 2) computer_ai(e);                                         /* :106-107 */
     else return -1;
-    collision(&e->puck, &e->robot, dot_fma);                                       /* :113-114, robot first */
-    collision(&e->puck, &e->opp, dot_fma);
+    int c0 = collision(&e->puck, &e->robot, dot_fma, dmin);                        /* :113-114, robot first */
+    int c1 = collision(&e->puck, &e->opp, dot_fma, dmin);
+    if (contacts) { contacts[0] += c0; contacts[1] += c1; }
     if (friction) friction_on_puck(&e->puck);   /* not in the reference's live path; off by default */
     limit_puck_speed(&e->puck);                                                    /* :117 */
     puck_update(&e->puck);                                                         /* :118 */
     mallet_update(&e->robot, ROBOT_LEFT, ROBOT_RIGHT, &lx, &ly);                   /* :121-122 */
     mallet_update(&e->opp, OPP_LEFT, OPP_RIGHT, &lx, &ly);
     return 0;
+}
+
+static int update_state(env_t* e, int agent, int kind, int ia, double ax, double ay, int dot_fma, int friction) {
+    return update_state_c(e, agent, kind, ia, ax, ay, dot_fma, friction, NULL, NULL);
 }
 
 /* ------------------------------------------------------------------ airhockey.py:136-147 + puck.py:120-133 + mallet.py:86-99 */
@@ -378,6 +385,8 @@ typedef struct {
     double* states_rec;     /* [T/record_every][n][13] */
     int32_t* scores_rec;    /* [T/record_every][n][2] */
     int64_t* stats;         /* [16] summed over all envs and frames, see AH_STAT_* in include/ah_b200.h */
+    uint8_t* contacts;      /* [T][n]  test diagnostics: collision() == True count in the frame (0..6) */
+    double* contact_dmin;   /* [T][n]  test diagnostics: smallest centre distance among them (inf if none) */
 } orc_outputs_t;
 
 /*
@@ -413,9 +422,10 @@ int orc_frames(int64_t n, int T, double* state13, int32_t* scores2,
             if (actions_i8) ia = actions_i8[o];
             else if (actions_f64) { kind = 1; ax = actions_f64[2 * o]; ay = actions_f64[2 * o + 1]; }
             else ia = rng_action(seed, rs.env_id, frame0 + (uint64_t)t);
-            update_state(&e, 0, kind, ia, ax, ay, dot_fma, friction);     /* robot.move(a)       game.py:136 */
+            int cts[2] = {0, 0}; double dmin = INFINITY;
+            update_state_c(&e, 0, kind, ia, ax, ay, dot_fma, friction, cts, &dmin);   /* robot.move(a)  game.py:136 */
             if (out->obs_state) get_state(&e, 1, out->obs_state + 8 * o); /* state                agent.py:61 */
-            update_state(&e, 0, kind, ia, ax, ay, dot_fma, friction);     /* self.move(a)        agent.py:64 */
+            update_state_c(&e, 0, kind, ia, ax, ay, dot_fma, friction, cts, &dmin);   /* self.move(a)   agent.py:64 */
             if (out->obs_new_state) get_state(&e, 1, out->obs_new_state + 8 * o);   /*            agent.py:67 */
             int rw, sc, dn;
             rewards_call(&e, dot_fma, &rw, &sc, &dn);                     /*                      agent.py:71 */
@@ -424,7 +434,7 @@ int orc_frames(int64_t n, int T, double* state13, int32_t* scores2,
             int go = 0;                                                   /* stats()             game.py:101-109 */
             if (e.robot_score == 10) go = 1;
             if (e.opp_score == 10) go = 2;
-            update_state(&e, 2, 0, -1, 0, 0, dot_fma, friction);          /* computer            game.py:166 */
+            update_state_c(&e, 2, 0, -1, 0, 0, dot_fma, friction, cts, &dmin);        /* computer       game.py:166 */
             if (e.opp_score == 10) env_reset(&e, 1, &rs);                 /*                     game.py:169-172 */
             if (e.robot_score == 10) env_reset(&e, 1, &rs);               /*                     game.py:174-177 */
             if (out->obs_next) get_state(&e, 1, out->obs_next + 8 * o);
@@ -432,6 +442,10 @@ int orc_frames(int64_t n, int T, double* state13, int32_t* scores2,
             if (out->score) out->score[o] = (int8_t)sc;
             if (out->done) out->done[o] = (uint8_t)dn;
             if (out->game_over) out->game_over[o] = (uint8_t)go;
+            if (out->contacts) out->contacts[o] = (uint8_t)(cts[0] + cts[1]);
+            if (out->contact_dmin) out->contact_dmin[o] = dmin;
+            stats_acc[14] += cts[0];           /* collision() true, robot mallet */
+            stats_acc[15] += cts[1];           /* collision() true, opponent mallet */
             stats_acc[0] += 1;                 /* frames */
             stats_acc[1] += (sc > 0);          /* robot goals */
             stats_acc[2] += (sc < 0);          /* opponent goals */

@@ -19,13 +19,14 @@ _lib = None
 DOT_FMA_DEFAULT = 1
 
 STAT_NAMES = ("frames", "robot_goals", "opponent_goals", "robot_wins", "opponent_wins", "dones",
-              "reward_sum", "reward_sq_sum")
+              "reward_sum", "reward_sq_sum", "_8", "_9", "_10", "_11", "_12", "_13", "contacts_robot", "contacts_opponent")
 
 
 class _Outputs(C.Structure):
     _fields_ = [("obs_state", C.c_void_p), ("obs_new_state", C.c_void_p), ("obs_next", C.c_void_p),
                 ("reward", C.c_void_p), ("score", C.c_void_p), ("done", C.c_void_p), ("game_over", C.c_void_p),
-                ("states_rec", C.c_void_p), ("scores_rec", C.c_void_p), ("stats", C.c_void_p)]
+                ("states_rec", C.c_void_p), ("scores_rec", C.c_void_p), ("stats", C.c_void_p),
+                ("contacts", C.c_void_p), ("contact_dmin", C.c_void_p)]
 
 
 def lib() -> C.CDLL:
@@ -109,7 +110,8 @@ def run_frames(state: np.ndarray, scores: np.ndarray, T: int, *,
     out: Dict[str, np.ndarray] = {}
     shapes = {"obs_state": ((T, n, 8), np.float64), "obs_new_state": ((T, n, 8), np.float64),
               "obs_next": ((T, n, 8), np.float64), "reward": ((T, n), np.int32), "score": ((T, n), np.int8),
-              "done": ((T, n), np.uint8), "game_over": ((T, n), np.uint8)}
+              "done": ((T, n), np.uint8), "game_over": ((T, n), np.uint8),
+              "contacts": ((T, n), np.uint8), "contact_dmin": ((T, n), np.float64)}
     for k in want:
         out[k] = np.zeros(*shapes[k])
     if record_every:

@@ -58,6 +58,7 @@ def test_mallet_limits(dtype):
     env.robot[:, 0:2] = torch.tensor([[-1.0, -1.0], [1000.0, 1000.0]], dtype=dtype)
     env.update_state(agent_name="computer")      # tail of update_state runs Mallet.update on both mallets
     assert env.robot[:, 0:2].tolist() == [[20, 20], [430, 460]]
+    env.opponent[:, 2:4] = 0                     # computerAI left a velocity behind; the tail advances by it
     env.update_state(torch.tensor([[-1.0, -1.0], [1000.0, 1000.0]], dtype=dtype, device=env.device), "human")
     assert env.opponent[:, 0:2].tolist() == [[470, 20], [880, 460]]
 
@@ -74,9 +75,9 @@ def test_reward_predicates(dtype):
     env.puck[:, 0:2] = P.to(env.device)
     reward, score, done = env.rewards()
     assert done.tolist() == [1, 0, 0, 0, 0, 0, 0, 0]
-    assert score.tolist() == [0, 0, 0, 0, 0, 0, -1, 1]
+    assert score.tolist() == [0, 0, -1, 0, 1, 0, -1, 1]          # y = 300 is inside the goal mouth (|240 - y| < 95)
     # reward = (3 | -1) + wall(-2 | +2 | 0) + (+1: closer than prev (inf))
-    assert reward.tolist() == [4, 0, -2, 0, 2, 0, -2, 2]
+    assert reward.tolist() == [4, 0, -2, 0, 2, 0, -2, 0]         # x = 900 is 18 px from right_wall = 882: no wall term
     assert not torch.isinf(env.prev_dist).any()
     # goal test fails away from the mouth: (10, 30) and (900, 30)   (tests/test_goal.py:25,39)
     env.puck[0:2, 0:2] = torch.tensor([[10, 30], [900, 30]], dtype=dtype).to(env.device)
