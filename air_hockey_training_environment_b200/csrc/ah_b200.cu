@@ -124,126 +124,171 @@ struct StepArgs {
     DevBlock* blk;
 };
 
-struct Tally {   // per-thread event counters of one launch
-    int frames, robot_goals, opp_goals, robot_wins, opp_wins, dones, reward_sum, reward_sq, games, nonfinite;
-    int c_robot, c_opp;
-    long long len_sum, len_sq, ret_sum;
+// Block-level statistics: rare events (goals, wins, contacts ...) are counted with shared-memory atomics right
+// where they happen (they cost nothing on the common path and hold no registers); the two per-frame sums
+// (reward, reward^2) live in registers and are REDUX/shuffle-reduced per warp at the end of the launch.
+struct BlockStats {
+    int v[AH_NSTATS];                 // 32-bit: native shared-memory atomic add (a 64-bit one is a CAS loop)
+    unsigned long long len_sq;        // the only sum that can outgrow 32 bits within one block and launch
 };
 
-__device__ __forceinline__ long long warp_sum(long long v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
+__device__ __forceinline__ void stat_add(BlockStats& bs, int which, int x) { atomicAdd(&bs.v[which], x); }
 
 constexpr int kThreads = 256;
 
-template <typename R, int ACT>   // ACT: 1 discrete, 2 continuous, 3 philox
-__global__ void __launch_bounds__(kThreads) step_kernel(const StepArgs<R> a) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+template <typename R> struct Occ { static constexpr int blocks = 4; };
+template <> struct Occ<double> { static constexpr int blocks = 2; };
+
+// Output modes (compile-time, chosen by the host from which pointers were given):
+//   MODE_LEAN     reward, done, score, game_over [K][n] and obs_next [n][8] are ALL present; no per-frame
+//                 observations, no ring, no friction -> no pointer tests inside the frame loop (rollout mode)
+//   MODE_SIM      no per-frame output at all (obs_next [n][8] optional): pure simulation
+//   MODE_GENERIC  every output nullable, per-frame observations, fused ring append, friction flag
+enum { MODE_LEAN = 0, MODE_SIM = 1, MODE_GENERIC = 2 };
+
+template <typename R, int ACT, int MODE>   // ACT: 1 discrete, 2 continuous, 3 philox
+__global__ void __launch_bounds__(kThreads, Occ<R>::blocks) step_kernel(const StepArgs<R> a) {
+    using V2 = typename std::conditional<sizeof(R) == 4, float2, double2>::type;
+    __shared__ BlockStats bs;
+    if (threadIdx.x < AH_NSTATS) bs.v[threadIdx.x] = 0;
+    if (threadIdx.x == 0) bs.len_sq = 0ull;
+    __syncthreads();
+
+    const uint32_t n = (uint32_t)a.n;                         // n < 2^31 (checked by ah_create)
+    const uint32_t stride = gridDim.x * blockDim.x;
     const unsigned long long frame0 = a.blk->frame;
     const unsigned long long ring0 = a.blk->ring_appended;
     const bool repeat = (a.action_kind == AH_ACT_DISCRETE_REPEAT) || (a.action_kind == AH_ACT_CONTINUOUS_REPEAT);
-    const bool dot_fma = a.dot_fma != 0, friction = a.friction != 0;
-    Tally t = {};
-    unsigned overflow = 0;
+    const bool dot_fma = a.dot_fma != 0;
+    const bool friction = (MODE == MODE_GENERIC) && (a.friction != 0);
+    const bool want_obs = (MODE == MODE_GENERIC) && (a.obs_state || a.obs_new_state || a.ring_capacity > 0);
+    const int K = a.K;
+    const size_t act_step = repeat ? 0 : (size_t)n;           // elements between frame k and k+1 of the action tensor
+    int reward_sum = 0, reward_sq = 0, frames = 0;
 
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         Env<R> e = load_env<R>(a.st, i);
+        // 10-goal flag carried into the frame (only reachable through injected state; see game.py:169-177)
+        int go = (e.robot_score == 10) ? 1 : ((e.opp_score == 10) ? 2 : 0);
+        int contacts_r = 0, contacts_o = 0;
+        unsigned overflow = 0;
         Philox4 ablock = {};
         uint32_t ablock_id = 0xffffffffu;
-        for (int k = 0; k < a.K; ++k) {
-            const int64_t row = (int64_t)k * a.n + i;
+        // warp-uniform per-frame base pointers (advanced by n per frame); the thread adds its 32-bit env index
+        const int8_t* act_i8 = reinterpret_cast<const int8_t*>(a.actions);
+        const V2* act_v2 = reinterpret_cast<const V2*>(a.actions);
+        R* reward_k = a.reward; uint8_t* done_k = a.done; int8_t* score_k = a.score; uint8_t* over_k = a.game_over;
+        // software-pipelined action fetch: frame k+1's action is requested before frame k is computed
+        int ia_next = -1; V2 av_next = {};
+        if (ACT == 1) ia_next = act_i8[i];
+        if (ACT == 2) av_next = act_v2[i];
+        for (int k = 0; k < K; ++k) {
             // ---- the robot's action for this frame
             int ia = -1; R ax = R(0), ay = R(0);
             if (ACT == 1) {
-                ia = reinterpret_cast<const int8_t*>(a.actions)[repeat ? i : row];
+                ia = ia_next;
+                act_i8 += act_step;
+                if (k + 1 < K) ia_next = act_i8[i];
+                action_nudge<R>(ia, ax, ay);
             } else if (ACT == 2) {
-                using V2 = typename std::conditional<sizeof(R) == 4, float2, double2>::type;
-                const V2 v = reinterpret_cast<const V2*>(a.actions)[repeat ? i : row];
-                ax = v.x; ay = v.y;
+                ax = av_next.x; ay = av_next.y;
+                act_v2 += act_step;
+                if (k + 1 < K) av_next = act_v2[i];
             } else {
                 const unsigned long long f = frame0 + (unsigned long long)k;
                 const uint32_t bid = (uint32_t)(f >> 6);
                 if (bid != ablock_id) { ablock = action_block(a.rs.seed, a.rs.env_id0 + (uint64_t)i, bid); ablock_id = bid; }
                 ia = action_from_block(ablock, (uint32_t)(f & 63u));
+                action_nudge<R>(ia, ax, ay);
             }
             // ---- robot.move(a): sub-update #1                      game.py:136 -> agent.py:32-36
-            move_robot<R>(e, ACT == 2, ia, ax, ay);
-            physics_tail<R>(e, dot_fma, friction, t.c_robot, t.c_opp);
-            const Obs<R> s0 = get_state<R>(e, true);                // Observation.state      agent.py:61
+            move_robot<R>(e, ACT == 2, ax, ay);
+            physics_tail<R>(e, dot_fma, friction, contacts_r, contacts_o);
+            Obs<R> s0, s1;
+            if (MODE == MODE_GENERIC && want_obs) s0 = get_state<R>(e, true);   // Observation.state      agent.py:61
             // ---- robot.step(a) -> self.move(a): sub-update #2      agent.py:64
-            move_robot<R>(e, ACT == 2, ia, ax, ay);
-            physics_tail<R>(e, dot_fma, friction, t.c_robot, t.c_opp);
-            const Obs<R> s1 = get_state<R>(e, true);                // Observation.new_state  agent.py:67
+            move_robot<R>(e, ACT == 2, ax, ay);
+            physics_tail<R>(e, dot_fma, friction, contacts_r, contacts_o);
+            if (MODE == MODE_GENERIC && want_obs) s1 = get_state<R>(e, true);   // Observation.new_state  agent.py:67
             // ---- Rewards                                           agent.py:70-71
             int rw, sc; bool dn;
             rewards_call<R>(e, dot_fma, rw, sc, dn);
             e.game_frames += 1; e.game_return += rw;
+            reward_sum += rw; reward_sq += rw * rw;
             // ---- env.update_score(score)                           game.py:142 -> airhockey.py:149-169
             if (sc != 0) {
-                if (sc > 0) { e.robot_score += 1; t.robot_goals += 1; } else { e.opp_score += 1; t.opp_goals += 1; }
+                if (sc > 0) { e.robot_score += 1; stat_add(bs, AH_STAT_ROBOT_GOALS, 1); }
+                else { e.opp_score += 1; stat_add(bs, AH_STAT_OPPONENT_GOALS, 1); }
                 env_reset<R>(e, false, a.rs, i, overflow);
+                // stats(): win flags are read BEFORE the opponent moves and before the total reset (game.py:101-109)
+                go = (e.robot_score == 10) ? 1 : go;
+                go = (e.opp_score == 10) ? 2 : go;
             }
-            // ---- stats(): win flags are read BEFORE the opponent moves and before the total reset (game.py:101-109)
-            int go = 0;
-            if (e.robot_score == 10) go = 1;
-            if (e.opp_score == 10) go = 2;
+            if (dn) stat_add(bs, AH_STAT_DONES, 1);
             // ---- env.update_state(agent_name="computer"): sub-update #3   game.py:166
             computer_ai<R>(e);
-            physics_tail<R>(e, dot_fma, friction, t.c_robot, t.c_opp);
+            physics_tail<R>(e, dot_fma, friction, contacts_r, contacts_o);
+            // ---- outputs, straight into the caller's tensors
+            if (MODE == MODE_LEAN) {
+                reward_k[i] = (R)rw; done_k[i] = dn ? 1 : 0; score_k[i] = (int8_t)sc; over_k[i] = (uint8_t)go;
+                reward_k += n; done_k += n; score_k += n; over_k += n;
+            } else if (MODE == MODE_GENERIC) {
+                const int64_t row = (int64_t)k * n + i;
+                if (a.reward) a.reward[row] = (R)rw;
+                if (a.done) a.done[row] = dn ? 1 : 0;
+                if (a.score) a.score[row] = (int8_t)sc;
+                if (a.game_over) a.game_over[row] = (uint8_t)go;
+                if (a.obs_state) store_obs<R>(a.obs_state, row, s0);
+                if (a.obs_new_state) store_obs<R>(a.obs_new_state, row, s1);
+                if (a.ring_capacity > 0) {      // fused MemoryBuffer.append(Observation(...))   lib/buffer.py:24-32
+                    const int64_t slot = (int64_t)((ring0 + (unsigned long long)k) % (unsigned long long)a.ring_capacity);
+                    const int64_t rrow = slot * n + i;
+                    store_obs<R>(a.ring_state, rrow, s0);
+                    store_obs<R>(a.ring_new_state, rrow, s1);
+                    if (ACT == 2) reinterpret_cast<V2*>(a.ring_action)[rrow] = V2{ax, ay};
+                    else reinterpret_cast<int8_t*>(a.ring_action)[rrow] = (int8_t)ia;
+                    a.ring_reward[rrow] = (R)rw;
+                    a.ring_done[rrow] = dn ? 1 : 0;
+                }
+            }
             // ---- 10-goal game over                                 game.py:169-177
             if (go != 0) {
-                t.games += 1; t.robot_wins += (go == 1); t.opp_wins += (go == 2);
-                t.len_sum += e.game_frames; t.len_sq += (long long)e.game_frames * e.game_frames;
-                t.ret_sum += e.game_return;
+                stat_add(bs, AH_STAT_GAMES, 1);
+                stat_add(bs, go == 1 ? AH_STAT_ROBOT_WINS : AH_STAT_OPPONENT_WINS, 1);
+                stat_add(bs, AH_STAT_GAME_LEN_SUM, e.game_frames);
+                atomicAdd(&bs.len_sq, (unsigned long long)e.game_frames * (unsigned long long)e.game_frames);
+                stat_add(bs, AH_STAT_GAME_RETURN_SUM, e.game_return);
                 e.game_frames = 0; e.game_return = 0;
                 env_reset<R>(e, true, a.rs, i, overflow);
+                go = 0;
             }
-            t.frames += 1; t.dones += dn ? 1 : 0; t.reward_sum += rw; t.reward_sq += rw * rw;
-            // ---- outputs, straight into the caller's tensors
-            if (a.obs_state) store_obs<R>(a.obs_state, row, s0);
-            if (a.obs_new_state) store_obs<R>(a.obs_new_state, row, s1);
-            if (a.reward) a.reward[row] = (R)rw;
-            if (a.done) a.done[row] = dn ? 1 : 0;
-            if (a.score) a.score[row] = (int8_t)sc;
-            if (a.game_over) a.game_over[row] = (uint8_t)go;
-            if (a.obs_next && (a.obs_next_per_frame || k == a.K - 1))
-                store_obs<R>(a.obs_next, a.obs_next_per_frame ? row : i, get_state<R>(e, true));
-            if (a.ring_capacity > 0) {      // fused MemoryBuffer.append(Observation(...))   lib/buffer.py:24-32
-                const int64_t slot = (int64_t)((ring0 + (unsigned long long)k) % (unsigned long long)a.ring_capacity);
-                const int64_t rrow = slot * a.n + i;
-                store_obs<R>(a.ring_state, rrow, s0);
-                store_obs<R>(a.ring_new_state, rrow, s1);
-                if (ACT == 2) { reinterpret_cast<R*>(a.ring_action)[2 * rrow] = ax; reinterpret_cast<R*>(a.ring_action)[2 * rrow + 1] = ay; }
-                else reinterpret_cast<int8_t*>(a.ring_action)[rrow] = (int8_t)ia;
-                a.ring_reward[rrow] = (R)rw;
-                a.ring_done[rrow] = dn ? 1 : 0;
-            }
+            if (MODE == MODE_GENERIC && a.obs_next && a.obs_next_per_frame)
+                store_obs<R>(a.obs_next, (int64_t)k * n + i, get_state<R>(e, true));
         }
-        if (!(isfinite((double)e.px) && isfinite((double)e.py) && isfinite((double)e.pdx) && isfinite((double)e.pdy))) t.nonfinite += 1;
+        // the next frame's policy input (agent.py:46)
+        if (a.obs_next && !(MODE == MODE_GENERIC && a.obs_next_per_frame)) store_obs<R>(a.obs_next, i, get_state<R>(e, true));
+        frames += K;
+        if (contacts_r) stat_add(bs, AH_STAT_CONTACTS_ROBOT, contacts_r);
+        if (contacts_o) stat_add(bs, AH_STAT_CONTACTS_OPPONENT, contacts_o);
+        if (overflow) stat_add(bs, AH_STAT_RESET_TABLE_OVERFLOW, (int)overflow);
+        if (!(isfinite((double)e.px) && isfinite((double)e.py) && isfinite((double)e.pdx) && isfinite((double)e.pdy)))
+            stat_add(bs, AH_STAT_NONFINITE, 1);
         store_env<R>(a.st, i, e);
     }
 
-    // ---- statistics: warp shuffle reduction, then one atomic set per block
-    __shared__ long long red[kThreads / 32][AH_NSTATS];
+    // ---- per-frame sums: warp reduction (REDUX), one shared atomic per warp; then one global atomic set per block
     if (a.collect_stats) {
-        long long v[AH_NSTATS] = {t.frames, t.robot_goals, t.opp_goals, t.robot_wins, t.opp_wins, t.dones, t.reward_sum,
-                                  t.reward_sq, t.games, t.len_sum, t.len_sq, t.ret_sum, t.nonfinite, (long long)overflow,
-                                  t.c_robot, t.c_opp};
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-        for (int q = 0; q < AH_NSTATS; ++q) {
-            // events are rare: skip the shuffle tree when no lane of the warp has anything to add
-            const bool any = __any_sync(0xffffffffu, v[q] != 0);
-            const long long s = any ? warp_sum(v[q]) : 0;
-            if (lane == 0) red[warp][q] = s;
+        const int fs = __reduce_add_sync(0xffffffffu, frames);
+        const int rs = __reduce_add_sync(0xffffffffu, reward_sum);
+        const int rq = __reduce_add_sync(0xffffffffu, reward_sq);
+        if ((threadIdx.x & 31) == 0) {
+            stat_add(bs, AH_STAT_FRAMES, fs);
+            stat_add(bs, AH_STAT_REWARD_SUM, rs);
+            stat_add(bs, AH_STAT_REWARD_SQ_SUM, rq);
         }
         __syncthreads();
         if (threadIdx.x < AH_NSTATS) {
-            long long s = 0;
-#pragma unroll
-            for (int w = 0; w < kThreads / 32; ++w) s += red[w][threadIdx.x];
+            const long long s = threadIdx.x == AH_STAT_GAME_LEN_SQ_SUM ? (long long)bs.len_sq : (long long)bs.v[threadIdx.x];
             if (s != 0) atomicAdd(&a.blk->stats[threadIdx.x], (unsigned long long)s);
         }
     }
@@ -257,8 +302,8 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const StepArgs<R> a) {
     }
     __syncthreads();
     if (is_last && threadIdx.x == 0) {
-        a.blk->frame = frame0 + (unsigned long long)a.K;
-        if (a.ring_capacity > 0) a.blk->ring_appended = ring0 + (unsigned long long)a.K;
+        a.blk->frame = frame0 + (unsigned long long)K;
+        if (a.ring_capacity > 0) a.blk->ring_appended = ring0 + (unsigned long long)K;
         a.blk->ticket = 0;
         __threadfence();
     }
@@ -302,10 +347,12 @@ __global__ void update_state_kernel(StatePtrs<R> st, int64_t n, const void* acti
     if (agent == AH_AGENT_ROBOT) {                                   // :100-101
         if (action_kind == AH_ACT_CONTINUOUS) {
             const V2 v = reinterpret_cast<const V2*>(actions)[i];
-            move_robot<R>(e, true, -1, v.x, v.y);
+            move_robot<R>(e, true, v.x, v.y);
         } else {
             const int ia = actions ? (int)reinterpret_cast<const int8_t*>(actions)[i] : -1;
-            move_robot<R>(e, false, ia, R(0), R(0));
+            R nx, ny;
+            action_nudge<R>(ia, nx, ny);
+            move_robot<R>(e, false, nx, ny);
         }
     } else if (agent == AH_AGENT_HUMAN) {                            // :102-105 teleport, then update()
         const V2 v = reinterpret_cast<const V2*>(actions)[i];
@@ -438,15 +485,26 @@ int launch_step(ah_env* env, const ah_step_io* io, int K, cudaStream_t s) {
     const int max_blocks = sizeof(R) == 4 ? env->blocks_f32 : env->blocks_f64;
     int64_t want = (env->n + ah::kThreads - 1) / ah::kThreads;
     const unsigned grid = (unsigned)(want < max_blocks ? want : max_blocks);
+    // pick the specialised variant the given pointers allow
+    const bool per_frame_any = io->reward || io->done || io->score || io->game_over;
+    const bool per_frame_all = io->reward && io->done && io->score && io->game_over;
+    const bool heavy = io->obs_state || io->obs_new_state || io->ring || env->cfg.friction || (io->obs_next && io->obs_next_per_frame);
+    int mode = ah::MODE_GENERIC;
+    if (!heavy && per_frame_all && io->obs_next) mode = ah::MODE_LEAN;
+    else if (!heavy && !per_frame_any) mode = ah::MODE_SIM;
+    int act = 0;
     switch (io->action_kind) {
-        case AH_ACT_DISCRETE: case AH_ACT_DISCRETE_REPEAT:
-            ah::step_kernel<R, 1><<<grid, ah::kThreads, 0, s>>>(a); break;
-        case AH_ACT_CONTINUOUS: case AH_ACT_CONTINUOUS_REPEAT:
-            ah::step_kernel<R, 2><<<grid, ah::kThreads, 0, s>>>(a); break;
-        case AH_ACT_PHILOX:
-            ah::step_kernel<R, 3><<<grid, ah::kThreads, 0, s>>>(a); break;
+        case AH_ACT_DISCRETE: case AH_ACT_DISCRETE_REPEAT: act = 1; break;
+        case AH_ACT_CONTINUOUS: case AH_ACT_CONTINUOUS_REPEAT: act = 2; break;
+        case AH_ACT_PHILOX: act = 3; break;
         default: return AH_EINVAL;
     }
+#define AH_LAUNCH(ACT_, MODE_) ah::step_kernel<R, ACT_, MODE_><<<grid, ah::kThreads, 0, s>>>(a)
+#define AH_LAUNCH_MODE(ACT_) do { if (mode == ah::MODE_LEAN) AH_LAUNCH(ACT_, ah::MODE_LEAN); \
+        else if (mode == ah::MODE_SIM) AH_LAUNCH(ACT_, ah::MODE_SIM); else AH_LAUNCH(ACT_, ah::MODE_GENERIC); } while (0)
+    if (act == 1) AH_LAUNCH_MODE(1); else if (act == 2) AH_LAUNCH_MODE(2); else AH_LAUNCH_MODE(3);
+#undef AH_LAUNCH_MODE
+#undef AH_LAUNCH
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? AH_OK : cuda_fail(env, e);
 }
@@ -472,7 +530,7 @@ int ah_abi_version(void) { return AH_ABI_VERSION; }
 int ah_last_cuda_error(const ah_env* env) { return env ? env->last_cuda : 0; }
 
 int ah_create(ah_env** out, int64_t n, int dtype, int device, uint64_t seed, uint64_t env_id0, const ah_config* cfg) {
-    if (!out || n <= 0 || (dtype != AH_F32 && dtype != AH_F64) || device < 0) return AH_EINVAL;
+    if (!out || n <= 0 || n >= (int64_t(1) << 31) || (dtype != AH_F32 && dtype != AH_F64) || device < 0) return AH_EINVAL;
     *out = nullptr;
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || device >= count) return AH_ECUDA;   // no CPU fallback
@@ -486,8 +544,8 @@ int ah_create(ah_env** out, int64_t n, int dtype, int device, uint64_t seed, uin
     cudaError_t e = g.ok ? cudaSuccess : cudaErrorInvalidDevice;
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&env->sms, cudaDevAttrMultiProcessorCount, device);
     int occ32 = 0, occ64 = 0;
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ32, ah::step_kernel<float, 1>, ah::kThreads, 0);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ64, ah::step_kernel<double, 1>, ah::kThreads, 0);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ32, ah::step_kernel<float, 1, ah::MODE_LEAN>, ah::kThreads, 0);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ64, ah::step_kernel<double, 1, ah::MODE_GENERIC>, ah::kThreads, 0);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&env->blk), sizeof(ah::DevBlock));
     if (e == cudaSuccess) e = cudaMemset(env->blk, 0, sizeof(ah::DevBlock));
     if (e != cudaSuccess) { if (env->blk) cudaFree(env->blk); delete env; return AH_ECUDA; }

@@ -63,6 +63,11 @@ template <> struct Math<float> {
         asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
         return r;
     }
+    static __device__ __forceinline__ float rsqrt_(float v) {
+        float r;
+        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+        return r;
+    }
     static __device__ __forceinline__ float trunc_(float v) { return truncf(v); }
     static __device__ __forceinline__ float clamp(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
     static __device__ __forceinline__ float abs_(float v) { return fabsf(v); }
@@ -89,16 +94,22 @@ __device__ __forceinline__ void mallet_update(R& x, R& y, R dx, R dy, R lo, R hi
 // ---- AirHockey._move  environment/airhockey.py:65-94 ----
 // The nudge never enters the velocity: after the first update() the velocity is recomputed as the
 // displacement actually made (== the old velocity unless a limit shortened it).
+// Discrete action -> (nx, ny) nudge  (:74-84; any other int: no nudge)
 template <typename R>
-__device__ __forceinline__ void move_robot(Env<R>& e, bool continuous, int ia, R ax, R ay) {
-    if (continuous) {                              // :69-71
+__device__ __forceinline__ void action_nudge(int ia, R& nx, R& ny) {
+    ny = (ia == 0) ? K<R>::step : ((ia == 1) ? -K<R>::step : R(0));
+    nx = (ia == 3) ? K<R>::step : ((ia == 2) ? -K<R>::step : R(0));
+}
+
+// continuous: (ax, ay) is added to the velocity (:69-71); discrete: (ax, ay) is the position nudge
+template <typename R>
+__device__ __forceinline__ void move_robot(Env<R>& e, bool continuous, R ax, R ay) {
+    if (continuous) {
         e.rdx += ax;
         e.rdy += ay;
-    } else {                                       // :74-84 ; other ints: no nudge
-        const R ny = (ia == 0) ? K<R>::step : (ia == 1) ? -K<R>::step : R(0);
-        const R nx = (ia == 3) ? K<R>::step : (ia == 2) ? -K<R>::step : R(0);
-        e.ry += ny;
-        e.rx += nx;
+    } else {
+        e.ry += ay;
+        e.rx += ax;
     }
     const R lx = e.rx, ly = e.ry;                  // mallet.py:57-58 (last_x, last_y)
     mallet_update<R>(e.rx, e.ry, e.rdx, e.rdy, K<R>::robot_lo, K<R>::robot_hi);   // :87
@@ -123,7 +134,7 @@ __device__ __forceinline__ bool collision(R& px, R& py, R& pdx, R& pdy, R& mx, R
         if (distance > R(0)) { n_x = d_x / distance; n_y = d_y / distance; }   // :217
         else { n_x = d_x; n_y = d_y; }
     } else {
-        const R inv = dist_sq > R(0) ? rsqrtf((float)dist_sq) : R(1);
+        const R inv = dist_sq > R(0) ? (R)Math<float>::rsqrt_((float)dist_sq) : R(1);
         n_x = d_x * inv; n_y = d_y * inv;
     }
     // :220 `dcoll = radius - d` is a 2-VECTOR in the reference and :230 `np.max(dcoll - slop, 0)` is the
@@ -166,39 +177,46 @@ __device__ __forceinline__ void friction_on_puck(R& pdx, R& pdy) {
 // ---- Puck.limit_puck_speed  environment/puck.py:90-109 ----
 template <typename R>
 __device__ __forceinline__ void limit_puck_speed(R& pdx, R& pdy) {
-    pdx = (pdx > K<R>::speed) ? K<R>::speed : pdx;                 // :94-95
-    pdx = (pdx < -K<R>::speed) ? -K<R>::speed : pdx;               // :96-97
-    pdy = (pdy > K<R>::speed) ? K<R>::speed : pdy;                 // :100-101
-    pdy = (pdy < -K<R>::speed) ? K<R>::speed : pdy;                // :102-103: -> +speed, as in the reference
+    if (Math<R>::exact) {
+        pdx = (pdx > K<R>::speed) ? K<R>::speed : pdx;             // :94-95
+        pdx = (pdx < -K<R>::speed) ? -K<R>::speed : pdx;           // :96-97
+        pdy = (pdy > K<R>::speed) ? K<R>::speed : pdy;             // :100-101
+        pdy = (pdy < -K<R>::speed) ? K<R>::speed : pdy;            // :102-103: -> +speed, as in the reference
+    } else {
+        pdx = Math<R>::clamp(pdx, -K<R>::speed, K<R>::speed);
+        pdy = (pdy < -K<R>::speed) ? K<R>::speed : fminf(pdy, K<R>::speed);
+    }
 }
 
 // ---- Puck.update  environment/puck.py:45-71: clamp + reflect FIRST, then advance ----
 template <typename R>
 __device__ __forceinline__ void puck_update(R& px, R& py, R& pdx, R& pdy) {
-    const bool fx = (px <= K<R>::puck_x_lo) || (px >= K<R>::puck_x_hi);
-    px = (px <= K<R>::puck_x_lo) ? K<R>::puck_x_lo : ((px >= K<R>::puck_x_hi) ? K<R>::puck_x_hi : px);
-    pdx = fx ? -pdx : pdx;                                         // `dx *= -1`
-    const bool fy = (py <= K<R>::puck_y_lo) || (py >= K<R>::puck_y_hi);
-    py = (py <= K<R>::puck_y_lo) ? K<R>::puck_y_lo : ((py >= K<R>::puck_y_hi) ? K<R>::puck_y_hi : py);
-    pdy = fy ? -pdy : pdy;
+    const bool in_x = (px > K<R>::puck_x_lo) && (px < K<R>::puck_x_hi);     // not (x <= 15 or x >= 885)
+    px = Math<R>::clamp(px, K<R>::puck_x_lo, K<R>::puck_x_hi);
+    pdx = in_x ? pdx : -pdx;                                       // `dx *= -1`
+    const bool in_y = (py > K<R>::puck_y_lo) && (py < K<R>::puck_y_hi);
+    py = Math<R>::clamp(py, K<R>::puck_y_lo, K<R>::puck_y_hi);
+    pdy = in_y ? pdy : -pdy;
     px += pdx;                                                     // :68
     py += pdy;                                                     // :69
 }
 
-// ---- AirHockey.computerAI  environment/airhockey.py:270-308 ----
+// ---- AirHockey.computerAI  environment/airhockey.py:270-308 (written with selects: no divergence) ----
 template <typename R>
 __device__ __forceinline__ void computer_ai(Env<R>& e) {
     using M = Math<R>;
-    if (e.px < e.ox) e.odx = (e.px < K<R>::opp_lo) ? R(1) : R(-2);             // :273-277
-    if (e.px > e.ox) e.odx = (e.px > K<R>::opp_hi) ? R(-1) : R(2);             // :279-283
-    if (e.py < e.oy) e.ody = (e.py < K<R>::y_lo) ? R(1) : R(-6);               // :285-289
-    if (e.py > e.oy) {                                                         // :291
-        e.ody = (e.py <= R(360)) ? R(6) : ((e.oy > R(200)) ? R(-2) : R(0));    // :292-300
-        if (M::abs_(e.py - e.oy) < R(40) && M::abs_(e.px - e.ox) < R(40)) {    // :303
-            e.pdx += R(2);                                                     // :304
-            e.pdy += R(2);                                                     // :305
-        }
-    }
+    const bool x_lt = e.px < e.ox, x_gt = e.px > e.ox;
+    const R dx_lt = (e.px < K<R>::opp_lo) ? R(1) : R(-2);                      // :273-277
+    const R dx_gt = (e.px > K<R>::opp_hi) ? R(-1) : R(2);                      // :279-283
+    e.odx = x_lt ? dx_lt : (x_gt ? dx_gt : e.odx);
+    const bool y_lt = e.py < e.oy, y_gt = e.py > e.oy;
+    const R dy_lt = (e.py < K<R>::y_lo) ? R(1) : R(-6);                        // :285-289
+    const R dy_gt = (e.py <= R(360)) ? R(6) : ((e.oy > R(200)) ? R(-2) : R(0));   // :292-300
+    e.ody = y_lt ? dy_lt : (y_gt ? dy_gt : e.ody);
+    // :303-305, only inside the `puck.y > opponent.y` branch
+    const bool near = y_gt && (M::abs_(e.py - e.oy) < R(40)) && (M::abs_(e.px - e.ox) < R(40));
+    e.pdx = near ? e.pdx + R(2) : e.pdx;
+    e.pdy = near ? e.pdy + R(2) : e.pdy;
     mallet_update<R>(e.ox, e.oy, e.odx, e.ody, K<R>::opp_lo, K<R>::opp_hi);    // :307
 }
 
@@ -235,9 +253,9 @@ __device__ __forceinline__ void rewards_call(Env<R>& e, bool dot_fma, int& rewar
     // compute_score_reward  rewards.py:64-81 with Goal.__contains__  goal.py:13-18; its reward and its own
     // `done` are discarded by the caller (rewards.py:122).  The left-goal test comes second and wins ties.
     const bool in_y = M::abs_(K<R>::mid_y - e.py) < R(95);
-    score = 0;
-    if (M::abs_(K<R>::table_w - e.px) < R(30) && in_y) score = 1;
-    if (M::abs_(R(0) - e.px) < R(30) && in_y) score = -1;
+    const bool right = (M::abs_(K<R>::table_w - e.px) < R(30)) && in_y;
+    const bool left = (M::abs_(R(0) - e.px) < R(30)) && in_y;
+    score = left ? -1 : (right ? 1 : 0);
     // compute_mallet_hit_puck  rewards.py:83-89 with Puck.__and__  puck.py:135-146
     const R ex = e.px - e.rx, ey = e.py - e.ry;
     const R dsq = M::dot2(ex, ey, ex, ey, dot_fma);
@@ -248,17 +266,14 @@ __device__ __forceinline__ void rewards_call(Env<R>& e, bool dot_fma, int& rewar
     } else {
         done = dsq < K<R>::radius_sq;
     }
-    int rw = done ? 3 : -1;
-    // compute_wall_reward  rewards.py:45-62 with Puck.__lshift__/__rshift__  puck.py:148-164
-    int wall = 0;
-    if (M::abs_(e.px - K<R>::left_wall) < K<R>::puck_r) wall = -2;
-    if (M::abs_(e.px - K<R>::right_wall) < K<R>::puck_r) wall = 2;
-    rw += wall;
+    // compute_wall_reward  rewards.py:45-62 with Puck.__lshift__/__rshift__  puck.py:148-164 (second `if` wins)
+    const bool wl = M::abs_(e.px - K<R>::left_wall) < K<R>::puck_r;
+    const bool wr = M::abs_(e.px - K<R>::right_wall) < K<R>::puck_r;
     // compute_mallet_to_puck_distance  rewards.py:91-101 (np.linalg.norm == sqrt(np.dot))
     const R nd = M::sqrt_(dsq);
-    rw += (nd < e.prev_dist) ? 1 : -1;
+    const bool closer = nd < e.prev_dist;
     e.prev_dist = nd;
-    reward = rw;
+    reward = (done ? 3 : -1) + (wr ? 2 : (wl ? -2 : 0)) + (closer ? 1 : -1);
 }
 
 }  // namespace ah
