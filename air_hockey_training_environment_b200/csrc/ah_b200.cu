@@ -135,6 +135,7 @@ struct BlockStats {
 __device__ __forceinline__ void stat_add(BlockStats& bs, int which, int x) { atomicAdd(&bs.v[which], x); }
 
 constexpr int kThreads = 256;
+constexpr int kMaxBlocks = 1 << 20;
 
 template <typename R> struct Occ { static constexpr int blocks = 4; };
 template <> struct Occ<double> { static constexpr int blocks = 2; };
@@ -164,13 +165,17 @@ __global__ void __launch_bounds__(kThreads, Occ<R>::blocks) step_kernel(const St
     const bool want_obs = (MODE == MODE_GENERIC) && (a.obs_state || a.obs_new_state || a.ring_capacity > 0);
     const int K = a.K;
     const size_t act_step = repeat ? 0 : (size_t)n;           // elements between frame k and k+1 of the action tensor
-    int reward_sum = 0, reward_sq = 0, frames = 0;
+    int reward_sum = 0, reward_sq = 0, frames = 0, dones = 0;
 
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         Env<R> e = load_env<R>(a.st, i);
         // 10-goal flag carried into the frame (only reachable through injected state; see game.py:169-177)
         int go = (e.robot_score == 10) ? 1 : ((e.opp_score == 10) ? 2 : 0);
         int contacts_r = 0, contacts_o = 0;
+        // game_frames / reward_sum are not incremented per frame: frames-in-game = gf_base + frames done in this
+        // launch, and the launch's reward sum is recovered from game_return (+ the returns of finished games)
+        int gf_base = e.game_frames;
+        int ret_credit = -e.game_return;
         unsigned overflow = 0;
         Philox4 ablock = {};
         uint32_t ablock_id = 0xffffffffu;
@@ -213,8 +218,8 @@ __global__ void __launch_bounds__(kThreads, Occ<R>::blocks) step_kernel(const St
             // ---- Rewards                                           agent.py:70-71
             int rw, sc; bool dn;
             rewards_call<R>(e, dot_fma, rw, sc, dn);
-            e.game_frames += 1; e.game_return += rw;
-            reward_sum += rw; reward_sq += rw * rw;
+            e.game_return += rw;
+            reward_sq += rw * rw;
             // ---- env.update_score(score)                           game.py:142 -> airhockey.py:149-169
             if (sc != 0) {
                 if (sc > 0) { e.robot_score += 1; stat_add(bs, AH_STAT_ROBOT_GOALS, 1); }
@@ -224,7 +229,7 @@ __global__ void __launch_bounds__(kThreads, Occ<R>::blocks) step_kernel(const St
                 go = (e.robot_score == 10) ? 1 : go;
                 go = (e.opp_score == 10) ? 2 : go;
             }
-            if (dn) stat_add(bs, AH_STAT_DONES, 1);
+            dones += dn ? 1 : 0;
             // ---- env.update_state(agent_name="computer"): sub-update #3   game.py:166
             computer_ai<R>(e);
             physics_tail<R>(e, dot_fma, friction, contacts_r, contacts_o);
@@ -255,10 +260,12 @@ __global__ void __launch_bounds__(kThreads, Occ<R>::blocks) step_kernel(const St
             if (go != 0) {
                 stat_add(bs, AH_STAT_GAMES, 1);
                 stat_add(bs, go == 1 ? AH_STAT_ROBOT_WINS : AH_STAT_OPPONENT_WINS, 1);
-                stat_add(bs, AH_STAT_GAME_LEN_SUM, e.game_frames);
-                atomicAdd(&bs.len_sq, (unsigned long long)e.game_frames * (unsigned long long)e.game_frames);
+                const int len = gf_base + k + 1;
+                stat_add(bs, AH_STAT_GAME_LEN_SUM, len);
+                atomicAdd(&bs.len_sq, (unsigned long long)len * (unsigned long long)len);
                 stat_add(bs, AH_STAT_GAME_RETURN_SUM, e.game_return);
-                e.game_frames = 0; e.game_return = 0;
+                ret_credit += e.game_return;
+                gf_base = -(k + 1); e.game_return = 0;
                 env_reset<R>(e, true, a.rs, i, overflow);
                 go = 0;
             }
@@ -268,6 +275,8 @@ __global__ void __launch_bounds__(kThreads, Occ<R>::blocks) step_kernel(const St
         // the next frame's policy input (agent.py:46)
         if (a.obs_next && !(MODE == MODE_GENERIC && a.obs_next_per_frame)) store_obs<R>(a.obs_next, i, get_state<R>(e, true));
         frames += K;
+        e.game_frames = gf_base + K;
+        reward_sum += e.game_return + ret_credit;
         if (contacts_r) stat_add(bs, AH_STAT_CONTACTS_ROBOT, contacts_r);
         if (contacts_o) stat_add(bs, AH_STAT_CONTACTS_OPPONENT, contacts_o);
         if (overflow) stat_add(bs, AH_STAT_RESET_TABLE_OVERFLOW, (int)overflow);
@@ -281,7 +290,9 @@ __global__ void __launch_bounds__(kThreads, Occ<R>::blocks) step_kernel(const St
         const int fs = __reduce_add_sync(0xffffffffu, frames);
         const int rs = __reduce_add_sync(0xffffffffu, reward_sum);
         const int rq = __reduce_add_sync(0xffffffffu, reward_sq);
+        const int dd = __reduce_add_sync(0xffffffffu, dones);
         if ((threadIdx.x & 31) == 0) {
+            stat_add(bs, AH_STAT_DONES, dd);
             stat_add(bs, AH_STAT_FRAMES, fs);
             stat_add(bs, AH_STAT_REWARD_SUM, rs);
             stat_add(bs, AH_STAT_REWARD_SQ_SUM, rq);
@@ -549,8 +560,17 @@ int ah_create(ah_env** out, int64_t n, int dtype, int device, uint64_t seed, uin
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&env->blk), sizeof(ah::DevBlock));
     if (e == cudaSuccess) e = cudaMemset(env->blk, 0, sizeof(ah::DevBlock));
     if (e != cudaSuccess) { if (env->blk) cudaFree(env->blk); delete env; return AH_ECUDA; }
-    env->blocks_f32 = env->sms * (occ32 > 0 ? occ32 : 1);
-    env->blocks_f64 = env->sms * (occ64 > 0 ? occ64 : 1);
+    // Grid: one thread per environment, blocks of 256, left to the hardware block scheduler.  Measured on B200
+    // at n = 2^20, K = 8 (FP32): 148 x 4 persistent blocks 123 us, 4096 blocks 115 us -- the frame loop is
+    // ALU-pipe bound, so finer-grained blocks only help by evening out the tail.  The grid-stride loop in the
+    // kernel stays for n > kMaxBlocks * 256 and for the AH_GRID_BLOCKS tuning override.
+    (void)occ32; (void)occ64;
+    env->blocks_f32 = ah::kMaxBlocks;
+    env->blocks_f64 = ah::kMaxBlocks;
+    if (const char* ov = getenv("AH_GRID_BLOCKS")) {       // tuning aid: override the grid size
+        const int b = atoi(ov);
+        if (b > 0) { env->blocks_f32 = b; env->blocks_f64 = b; }
+    }
     *out = env;
     return AH_OK;
 }

@@ -119,15 +119,19 @@ __device__ __forceinline__ void move_robot(Env<R>& e, bool continuous, R ax, R a
 }
 
 // ---- AirHockey.collision  environment/airhockey.py:189-268 (correction=True) ----
+// Split in two: the distance test that every sub-update pays (5 flops), and the contact response that runs
+// for ~0.5 % of the tests.  `d = mallet - puck` and `dist_sq = np.dot(d, d)` are handed over from the test.
 template <typename R>
-__device__ __forceinline__ bool collision(R& px, R& py, R& pdx, R& pdy, R& mx, R& my, R& mdx, R& mdy, bool dot_fma,
-                                          int& contacts) {
+__device__ __forceinline__ R contact_dist_sq(R px, R py, R mx, R my, bool dot_fma, R& d_x, R& d_y) {
+    d_x = mx - px;                                                 // :198
+    d_y = my - py;                                                 // :199
+    return Math<R>::dot2(d_x, d_y, d_x, d_y, dot_fma);             // :203
+}
+
+template <typename R>
+__device__ __forceinline__ void contact_response(R& px, R& py, R& pdx, R& pdy, R& mx, R& my, R& mdx, R& mdy,
+                                                 R d_x, R d_y, R dist_sq, bool dot_fma) {
     using M = Math<R>;
-    const R d_x = mx - px;                                         // :198
-    const R d_y = my - py;                                         // :199
-    const R dist_sq = M::dot2(d_x, d_y, d_x, d_y, dot_fma);        // :203
-    if (dist_sq > K<R>::radius_sq) return false;                   // :210 (touching counts as contact)
-    contacts += 1;
     R n_x, n_y;
     if (M::exact) {
         const R distance = M::sqrt_(dist_sq);                      // :214
@@ -142,27 +146,34 @@ __device__ __forceinline__ bool collision(R& px, R& py, R& pdx, R& pdy, R& mx, R
     const R a = (K<R>::radius - d_x) - R(0.01);
     const R b = (K<R>::radius - d_y) - R(0.01);
     const R m = (a >= b) ? a : b;
-    R s;
-    if (M::exact) s = (m / K<R>::imass_sum) * R(0.2);              // :230 ((max / imass_sum) * percent)
-    else s = m * R(0.2 / 12.0);
-    const R sep_x = s * n_x, sep_y = s * n_y;
-    px -= sep_x * K<R>::puck_imass;                                // :235
-    py -= sep_y * K<R>::puck_imass;                                // :236
-    mx += sep_x * K<R>::mallet_imass;                              // :237
-    my += sep_y * K<R>::mallet_imass;                              // :238
+    if (M::exact) {
+        const R s = (m / K<R>::imass_sum) * R(0.2);                // :230 ((max / imass_sum) * percent)
+        const R sep_x = s * n_x, sep_y = s * n_y;
+        px -= sep_x * K<R>::puck_imass;                            // :235
+        py -= sep_y * K<R>::puck_imass;                            // :236
+        mx += sep_x * K<R>::mallet_imass;                          // :237
+        my += sep_y * K<R>::mallet_imass;                          // :238
+    } else {
+        const float sp = (float)m * (float)(-10.0 * 0.2 / 12.0), sm = (float)m * (float)(2.0 * 0.2 / 12.0);
+        px = fmaf(sp, n_x, px); py = fmaf(sp, n_y, py);
+        mx = fmaf(sm, n_x, mx); my = fmaf(sm, n_y, my);
+    }
     const R v_x = mdx - pdx;                                       // :241
     const R v_y = mdy - pdy;                                       // :242
     const R vn = M::dot2(v_x, v_y, n_x, n_y, dot_fma);             // :246
-    if (vn > R(0)) return true;                                    // :249 moving apart
-    R j;
-    if (M::exact) j = -(R(1.0) + R(0.9)) * (vn / K<R>::imass_sum); // :256
-    else j = vn * R(-1.9 / 12.0);
-    const R i_x = j * n_x, i_y = j * n_y;                          // :259
-    pdx -= i_x * K<R>::puck_imass;                                 // :262
-    pdy -= i_y * K<R>::puck_imass;                                 // :263
-    mdx += i_x * K<R>::mallet_imass;                               // :265
-    mdy += i_y * K<R>::mallet_imass;                               // :266
-    return true;
+    if (vn > R(0)) return;                                         // :249 moving apart
+    if (M::exact) {
+        const R j = -(R(1.0) + R(0.9)) * (vn / K<R>::imass_sum);   // :256
+        const R i_x = j * n_x, i_y = j * n_y;                      // :259
+        pdx -= i_x * K<R>::puck_imass;                             // :262
+        pdy -= i_y * K<R>::puck_imass;                             // :263
+        mdx += i_x * K<R>::mallet_imass;                           // :265
+        mdy += i_y * K<R>::mallet_imass;                           // :266
+    } else {
+        const float jp = (float)vn * (float)(10.0 * 1.9 / 12.0), jm = (float)vn * (float)(-2.0 * 1.9 / 12.0);
+        pdx = fmaf(jp, n_x, pdx); pdy = fmaf(jp, n_y, pdy);
+        mdx = fmaf(jm, n_x, mdx); mdy = fmaf(jm, n_y, mdy);
+    }
 }
 
 // ---- Puck.friction_on_puck  environment/puck.py:73-88 (dead code in the reference; opt-in flag) ----
@@ -221,10 +232,24 @@ __device__ __forceinline__ void computer_ai(Env<R>& e) {
 }
 
 // ---- the common tail of AirHockey.update_state  environment/airhockey.py:112-122 ----
+// The two contact tests (robot first, then opponent, :113-114) share ONE rarely-taken branch; inside it the
+// opponent's test is re-evaluated against the puck as the robot's response left it, as the reference does.
 template <typename R>
 __device__ __forceinline__ void physics_tail(Env<R>& e, bool dot_fma, bool friction, int& c_robot, int& c_opp) {
-    collision<R>(e.px, e.py, e.pdx, e.pdy, e.rx, e.ry, e.rdx, e.rdy, dot_fma, c_robot);   // :113-114 robot first
-    collision<R>(e.px, e.py, e.pdx, e.pdy, e.ox, e.oy, e.odx, e.ody, dot_fma, c_opp);
+    R rdx_, rdy_, odx_, ody_;
+    const R dr = contact_dist_sq<R>(e.px, e.py, e.rx, e.ry, dot_fma, rdx_, rdy_);
+    R dq = contact_dist_sq<R>(e.px, e.py, e.ox, e.oy, dot_fma, odx_, ody_);
+    if (!(dr > K<R>::radius_sq) || !(dq > K<R>::radius_sq)) {                    // :210 (touching counts as contact)
+        if (!(dr > K<R>::radius_sq)) {
+            c_robot += 1;
+            contact_response<R>(e.px, e.py, e.pdx, e.pdy, e.rx, e.ry, e.rdx, e.rdy, rdx_, rdy_, dr, dot_fma);
+            dq = contact_dist_sq<R>(e.px, e.py, e.ox, e.oy, dot_fma, odx_, ody_);
+        }
+        if (!(dq > K<R>::radius_sq)) {
+            c_opp += 1;
+            contact_response<R>(e.px, e.py, e.pdx, e.pdy, e.ox, e.oy, e.odx, e.ody, odx_, ody_, dq, dot_fma);
+        }
+    }
     if (friction) friction_on_puck<R>(e.pdx, e.pdy);
     limit_puck_speed<R>(e.pdx, e.pdy);                                           // :117
     puck_update<R>(e.px, e.py, e.pdx, e.pdy);                                    // :118
