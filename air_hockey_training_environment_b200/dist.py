@@ -1,0 +1,100 @@
+"""Multi-GPU plumbing: environments shard trivially, one process per GPU.
+
+The reference is a single-process, single-game loop (game.py:179-196); nothing in the environment step reads or
+writes another game's state, so N games are split into contiguous slices, one per rank, with NO collective in the
+step itself.  The only exchange is the small per-rollout all-reduce of the episode / score statistics vector
+(the device-side equivalent of scores.csv, game.py:82-112, and of the rewards CSV, lib/rewards.py:129-140).
+
+RNG keys use the GLOBAL env id (``env_id0 = first env of this rank``), so the union of the shards is bit-identical
+to one big environment (tests/test_gpu_api.py::test_sharding_invariance).
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import _capi
+
+
+def shard_bounds(n_global: int, world_size: int, rank: int) -> Tuple[int, int]:
+    """Contiguous slice [lo, hi) of the global env index space owned by ``rank`` (sizes differ by at most 1)."""
+    if not (0 <= rank < world_size):
+        raise ValueError("rank out of range")
+    base, extra = divmod(n_global, world_size)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def rank_info() -> Tuple[int, int, int]:
+    """(rank, world_size, local_rank) from the torchrun environment; (0, 1, 0) when not launched by torchrun."""
+    return (int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")),
+            int(os.environ.get("LOCAL_RANK", "0")))
+
+
+def init_process_group(backend: Optional[str] = None) -> Tuple[int, int, int]:
+    """Initialise torch.distributed from the torchrun environment (nccl on GPUs, gloo on CPU)."""
+    rank, world, local = rank_info()
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            dist.init_process_group(backend, device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend)
+    return rank, world, local
+
+
+def all_reduce_stats(stats: torch.Tensor, group=None) -> torch.Tensor:
+    """Sum the int64[16] statistics vector over all ranks, in place (one 128-byte all-reduce per rollout; NCCL
+    over NVLink on GPUs).  A no-op for a single process."""
+    if stats.dtype != torch.int64 or stats.numel() != _capi.AH_NSTATS:
+        raise ValueError("stats must be the int64[16] vector returned by BatchedAirHockey.stats_tensor()")
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
+    return stats
+
+
+def summarize(stats: torch.Tensor) -> Dict[str, float]:
+    """Host-side summary of a (reduced) statistics vector: the aggregates the reference logs per frame / per
+    episode (robot_goal, opponent_goal, robot_win, opponent_win, mean reward), as rates."""
+    v = dict(zip(_capi.STAT_NAMES, stats.tolist()))
+    f = max(v["frames"], 1)
+    g = max(v["games"], 1)
+    out = dict(v)
+    out.update({
+        "robot_goals_per_1k_frames": 1e3 * v["robot_goals"] / f,
+        "opponent_goals_per_1k_frames": 1e3 * v["opponent_goals"] / f,
+        "dones_per_1k_frames": 1e3 * v["dones"] / f,
+        "mean_reward": v["reward_sum"] / f,
+        "reward_var": v["reward_sq_sum"] / f - (v["reward_sum"] / f) ** 2,
+        "robot_win_rate": v["robot_wins"] / g,
+        "mean_game_length": v["game_len_sum"] / g,
+        "game_length_var": v["game_len_sq_sum"] / g - (v["game_len_sum"] / g) ** 2,
+        "mean_game_return": v["game_return_sum"] / g,
+        "contacts_robot_per_1k_frames": 1e3 * v["contacts_robot"] / f,
+        "contacts_opponent_per_1k_frames": 1e3 * v["contacts_opponent"] / f,
+    })
+    return out
+
+
+class ShardedAirHockey:
+    """This rank's slice of ``n_global`` games.  Thin convenience over ``BatchedAirHockey``: same verbs, plus
+    ``reduced_stats`` which performs the per-rollout all-reduce."""
+
+    def __init__(self, n_global: int, dtype: torch.dtype = torch.float32, seed: int = 0, **kw):
+        from .env import BatchedAirHockey
+        self.rank, self.world, self.local = rank_info()
+        self.n_global = int(n_global)
+        self.lo, self.hi = shard_bounds(self.n_global, self.world, self.rank)
+        self.env = BatchedAirHockey(self.hi - self.lo, dtype=dtype, device=torch.device("cuda", self.local),
+                                    seed=seed, env_id0=self.lo, **kw)
+
+    def __getattr__(self, name):
+        return getattr(self.env, name)
+
+    def reduced_stats(self, clear: bool = True) -> torch.Tensor:
+        return all_reduce_stats(self.env.stats_tensor(clear=clear).clone())

@@ -1,0 +1,126 @@
+"""Zero-copy rollout collection: the step kernel writes observations, rewards and dones straight into the
+preallocated ``[T(+1), N, ...]`` rollout tensors that a PPO / A2C / DQN learner consumes on the device -- no host
+round-trip anywhere in the loop (BASELINE config 5: 65,536 envs x 128 steps feeding a torch policy).
+
+What it replaces in the reference (paths relative to the reference root):
+    Agent.get_action -> env.get_state -> serialize_state -> policy          lib/agents/agent.py:42-48
+    Agent.move / Agent.step / env.update_score / computer sub-update        game.py:133-177 (fused: env.step)
+    self.memory.append(observation)                                          lib/agents/ppo/ppo.py:144, lib/buffer.py:24-32
+The learners themselves (Keras PPO/A2C/DDQN, lib/agents/**) are consumers of these tensors and are out of scope
+here; ``ActorMLP`` only mirrors the reference's discrete PPO actor so the rollout runs a policy of the right shape.
+
+The whole T-step loop (policy forward, action sampling, env.step) can be captured in ONE CUDA graph: every C-ABI
+call enqueues on the caller's stream without allocating or synchronising, and the frame / ring counters live on
+the device.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, Optional
+
+import torch
+from torch import nn
+
+from .env import BatchedAirHockey, StepOutputs
+
+
+class ActorMLP(nn.Module):
+    """The reference's discrete PPO actor: Dense(4, relu) - BatchNorm - Dense(6, relu) - Dense(4, relu) -
+    Dense(4, softmax)  (lib/agents/ppo/model.py:63-74; ``kernel_initializer="normal"`` is N(0, 0.05) in Keras).
+    Inference only (BatchNorm in eval mode)."""
+
+    def __init__(self, state_size: int = 8, action_size: int = 4):
+        super().__init__()
+        self.net = nn.Sequential(nn.Linear(state_size, 4), nn.ReLU(), nn.BatchNorm1d(4), nn.Linear(4, 6), nn.ReLU(),
+                                 nn.Linear(6, 4), nn.ReLU(), nn.Linear(4, action_size))
+        for m in self.net:
+            if isinstance(m, nn.Linear):
+                nn.init.normal_(m.weight, std=0.05)
+                nn.init.zeros_(m.bias)
+        self.eval()
+
+    def forward(self, obs: torch.Tensor) -> torch.Tensor:      # obs [N, 8] -> action probabilities [N, 4]
+        return torch.softmax(self.net(obs), dim=-1)
+
+
+class RolloutCollector:
+    """Collects ``T`` frames from ``env`` under ``policy`` into preallocated device tensors.
+
+    obs      real [T+1, N, 8]   obs[t] is the policy input of frame t (agent.py:46); obs[T] bootstraps the value
+    actions  int8 [T, N]
+    rewards  real [T, N], dones u8 [T, N], scores i8 [T, N], game_over u8 [T, N]
+    probs    real [T, N, A]     the policy's action distribution at frame t (PPO's ``old_prediction``)
+    """
+
+    def __init__(self, env: BatchedAirHockey, T: int, policy: Optional[Callable[[torch.Tensor], torch.Tensor]] = None,
+                 action_size: int = 4, use_graph: bool = True, seed: int = 0):
+        self.env, self.T, self.A = env, int(T), int(action_size)
+        n, dt, dev = env.n, env.dtype, env.device
+        self.policy = policy if policy is not None else ActorMLP(8, action_size).to(device=dev, dtype=dt)
+        self.obs = torch.zeros(T + 1, n, 8, dtype=dt, device=dev)
+        self.actions = torch.zeros(T, n, dtype=torch.int8, device=dev)
+        self.rewards = torch.zeros(T, n, dtype=dt, device=dev)
+        self.dones = torch.zeros(T, n, dtype=torch.uint8, device=dev)
+        self.scores = torch.zeros(T, n, dtype=torch.int8, device=dev)
+        self.game_over = torch.zeros(T, n, dtype=torch.uint8, device=dev)
+        self.probs = torch.zeros(T, n, action_size, dtype=dt, device=dev)
+        # views handed to the kernel: it writes frame t's outputs directly into row t of the rollout tensors
+        self._outs = [StepOutputs(reward=self.rewards[t:t + 1], done=self.dones[t:t + 1], score=self.scores[t:t + 1],
+                                  game_over=self.game_over[t:t + 1], obs_next=self.obs[t + 1]) for t in range(T)]
+        self.gen = torch.Generator(device=dev)
+        self.gen.manual_seed(seed)
+        self.use_graph = use_graph
+        self._graph = None
+        self.env.get_state("robot", out=self.obs[0])
+
+    def _loop(self, collect_stats: bool = True) -> None:
+        with torch.no_grad():
+            for t in range(self.T):
+                p = self.policy(self.obs[t])
+                self.probs[t].copy_(p)
+                a = torch.multinomial(p.float(), 1, generator=self.gen).squeeze(1)
+                self.actions[t].copy_(a)                         # int64 -> int8, into the rollout tensor
+                self.env.step(self.actions[t], K=1, out=self._outs[t], collect_stats=collect_stats)
+
+    def _capture(self) -> None:
+        dev = self.env.device
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        saved = self.env.state_dict()
+        with torch.cuda.stream(side):                            # warm-up outside the capture (lazy init of kernels)
+            self._loop(collect_stats=False)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.env.load_state_dict(saved)                          # the warm-up must not advance the games
+        self.env.get_state("robot", out=self.obs[0])
+        g = torch.cuda.CUDAGraph()
+        g.register_generator_state(self.gen)
+        with torch.cuda.graph(g):
+            self._loop()
+        self._graph = g
+        self.env.load_state_dict(saved)                          # the capture pass itself ran nothing, but be explicit
+        self.env.get_state("robot", out=self.obs[0])
+
+    def collect(self) -> Dict[str, torch.Tensor]:
+        """Run T frames.  The previous rollout's last observation becomes obs[0]."""
+        if self.use_graph:
+            if self._graph is None:
+                self._capture()
+            else:
+                self.obs[0].copy_(self.obs[self.T])
+            self._graph.replay()
+        else:
+            if self._ran:
+                self.obs[0].copy_(self.obs[self.T])
+            self._loop()
+        self._ran = True
+        return {"obs": self.obs, "actions": self.actions, "rewards": self.rewards, "dones": self.dones,
+                "scores": self.scores, "game_over": self.game_over, "probs": self.probs}
+
+    _ran = False
+
+    def discounted_returns(self, gamma: float = 0.8) -> torch.Tensor:
+        """Monte-Carlo discounted returns over the rollout, ``rewards[j] += rewards[j+1] * gamma`` backwards in
+        time (lib/agents/ppo/ppo.py:142-146; gamma = 0.8 is the reference's PPO setting, ppo/model.py:37)."""
+        ret = self.rewards.clone()
+        for t in range(self.T - 2, -1, -1):
+            ret[t] += gamma * ret[t + 1]
+        return ret
