@@ -4,18 +4,22 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (BASELINE.json configs[2], and configs[3] sharded over N GPUs): per GPU 2^20 environments, FP32
-throughput build, one bench "step" = ONE launch of the fused step kernel = 8 frames per env with per-frame
-discrete actions read from an int8 [8, n] tensor, the in-kernel computerAI opponent and Rewards reward,
-writing reward/done/score/game_over [8, n] and the next observation [n, 8]; statistics are warp/block
-reduced in-kernel and (N > 1) all-reduced over NCCL once per step.  1 env-step = 1 frame of Game.play
-(3 physics sub-updates + reward + score / game-over handling).
+Workload (BASELINE.json configs[2]; configs[3] = the same per-GPU work sharded over N GPUs): per GPU 2^20
+environments, FP32 throughput build, one bench "step" = ONE launch of the fused step kernel = 8 frames per env with
+per-frame discrete actions read from an int8 [8, n] tensor, the in-kernel computerAI opponent and Rewards reward,
+writing reward/done/score/game_over [8, n] and the next observation [n, 8]; statistics are reduced in-kernel and
+(N > 1) all-reduced over NCCL once per step.  1 env-step = 1 frame of Game.play (3 physics sub-updates + reward +
+score / game-over handling).
 
-`value`  : device-resident throughput (actions already in HBM).
-`e2e`    : same call, but every step's actions come from pinned HOST memory (H2D inside the timed region) and
-           the step's results (reward, done, next observation) are copied back to pinned host memory.
-`cpu_baseline` / `--impl reference`: the C restatement of the reference (oracle/, kind "port") on the host
-           cores with OpenMP -- the Python reference itself cannot travel to the GPU box.
+`value`        device-resident throughput (actions already in HBM), CUDA events, max over ranks.
+`e2e`          same public-API call, but every step's actions come from pinned HOST memory (H2D inside the timed
+               region) and the step's results (reward, done, next observation) go back to pinned host memory.
+`roofline`     the fused K=8 kernel is bound by FP32/ALU-pipe issue, not by HBM: `achieved` counts the
+               ALGORITHMIC lane-ops (254 per env-step) per second against 148 SMs x 128 lanes x
+               SM clock; the HBM view of the same launch is reported beside it (`hbm_*`).
+`rollout_k1`   the HBM-bound mode (one policy decision per launch, all outputs written) with its own HBM roofline.
+`cpu_baseline` / `--impl reference`: the C restatement of the reference (oracle/, kind "port") on the host cores
+               with OpenMP -- the Python reference itself cannot travel to the GPU box.
 """
 from __future__ import annotations
 
@@ -35,6 +39,8 @@ FRAMES_PER_STEP = 8          # K fused frames per launch (BASELINE config 3)
 ENVS_PER_GPU = 1 << 20
 METRIC = "env-steps/sec"
 UNIT = "env-steps/s"
+LANE_OPS_PER_ENV_STEP = 254  # algorithmic FP32-pipe lane-ops per frame (88 FLOP + 166 cmp/sel/cvt)
+STATE_BYTES = 3 * 16 + 4 + 16   # puck, robot, opponent float4 + prev_dist + meta int4
 
 
 def peaks():
@@ -45,10 +51,19 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
 
 
+def profile_fact(name, default=None):
+    """Numbers that only ncu can provide (committed under profiles/ from the last capture of this kernel)."""
+    p = os.path.join(ROOT, "profiles", "step_kernel_facts.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get(name, default)
+    return default
+
+
 # ----------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
 
     def __init__(self, index: int):
         self.index, self.rows, self.proc = index, [], None
@@ -56,7 +71,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -66,32 +81,32 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), line.strip()))
 
-    def stop(self, t0: float, t1: float) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for _, r in self.rows[-3:]]
-        sm, mx, reasons = [], [], set()
-        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for r in rows:
+    def window(self, t0: float, t1: float):
+        sm, mx, pw, reasons = [], [], [], set()
+        for t, r in self.rows:
+            if not (t0 <= t <= t1):
+                continue
             f = [x.strip() for x in r.split(",")]
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
             except Exception:
                 continue
-            for name, v in zip(names, f[3:7]):
+            for name, v in zip(self.NAMES, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
 
 
 # ----------------------------------------------------------------------------------------------- CPU arm
-def cpu_port_throughput(seconds: float = 10.0, envs: int = 1 << 18, threads: int = 0):
-    """The C oracle (a port of the reference's step) on the host cores, same workload shape: 8 frames per
-    env per call, per-frame int8 actions, Philox resets.  Returns (env-steps/s, threads, sample description)."""
+def cpu_port_run(steps: int, warmup: int, envs: int = 1 << 18, threads: int = 0, seconds: float = 0.0):
+    """The C oracle (a port of the reference's step) on the host cores, same workload shape: 8 frames per env per
+    call, per-frame int8 actions, Philox resets.  Either `steps` calls or as many as fit in `seconds`."""
     import numpy as np
     from oracle import oracle
     threads = threads or len(os.sched_getaffinity(0))
@@ -100,45 +115,33 @@ def cpu_port_throughput(seconds: float = 10.0, envs: int = 1 << 18, threads: int
     cur = np.zeros(envs, np.int32)
     acts = rng.integers(0, 4, (FRAMES_PER_STEP, envs)).astype(np.int8)
     kw = dict(actions=acts, reset_cursor=cur, seed=1234, nthreads=threads, want=("reward", "done", "score", "game_over"))
-    oracle.run_frames(st, sc, FRAMES_PER_STEP, **kw)                 # warm-up (thread pool, page faults)
+    for _ in range(max(1, warmup)):
+        oracle.run_frames(st, sc, FRAMES_PER_STEP, **kw)
     calls, t0 = 0, time.perf_counter()
     while True:
         oracle.run_frames(st, sc, FRAMES_PER_STEP, **kw)
         calls += 1
         dt = time.perf_counter() - t0
-        if dt >= seconds:
+        if (seconds > 0 and dt >= seconds) or (seconds <= 0 and calls >= steps):
             break
-    return envs * FRAMES_PER_STEP * calls / dt, threads, f"{envs} envs x {FRAMES_PER_STEP} frames x {calls} calls ({dt:.1f} s)"
+    return envs * FRAMES_PER_STEP * calls / dt, threads, dt, calls, envs
 
 
 def run_reference_arm(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    import numpy as np
-    from oracle import oracle
-    threads = len(os.sched_getaffinity(0))
-    envs = 1 << 18
-    rng = np.random.default_rng(0)
-    st, sc = oracle.initial_state(envs)
-    cur = np.zeros(envs, np.int32)
-    acts = rng.integers(0, 4, (FRAMES_PER_STEP, envs)).astype(np.int8)
-    kw = dict(actions=acts, reset_cursor=cur, seed=1234, nthreads=threads, want=("reward", "done", "score", "game_over"))
-    for _ in range(args.warmup):
-        oracle.run_frames(st, sc, FRAMES_PER_STEP, **kw)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        oracle.run_frames(st, sc, FRAMES_PER_STEP, **kw)
-    dt = time.perf_counter() - t0
-    v = envs * FRAMES_PER_STEP * args.steps / dt
-    sample = f"{envs} envs x {FRAMES_PER_STEP} frames per step (bounded sample of the {ENVS_PER_GPU}-env-per-GPU workload)"
+    v, threads, dt, calls, envs = cpu_port_run(args.steps, min(args.warmup, 5))
+    sample = (f"{envs} envs x {FRAMES_PER_STEP} frames per step, {calls} steps: a bounded sample of the "
+              f"{ENVS_PER_GPU}-envs-per-GPU workload; C port of the reference step (oracle/ah_oracle.c, bit-exact vs the "
+              "Python reference), OpenMP over all host threads")
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": calls,
+        "warmup": min(args.warmup, 5), "ms_per_step": 1e3 * dt / calls, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args.gpus), "sample": sample},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
     }))
 
 
@@ -152,13 +155,14 @@ def workload_name(gpus: int) -> str:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=260)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -205,27 +209,45 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-        time.sleep(0.25)
+        time.sleep(0.3)
     barrier()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.time()
-    ev[0].record(stream)
+    ev0.record(stream)
     for i in range(args.steps):
         one_step(i)
-        ev[i + 1].record(stream)
+    ev1.record(stream)
     barrier()
     t_wall1 = time.time()
-    total_ms = ev[0].elapsed_time(ev[-1])
+    total_ms = ev0.elapsed_time(ev1)
     if world > 1:
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
-    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    value = world * n * K * args.steps / (total_ms * 1e-3)
 
-    # kernel-only duration (N = 1: step == one kernel launch; events sit on the launching stream)
+    clocks = None
+    if rank == 0:
+        clocks = sampler.window(t_wall0, t_wall1)
+        clocks["window"] = "timed region"
+    if world == 1 and (clocks is None or clocks["samples"] < 3):
+        # the timed region was shorter than nvidia-smi's sampling period: keep the same launches going for ~1.2 s
+        # (untimed) so that the recorded clocks are clocks UNDER THIS LOAD, and say so
+        t0 = time.time()
+        while time.time() - t0 < 1.2:
+            for i in range(50):
+                one_step(i)
+            torch.cuda.synchronize(dev)
+        clocks = sampler.window(t0 + 0.1, time.time())
+        clocks["window"] = "1.2 s of the same launches right after the (shorter) timed region"
+    if rank == 0:
+        sampler.stop()
+
+    # ---- kernel-only duration of the dominant kernel (CUDA events around each launch, on the launching stream)
     kernel_ms = None
     if world == 1:
-        kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        reps = min(args.steps, 200)
+        kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
         for i, (a, b) in enumerate(kev):
             a.record(stream)
             env.step(acts[i % n_act], K=K, out=out)
@@ -233,12 +255,16 @@ def main():
         torch.cuda.synchronize(dev)
         kernel_ms = sum(a.elapsed_time(b) for a, b in kev) / len(kev)
 
-    value = world * n * K * args.steps / (total_ms * 1e-3)
-
-    # ---- e2e: host actions in, host results out, copies inside the timed region (double-buffered streams)
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(env, dev, n, K, max(3, min(W, 10)), max(10, min(args.steps, 50)), world)
+        e2e = run_e2e(env, dev, n, K, 5, max(10, min(args.steps, 40)), world)
+
+    extras = {}
+    if world == 1 and not args.no_extras:
+        extras["rollout_k1"] = run_rollout_k1(env, dev, n)
+        extras["philox_sim_k8"] = run_philox_sim(env, dev, n, K)
+        extras["ppo_rollout_cfg5"] = run_ppo_rollout(dev)
+        extras["fp64_validation_cfg2"] = run_fp64(dev)
 
     if rank != 0:
         if world > 1:
@@ -246,41 +272,121 @@ def main():
         return
 
     hbm_peak, peak_src, sm_max = peaks()
-    # algorithmic bytes per launch: state 68 B read + 68 B written per env; per frame 1 B action,
-    # 4 B reward, 1 B done, 1 B score, 1 B game_over; 32 B obs_next per env per launch
-    state_b = 3 * 16 + 4 + 16
-    bytes_per_launch = n * (2 * state_b + 32 + K * (1 + 4 + 1 + 1 + 1))
-    info = env.launch_info()
+    bytes_per_launch = n * (2 * STATE_BYTES + 32 + K * (1 + 4 + 1 + 1 + 1))
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(world), "envs_per_gpu": n, "frames_per_step": K,
                    "sub_updates_per_sec": 3 * value,
-                   "l2": "no flush: each step touches %.0f MB of distinct HBM lines (> 126 MB L2)" % (bytes_per_launch / 1e6 - 0),
-                   "launch": info},
+                   "l2": "no flush: each step touches %.0f MB of distinct HBM lines (> 126 MB L2)" % (bytes_per_launch / 1e6),
+                   "launch": env.launch_info()},
         "gpu_launches": args.steps * (1 if world == 1 else 2),
         "clocks": clocks,
     }
     if e2e is not None:
         line["e2e"] = e2e
     if kernel_ms is not None:
-        achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic_step_kernel.json")
-        if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
-        line["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                            "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                            "kernel": "ah::step_kernel<float,1>", "kernel_ms": kernel_ms,
-                            "algorithmic_bytes_per_launch": bytes_per_launch,
-                            "bytes_per_env_step": bytes_per_launch / (n * K)}
+        sm_mhz = (clocks or {}).get("sm_mhz") or sm_max
+        lane_peak = 148 * 128 * sm_mhz * 1e6 / 1e9               # Glane-op/s at the SM clock seen under this load
+        lane_ach = LANE_OPS_PER_ENV_STEP * n * K / (kernel_ms * 1e-3) / 1e9
+        hbm_ach = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
+        line["roofline"] = {
+            "bound": "fp32", "achieved": lane_ach, "peak": lane_peak, "unit": "Glane-op/s", "frac": lane_ach / lane_peak,
+            "traffic": profile_fact("dram_bytes_per_launch"),
+            "kernel": "ah::step_kernel<float, discrete, LEAN>", "kernel_ms": kernel_ms,
+            "note": "K=8 fused frames: bound by FP32/ALU-pipe issue, not HBM (north_star: the slower of FP32 peak and "
+                    "state bytes over HBM bandwidth). achieved = 254 algorithmic lane-ops/env-step x env-steps/s; "
+                    "peak = 148 SMs x 128 FP32 lanes x SM clock under load. The HBM view of the same launch follows.",
+            "algorithmic_lane_ops_per_env_step": LANE_OPS_PER_ENV_STEP,
+            "executed_warp_insts_per_warp_frame": profile_fact("warp_insts_per_warp_frame"),
+            "alu_pipe_active_pct_ncu": profile_fact("alu_pipe_active_pct"),
+            "issue_active_pct_ncu": profile_fact("issue_active_pct"),
+            "hbm_achieved": hbm_ach, "hbm_peak": hbm_peak, "hbm_unit": "GB/s", "hbm_frac": hbm_ach / hbm_peak,
+            "hbm_peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
+            "bytes_per_env_step": bytes_per_launch / (n * K),
+        }
     if not args.no_cpu_baseline and world == 1:
-        v, cores, sample = cpu_port_throughput(args.cpu_seconds)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        v, cores, dt, calls, envs = cpu_port_run(0, 1, seconds=args.cpu_seconds)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"{envs} envs x {FRAMES_PER_STEP} frames x {calls} calls ({dt:.1f} s), OpenMP"}
+    if extras:
+        line["extras"] = extras
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def _time_loop(dev, fn, warm, reps):
+    import torch
+    for i in range(warm):
+        fn(i)
+    torch.cuda.synchronize(dev)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s = torch.cuda.current_stream(dev)
+    a.record(s)
+    for i in range(reps):
+        fn(i)
+    b.record(s)
+    torch.cuda.synchronize(dev)
+    return a.elapsed_time(b) / reps
+
+
+def run_rollout_k1(env, dev, n):
+    """K = 1: one policy decision per launch, every output written -- the HBM-bound mode a PPO collector uses."""
+    import torch
+    out = env.make_outputs(1, ("reward", "done", "score", "game_over", "obs_next"))
+    acts = [torch.randint(0, 4, (n,), dtype=torch.int8, device=dev) for _ in range(4)]
+    ms = _time_loop(dev, lambda i: env.step(acts[i % 4], K=1, out=out), 20, 200)
+    hbm_peak, src, _ = peaks()
+    b = n * (2 * STATE_BYTES + 32 + (1 + 4 + 1 + 1 + 1))
+    ach = b / (ms * 1e-3) / 1e9
+    return {"value": n / (ms * 1e-3), "unit": UNIT, "kernel_ms": ms,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                         "traffic": None, "algorithmic_bytes_per_launch": b, "bytes_per_env_step": b / n}}
+
+
+def run_philox_sim(env, dev, n, K):
+    """Pure simulation: actions drawn in-kernel (Philox), only the final observation written."""
+    out = env.make_outputs(K, ("obs_next",))
+    ms = _time_loop(dev, lambda i: env.step(None, K=K, out=out), 10, 100)
+    return {"value": n * K / (ms * 1e-3), "unit": UNIT, "kernel_ms": ms}
+
+
+def run_ppo_rollout(dev):
+    """BASELINE config 5: 65,536 envs x 128 frames, reference-shaped actor MLP, sampling and env.step in one CUDA graph."""
+    import torch
+    from air_hockey_training_environment_b200 import BatchedAirHockey
+    from air_hockey_training_environment_b200.rollout import RolloutCollector
+    n, T = 65536, 128
+    env = BatchedAirHockey(n, dtype=torch.float32, device=dev, seed=7)
+    col = RolloutCollector(env, T, use_graph=True, seed=7)
+    for _ in range(3):
+        col.collect()
+    torch.cuda.synchronize(dev)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    reps = 10
+    for _ in range(reps):
+        col.collect()
+    b.record()
+    torch.cuda.synchronize(dev)
+    ms = a.elapsed_time(b) / reps
+    return {"value": n * T / (ms * 1e-3), "unit": UNIT, "ms_per_rollout": ms, "envs": n, "frames": T,
+            "note": "policy forward + multinomial sampling + env.step per frame, one CUDA graph per rollout"}
+
+
+def run_fp64(dev):
+    """BASELINE config 2 shape (4,096 envs, FP64 validation build), timed: 1,000 frames in launches of 100."""
+    import torch
+    from air_hockey_training_environment_b200 import BatchedAirHockey
+    n = 4096
+    env = BatchedAirHockey(n, dtype=torch.float64, device=dev, seed=3)
+    out = env.make_outputs(100, ("reward", "done", "score", "game_over", "obs_next"))
+    acts = torch.randint(0, 4, (100, n), dtype=torch.int8, device=dev)
+    ms = _time_loop(dev, lambda i: env.step(acts, K=100, out=out), 2, 10)
+    return {"value": n * 100 / (ms * 1e-3), "unit": UNIT, "ms_per_100_frames": ms, "envs": n,
+            "parity": "bit-exact vs the reference (tests/test_gpu_parity.py)"}
 
 
 def run_e2e(env, dev, n, K, warm, steps, world):
@@ -292,7 +398,7 @@ def run_e2e(env, dev, n, K, warm, steps, world):
     slots = 2
     h_act = [torch.randint(0, 4, (K, n), dtype=torch.int8).pin_memory() for _ in range(slots)]
     d_act = [torch.empty(K, n, dtype=torch.int8, device=dev) for _ in range(slots)]
-    outs = [env.make_outputs(K, ("reward", "done", "obs_next")) for _ in range(slots)]
+    outs = [env.make_outputs(K, ("reward", "done", "score", "game_over", "obs_next")) for _ in range(slots)]
     h_out = [(torch.empty(K, n, dtype=torch.float32).pin_memory(), torch.empty(K, n, dtype=torch.uint8).pin_memory(),
               torch.empty(n, 8, dtype=torch.float32).pin_memory()) for _ in range(slots)]
     s_in, s_run, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
@@ -338,8 +444,8 @@ def run_e2e(env, dev, n, K, warm, steps, world):
     h2d = K * n
     d2h = K * n * 4 + K * n + n * 8 * 4
     return {"value": world * n * K * steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-            "steps": steps, "note": "pinned host buffers, 2 slots / 3 streams; timed with the host clock around a "
-                                    "barrier + synchronize on both sides"}
+            "steps": steps, "note": "pinned host buffers, 2 slots / 3 streams (copies overlap the kernel); timed with the "
+                                    "host clock around a barrier + synchronize on both sides; PCIe-bound"}
 
 
 if __name__ == "__main__":
