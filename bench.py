@@ -188,16 +188,26 @@ def main():
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     n_act = 4                                                    # rotate several action tensors
     acts = [torch.randint(0, 4, (K, n), dtype=torch.int8, device=dev, generator=gen) for _ in range(n_act)]
-    stats = torch.zeros(16, dtype=torch.int64, device=dev)
+    stats = [torch.zeros(16, dtype=torch.int64, device=dev) for _ in range(4)]
+    pending = [None] * 4
     stream = torch.cuda.current_stream(dev)
 
     def one_step(i: int):
         env.step(acts[i % n_act], K=K, out=out)
-        if world > 1:                                            # per-rollout episode/score statistics
-            env.stats_tensor(clear=True, out=stats)
-            dist.all_reduce(stats)
+        if world > 1:
+            # per-rollout episode/score statistics: 128 B summed over NVLink.  Issued asynchronously (NCCL's stream
+            # waits for the step kernel; the next step's kernel does not wait for the all-reduce), 4 rotating buffers.
+            j = i % 4
+            if pending[j] is not None:
+                pending[j].wait()
+            env.stats_tensor(clear=True, out=stats[j])
+            pending[j] = dist.all_reduce(stats[j], async_op=True)
 
     def barrier():
+        for j in range(4):
+            if pending[j] is not None:
+                pending[j].wait()
+                pending[j] = None
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
@@ -230,16 +240,18 @@ def main():
     if rank == 0:
         clocks = sampler.window(t_wall0, t_wall1)
         clocks["window"] = "timed region"
-    if world == 1 and (clocks is None or clocks["samples"] < 3):
-        # the timed region was shorter than nvidia-smi's sampling period: keep the same launches going for ~1.2 s
-        # (untimed) so that the recorded clocks are clocks UNDER THIS LOAD, and say so
+    if total_ms < 600.0:
+        # the timed region was shorter than a few nvidia-smi sampling periods: keep the same launches going for
+        # ~1.2 s (untimed; the same iteration count on every rank) so that the recorded clocks are clocks UNDER THIS
+        # LOAD, and say so
+        iters = int(1200.0 / (total_ms / args.steps)) + 1
         t0 = time.time()
-        while time.time() - t0 < 1.2:
-            for i in range(50):
-                one_step(i)
-            torch.cuda.synchronize(dev)
-        clocks = sampler.window(t0 + 0.1, time.time())
-        clocks["window"] = "1.2 s of the same launches right after the (shorter) timed region"
+        for i in range(iters):
+            one_step(i)
+        barrier()
+        if rank == 0:
+            clocks = sampler.window(t0 + 0.1, time.time())
+            clocks["window"] = "1.2 s of the same launches right after the (shorter) timed region"
     if rank == 0:
         sampler.stop()
 
@@ -281,7 +293,7 @@ def main():
                    "sub_updates_per_sec": 3 * value,
                    "l2": "no flush: each step touches %.0f MB of distinct HBM lines (> 126 MB L2)" % (bytes_per_launch / 1e6),
                    "launch": env.launch_info()},
-        "gpu_launches": args.steps * (1 if world == 1 else 2),
+        "gpu_launches": args.steps * (1 if world == 1 else 2),   # step kernel (+ stats copy kernel when N > 1), per rank
         "clocks": clocks,
     }
     if e2e is not None:
