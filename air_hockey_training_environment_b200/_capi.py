@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libah_b200.so")
+LIB_PATH = os.environ.get("AH_B200_LIB", os.path.join(HERE, "libah_b200.so"))   # override: tuning experiments only
 
 AH_OK, AH_EINVAL, AH_ECUDA, AH_ENOMEM, AH_EAGENT, AH_ESTATE = 0, -1, -2, -3, -4, -5
 AH_F32, AH_F64 = 0, 1

@@ -130,14 +130,27 @@ struct StepArgs {
 struct BlockStats {
     int v[AH_NSTATS];                 // 32-bit: native shared-memory atomic add (a 64-bit one is a CAS loop)
     unsigned long long len_sq;        // the only sum that can outgrow 32 bits within one block and launch
+    int warps_done;                   // the last warp of the block to finish flushes the block's statistics
 };
 
-__device__ __forceinline__ void stat_add(BlockStats& bs, int which, int x) { atomicAdd(&bs.v[which], x); }
+// `red.shared.add` issued by exactly the lanes that saw the event.  (A plain atomicAdd makes the compiler wrap every
+// call in a vote / REDUX / elect-one-lane sequence -- ~15 instructions executed by the whole warp -- to save an
+// atomic that, for these rare events, is a single lane's anyway.)
+__device__ __forceinline__ void stat_add(BlockStats& bs, int which, int x) {
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(&bs.v[which]);
+    asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(addr), "r"(x) : "memory");
+}
 
-constexpr int kThreads = 256;
+#ifndef AH_THREADS
+#define AH_THREADS 256
+#endif
+#ifndef AH_OCC_F32
+#define AH_OCC_F32 4
+#endif
+constexpr int kThreads = AH_THREADS;
 constexpr int kMaxBlocks = 1 << 20;
 
-template <typename R> struct Occ { static constexpr int blocks = 4; };
+template <typename R> struct Occ { static constexpr int blocks = AH_OCC_F32; };
 template <> struct Occ<double> { static constexpr int blocks = 2; };
 
 // Output modes (compile-time, chosen by the host from which pointers were given):
@@ -151,14 +164,24 @@ template <typename R, int ACT, int MODE>   // ACT: 1 discrete, 2 continuous, 3 p
 __global__ void __launch_bounds__(kThreads, Occ<R>::blocks) step_kernel(const StepArgs<R> a) {
     using V2 = typename std::conditional<sizeof(R) == 4, float2, double2>::type;
     __shared__ BlockStats bs;
+    // discrete action -> position nudge (airhockey.py:74-84) as a 5-entry shared table: one clamp + one LDS.64
+    // instead of four compares and four selects per frame.  Entry 4 = "any other int": no nudge.
+    __shared__ V2 s_nudge[8];
     if (threadIdx.x < AH_NSTATS) bs.v[threadIdx.x] = 0;
-    if (threadIdx.x == 0) bs.len_sq = 0ull;
+    if (threadIdx.x == 0) { bs.len_sq = 0ull; bs.warps_done = 0; }
+    if (threadIdx.x < 8) {
+        const int t = threadIdx.x;
+        s_nudge[t] = V2{t == 3 ? K<R>::step : (t == 2 ? -K<R>::step : R(0)), t == 0 ? K<R>::step : (t == 1 ? -K<R>::step : R(0))};
+    }
     __syncthreads();
 
     const uint32_t n = (uint32_t)a.n;                         // n < 2^31 (checked by ah_create)
     const uint32_t stride = gridDim.x * blockDim.x;
-    const unsigned long long frame0 = a.blk->frame;
-    const unsigned long long ring0 = a.blk->ring_appended;
+    // the device-side counters are read up front only by the variants that need them in the frame loop (Philox
+    // actions, ring append): a dependent L2 round-trip at the head of every thread is what the others avoid
+    unsigned long long frame0 = 0ull, ring0 = 0ull;
+    if (ACT == 3) frame0 = a.blk->frame;
+    if (MODE == MODE_GENERIC) ring0 = a.blk->ring_appended;
     const bool repeat = (a.action_kind == AH_ACT_DISCRETE_REPEAT) || (a.action_kind == AH_ACT_CONTINUOUS_REPEAT);
     const bool dot_fma = a.dot_fma != 0;
     const bool friction = (MODE == MODE_GENERIC) && (a.friction != 0);
@@ -172,6 +195,7 @@ __global__ void __launch_bounds__(kThreads, Occ<R>::blocks) step_kernel(const St
         // 10-goal flag carried into the frame (only reachable through injected state; see game.py:169-177)
         int go = (e.robot_score == 10) ? 1 : ((e.opp_score == 10) ? 2 : 0);
         int contacts_r = 0, contacts_o = 0;
+        bool speed_dirty = speed_out_of_limits<R>(e.pdx, e.pdy);   // only injected states can start out of limits
         // game_frames / reward_sum are not incremented per frame: frames-in-game = gf_base + frames done in this
         // launch, and the launch's reward sum is recovered from game_return (+ the returns of finished games)
         int gf_base = e.game_frames;
@@ -194,7 +218,8 @@ __global__ void __launch_bounds__(kThreads, Occ<R>::blocks) step_kernel(const St
                 ia = ia_next;
                 act_i8 += act_step;
                 if (k + 1 < K) ia_next = act_i8[i];
-                action_nudge<R>(ia, ax, ay);
+                const V2 nd = s_nudge[min((unsigned)ia, 4u)];
+                ax = nd.x; ay = nd.y;
             } else if (ACT == 2) {
                 ax = av_next.x; ay = av_next.y;
                 act_v2 += act_step;
@@ -204,16 +229,17 @@ __global__ void __launch_bounds__(kThreads, Occ<R>::blocks) step_kernel(const St
                 const uint32_t bid = (uint32_t)(f >> 6);
                 if (bid != ablock_id) { ablock = action_block(a.rs.seed, a.rs.env_id0 + (uint64_t)i, bid); ablock_id = bid; }
                 ia = action_from_block(ablock, (uint32_t)(f & 63u));
-                action_nudge<R>(ia, ax, ay);
+                const V2 nd = s_nudge[ia];
+                ax = nd.x; ay = nd.y;
             }
             // ---- robot.move(a): sub-update #1                      game.py:136 -> agent.py:32-36
             move_robot<R>(e, ACT == 2, ax, ay);
-            physics_tail<R>(e, dot_fma, friction, contacts_r, contacts_o);
+            physics_tail<R, false>(e, dot_fma, friction, speed_dirty, contacts_r, contacts_o);
             Obs<R> s0, s1;
             if (MODE == MODE_GENERIC && want_obs) s0 = get_state<R>(e, true);   // Observation.state      agent.py:61
             // ---- robot.step(a) -> self.move(a): sub-update #2      agent.py:64
             move_robot<R>(e, ACT == 2, ax, ay);
-            physics_tail<R>(e, dot_fma, friction, contacts_r, contacts_o);
+            physics_tail<R, false>(e, dot_fma, friction, speed_dirty, contacts_r, contacts_o);
             if (MODE == MODE_GENERIC && want_obs) s1 = get_state<R>(e, true);   // Observation.new_state  agent.py:67
             // ---- Rewards                                           agent.py:70-71
             int rw, sc; bool dn;
@@ -232,7 +258,7 @@ __global__ void __launch_bounds__(kThreads, Occ<R>::blocks) step_kernel(const St
             dones += dn ? 1 : 0;
             // ---- env.update_state(agent_name="computer"): sub-update #3   game.py:166
             computer_ai<R>(e);
-            physics_tail<R>(e, dot_fma, friction, contacts_r, contacts_o);
+            physics_tail<R, true>(e, dot_fma, friction, speed_dirty, contacts_r, contacts_o);
             // ---- outputs, straight into the caller's tensors
             if (MODE == MODE_LEAN) {
                 reward_k[i] = (R)rw; done_k[i] = dn ? 1 : 0; score_k[i] = (int8_t)sc; over_k[i] = (uint8_t)go;
@@ -267,6 +293,7 @@ __global__ void __launch_bounds__(kThreads, Occ<R>::blocks) step_kernel(const St
                 ret_credit += e.game_return;
                 gf_base = -(k + 1); e.game_return = 0;
                 env_reset<R>(e, true, a.rs, i, overflow);
+                speed_dirty = a.rs.table != nullptr;     // Philox draws are within the limits; table values may not be
                 go = 0;
             }
             if (MODE == MODE_GENERIC && a.obs_next && a.obs_next_per_frame)
@@ -285,36 +312,38 @@ __global__ void __launch_bounds__(kThreads, Occ<R>::blocks) step_kernel(const St
         store_env<R>(a.st, i, e);
     }
 
-    // ---- per-frame sums: warp reduction (REDUX), one shared atomic per warp; then one global atomic set per block
-    if (a.collect_stats) {
-        const int fs = __reduce_add_sync(0xffffffffu, frames);
-        const int rs = __reduce_add_sync(0xffffffffu, reward_sum);
-        const int rq = __reduce_add_sync(0xffffffffu, reward_sq);
-        const int dd = __reduce_add_sync(0xffffffffu, dones);
-        if ((threadIdx.x & 31) == 0) {
-            stat_add(bs, AH_STAT_DONES, dd);
-            stat_add(bs, AH_STAT_FRAMES, fs);
-            stat_add(bs, AH_STAT_REWARD_SUM, rs);
-            stat_add(bs, AH_STAT_REWARD_SQ_SUM, rq);
-        }
-        __syncthreads();
-        if (threadIdx.x < AH_NSTATS) {
-            const long long s = threadIdx.x == AH_STAT_GAME_LEN_SQ_SUM ? (long long)bs.len_sq : (long long)bs.v[threadIdx.x];
-            if (s != 0) atomicAdd(&a.blk->stats[threadIdx.x], (unsigned long long)s);
-        }
+    // ---- epilogue WITHOUT block barriers: warps finish at different times (contact / goal branches), so each warp
+    // folds its per-frame sums into the block's shared counters (REDUX + one shared red per value) and leaves; the
+    // LAST warp of the block to arrive flushes the block's statistics (<= 16 global atomics) and takes the launch
+    // ticket; the last block of the launch advances the device-side frame / ring counters (graph-capturable: no host
+    // value is baked into the launch).
+    const int fs = __reduce_add_sync(0xffffffffu, frames);
+    const int rs = __reduce_add_sync(0xffffffffu, reward_sum);
+    const int rq = __reduce_add_sync(0xffffffffu, reward_sq);
+    const int dd = __reduce_add_sync(0xffffffffu, dones);
+    const int lane = threadIdx.x & 31;
+    int arrived = 0;
+    if (lane == 0) {
+        stat_add(bs, AH_STAT_DONES, dd);
+        stat_add(bs, AH_STAT_FRAMES, fs);
+        stat_add(bs, AH_STAT_REWARD_SUM, rs);
+        stat_add(bs, AH_STAT_REWARD_SQ_SUM, rq);
+        __threadfence_block();
+        arrived = atomicAdd(&bs.warps_done, 1);
     }
-    // ---- the last block to finish advances the device-side counters (graph-capturable: no host value baked in)
-    __shared__ bool is_last;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        const unsigned tk = atomicAdd(&a.blk->ticket, 1u);
-        is_last = (tk == gridDim.x - 1);
+    arrived = __shfl_sync(0xffffffffu, arrived, 0);
+    if (arrived != (int)(blockDim.x >> 5) - 1) return;
+    __threadfence_block();
+    if (a.collect_stats && lane < AH_NSTATS) {                  // lane q flushes statistic q
+        const long long sv = lane == AH_STAT_GAME_LEN_SQ_SUM ? (long long)*(volatile unsigned long long*)&bs.len_sq
+                                                             : (long long)*(volatile int*)&bs.v[lane];
+        if (sv != 0) atomicAdd(&a.blk->stats[lane], (unsigned long long)sv);
     }
-    __syncthreads();
-    if (is_last && threadIdx.x == 0) {
-        a.blk->frame = frame0 + (unsigned long long)K;
-        if (a.ring_capacity > 0) a.blk->ring_appended = ring0 + (unsigned long long)K;
+    if (lane != 0) return;
+    __threadfence();
+    if (atomicAdd(&a.blk->ticket, 1u) == gridDim.x - 1) {
+        a.blk->frame = *(volatile unsigned long long*)&a.blk->frame + (unsigned long long)K;
+        if (a.ring_capacity > 0) a.blk->ring_appended = *(volatile unsigned long long*)&a.blk->ring_appended + (unsigned long long)K;
         a.blk->ticket = 0;
         __threadfence();
     }
@@ -373,7 +402,8 @@ __global__ void update_state_kernel(StatePtrs<R> st, int64_t n, const void* acti
         computer_ai<R>(e);
     }
     int c0 = 0, c1 = 0;
-    physics_tail<R>(e, dot_fma != 0, friction != 0, c0, c1);
+    bool dirty = true;
+    physics_tail<R, true>(e, dot_fma != 0, friction != 0, dirty, c0, c1);
     store_env<R>(st, i, e);
 }
 

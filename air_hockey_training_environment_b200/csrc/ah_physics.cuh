@@ -234,12 +234,19 @@ __device__ __forceinline__ void computer_ai(Env<R>& e) {
 // ---- the common tail of AirHockey.update_state  environment/airhockey.py:112-122 ----
 // The two contact tests (robot first, then opponent, :113-114) share ONE rarely-taken branch; inside it the
 // opponent's test is re-evaluated against the puck as the robot's response left it, as the reference does.
-template <typename R>
-__device__ __forceinline__ void physics_tail(Env<R>& e, bool dot_fma, bool friction, int& c_robot, int& c_opp) {
+//
+// Speed clamp (:117).  limit_puck_speed is idempotent and the puck's velocity changes only in a contact response,
+// in computerAI's nudge, or in a reset.  `speed_dirty` says "the velocity may be outside the limits": when it is
+// false and no contact happens, the clamp is a no-op and is skipped.  ALWAYS_LIMIT (the computer's sub-update,
+// whose nudge precedes it) clamps unconditionally.  Either way the result equals the reference's.
+template <typename R, bool ALWAYS_LIMIT>
+__device__ __forceinline__ void physics_tail(Env<R>& e, bool dot_fma, bool friction, bool& speed_dirty,
+                                             int& c_robot, int& c_opp) {
     R rdx_, rdy_, odx_, ody_;
     const R dr = contact_dist_sq<R>(e.px, e.py, e.rx, e.ry, dot_fma, rdx_, rdy_);
     R dq = contact_dist_sq<R>(e.px, e.py, e.ox, e.oy, dot_fma, odx_, ody_);
-    if (!(dr > K<R>::radius_sq) || !(dq > K<R>::radius_sq)) {                    // :210 (touching counts as contact)
+    const bool slow = !(dr > K<R>::radius_sq) || !(dq > K<R>::radius_sq) || (!ALWAYS_LIMIT && (speed_dirty || friction));
+    if (slow) {                                                                  // :210 (touching counts as contact)
         if (!(dr > K<R>::radius_sq)) {
             c_robot += 1;
             contact_response<R>(e.px, e.py, e.pdx, e.pdy, e.rx, e.ry, e.rdx, e.rdy, rdx_, rdy_, dr, dot_fma);
@@ -249,12 +256,25 @@ __device__ __forceinline__ void physics_tail(Env<R>& e, bool dot_fma, bool frict
             c_opp += 1;
             contact_response<R>(e.px, e.py, e.pdx, e.pdy, e.ox, e.oy, e.odx, e.ody, odx_, ody_, dq, dot_fma);
         }
+        if (!ALWAYS_LIMIT) {
+            if (friction) friction_on_puck<R>(e.pdx, e.pdy);
+            limit_puck_speed<R>(e.pdx, e.pdy);                                   // :117
+        }
     }
-    if (friction) friction_on_puck<R>(e.pdx, e.pdy);
-    limit_puck_speed<R>(e.pdx, e.pdy);                                           // :117
+    if (ALWAYS_LIMIT) {
+        if (friction) friction_on_puck<R>(e.pdx, e.pdy);
+        limit_puck_speed<R>(e.pdx, e.pdy);                                       // :117
+    }
+    speed_dirty = false;
     puck_update<R>(e.px, e.py, e.pdx, e.pdy);                                    // :118
     mallet_update<R>(e.rx, e.ry, e.rdx, e.rdy, K<R>::robot_lo, K<R>::robot_hi);  // :121-122
     mallet_update<R>(e.ox, e.oy, e.odx, e.ody, K<R>::opp_lo, K<R>::opp_hi);
+}
+
+// true when limit_puck_speed would change the velocity
+template <typename R>
+__device__ __forceinline__ bool speed_out_of_limits(R pdx, R pdy) {
+    return !(Math<R>::abs_(pdx) <= K<R>::speed) || !(pdy <= K<R>::speed) || !(pdy >= -K<R>::speed);
 }
 
 // ---- AirHockey.get_state + serialize_state  airhockey.py:136-147, puck.py:120-133, helpers.py:72-81 ----
