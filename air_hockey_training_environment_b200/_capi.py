@@ -21,7 +21,7 @@ STAT_NAMES = ("frames", "robot_goals", "opponent_goals", "robot_wins", "opponent
 
 # every symbol include/ah_b200.h declares (tests/test_capi_symbols.py checks header <-> library <-> this list)
 SYMBOLS = ("ah_strerror", "ah_abi_version", "ah_last_cuda_error", "ah_create", "ah_destroy", "ah_bind_state",
-           "ah_init_state", "ah_reset", "ah_update_state", "ah_get_state", "ah_update_score", "ah_rewards", "ah_step", "ah_stats",
+           "ah_init_state", "ah_reset", "ah_update_state", "ah_get_state", "ah_update_score", "ah_rewards", "ah_step", "ah_pack_host", "ah_stats",
            "ah_set_counters", "ah_get_counters", "ah_launch_info", "ah_selftest_nofma")
 
 
@@ -92,6 +92,8 @@ def lib() -> C.CDLL:
     L.ah_rewards.argtypes = [vp, vp, vp, vp, vp]
     L.ah_step.restype = i32
     L.ah_step.argtypes = [vp, C.POINTER(AhStepIO), i32, vp]
+    L.ah_pack_host.restype = i32
+    L.ah_pack_host.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp]
     L.ah_stats.restype = i32
     L.ah_stats.argtypes = [vp, vp, i32, vp]
     L.ah_set_counters.restype = i32

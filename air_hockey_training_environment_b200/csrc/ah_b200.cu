@@ -444,6 +444,23 @@ __global__ void rewards_kernel(StatePtrs<R> st, int64_t n, int dot_fma, R* rewar
     if (done) done[i] = dn ? 1 : 0;
 }
 
+// host-transfer packing (see ah_pack_host in include/ah_b200.h): 4 envs per thread, 128-bit loads of the rewards
+template <typename R>
+__global__ void pack_host_kernel(int64_t n, int K, const R* __restrict__ reward, const uint8_t* __restrict__ done,
+                                 const R* __restrict__ obs, uint8_t* __restrict__ events, short4* __restrict__ pos,
+                                 float4* __restrict__ vel) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int k = 0; k < K; ++k) {
+        const int64_t row = (int64_t)k * n + i;
+        const int rw = (int)reward[row] + 4;
+        events[row] = (uint8_t)((rw & 15) | ((done[row] ? 1 : 0) << 4));
+    }
+    const R* o = obs + 8 * i;
+    pos[i] = make_short4((short)o[0], (short)o[1], (short)o[2], (short)o[3]);
+    vel[i] = make_float4((float)o[4], (float)o[5], (float)o[6], (float)o[7]);
+}
+
 __global__ void stats_copy_kernel(DevBlock* blk, int64_t* out, int clear) {
     const int q = threadIdx.x;
     if (q < AH_NSTATS) {
@@ -714,6 +731,17 @@ int ah_step(ah_env* env, const ah_step_io* io, int K, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     if (env->dtype == AH_F32) return launch_step<float>(env, io, K, s);
     return launch_step<double>(env, io, K, s);
+}
+
+int ah_pack_host(ah_env* env, int K, const void* d_reward, const uint8_t* d_done, const void* d_obs_next,
+                 uint8_t* d_events, int16_t* d_obs_pos, float* d_obs_vel, void* stream) {
+    if (!env || K < 1 || !d_reward || !d_done || !d_obs_next || !d_events || !d_obs_pos || !d_obs_vel) return AH_EINVAL;
+    if (!aligned16(d_obs_vel) || (reinterpret_cast<uintptr_t>(d_obs_pos) & 7u)) return AH_EINVAL;
+    DeviceGuard g(env->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    AH_DISPATCH(env, (ah::pack_host_kernel<float><<<small_grid(env->n), 256, 0, s>>>(env->n, K, (const float*)d_reward, d_done, (const float*)d_obs_next, d_events, (short4*)d_obs_pos, (float4*)d_obs_vel)),
+                (ah::pack_host_kernel<double><<<small_grid(env->n), 256, 0, s>>>(env->n, K, (const double*)d_reward, d_done, (const double*)d_obs_next, d_events, (short4*)d_obs_pos, (float4*)d_obs_vel)));
+    AH_LAUNCH_RC(env);
 }
 
 int ah_stats(ah_env* env, int64_t* d_out, int clear, void* stream) {

@@ -1,0 +1,107 @@
+"""Host-buffer front end: step the games from HOST action buffers and get the results back on the HOST.
+
+This is the call a CPU-side consumer of the environment makes (the reference's own loop lives on the host:
+game.py:133-177).  On this path PCIe, not the kernel, is the bound, so the results cross the bus in a compact,
+lossless encoding (``ah_pack_host`` in include/ah_b200.h): per frame one byte per env (reward + done), per step the
+observation as 4 x int16 locations (they are int()-truncated in the reference, airhockey.py:136-147) + 4 x float32
+velocities -- 33 B/env at K = 8 instead of 72.  Copies are staged through pinned buffers on dedicated streams and
+double-buffered, so step i's device->host copy overlaps step i+1's kernel and step i+2's host->device copy.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional
+
+import torch
+
+from . import _capi
+from .env import BatchedAirHockey
+
+
+@dataclass
+class HostResult:
+    """Results of one step in pinned host memory (valid after ``wait()``)."""
+    events: torch.Tensor        # uint8 [K, n]: low nibble = reward + 4, bit 4 = done
+    obs_pos: torch.Tensor       # int16 [n, 4]: int(agent.x), int(agent.y), int(puck.x), int(puck.y)
+    obs_vel: torch.Tensor       # float32 [n, 4]: agent.dx, agent.dy, puck.dx, puck.dy
+    _event: Optional[torch.cuda.Event] = None
+
+    def wait(self) -> "HostResult":
+        if self._event is not None:
+            self._event.synchronize()
+        return self
+
+    @property
+    def reward(self) -> torch.Tensor:           # int8 [K, n]  (lib/rewards.py:118-142 returns integers)
+        return (self.events & 15).to(torch.int8) - 4
+
+    @property
+    def done(self) -> torch.Tensor:             # bool [K, n]
+        return (self.events >> 4).to(torch.bool)
+
+    @property
+    def obs(self) -> torch.Tensor:              # float32 [n, 8] in the reference's layout
+        return torch.cat([self.obs_pos.to(torch.float32), self.obs_vel], dim=1)
+
+
+class HostStepper:
+    """``submit(actions_host)`` enqueues H2D -> fused step -> pack -> D2H for one step and returns immediately;
+    the returned ``HostResult`` is complete after ``wait()``.  ``slots`` steps can be in flight."""
+
+    def __init__(self, env: BatchedAirHockey, K: int = 8, slots: int = 3):
+        self.env, self.K, self.slots = env, int(K), int(slots)
+        n, dev = env.n, env.device
+        self._lib = _capi.lib()
+        self.d_act = [torch.empty(K, n, dtype=torch.int8, device=dev) for _ in range(slots)]
+        self.outs = [env.make_outputs(K, ("reward", "done", "score", "game_over", "obs_next")) for _ in range(slots)]
+        self.d_events = [torch.empty(K, n, dtype=torch.uint8, device=dev) for _ in range(slots)]
+        self.d_pos = [torch.empty(n, 4, dtype=torch.int16, device=dev) for _ in range(slots)]
+        self.d_vel = [torch.empty(n, 4, dtype=torch.float32, device=dev) for _ in range(slots)]
+        self.h = [HostResult(torch.empty(K, n, dtype=torch.uint8).pin_memory(),
+                             torch.empty(n, 4, dtype=torch.int16).pin_memory(),
+                             torch.empty(n, 4, dtype=torch.float32).pin_memory()) for _ in range(slots)]
+        self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
+        self.e_in = [torch.cuda.Event() for _ in range(slots)]
+        self.e_run = [torch.cuda.Event() for _ in range(slots)]
+        self.e_out: List[Optional[torch.cuda.Event]] = [None] * slots
+        self._i = 0
+        self.h2d_bytes_per_step = K * n
+        self.d2h_bytes_per_step = K * n + n * 4 * 2 + n * 4 * 4
+
+    def submit(self, actions_host: torch.Tensor) -> HostResult:
+        """actions_host: int8 [K, n] CPU tensor (pinned for an asynchronous copy)."""
+        K, n, s = self.K, self.env.n, self._i % self.slots
+        self._i += 1
+        if actions_host.dtype != torch.int8 or tuple(actions_host.shape) != (K, n) or actions_host.device.type != "cpu":
+            raise ValueError(f"actions_host must be an int8 [{K}, {n}] CPU tensor")
+        env = self.env
+        with torch.cuda.stream(self.s_in):
+            self.s_in.wait_event(self.e_run[s])               # the slot's previous kernel has consumed its actions
+            self.d_act[s].copy_(actions_host, non_blocking=True)
+            self.e_in[s].record(self.s_in)
+        with torch.cuda.stream(self.s_run):
+            self.s_run.wait_event(self.e_in[s])
+            if self.e_out[s] is not None:
+                self.s_run.wait_event(self.e_out[s])          # the slot's previous results have left the device
+            o = self.outs[s]
+            env.step(self.d_act[s], K=K, out=o)
+            _capi.check(self._lib.ah_pack_host(env._h, K, o.reward.data_ptr(), o.done.data_ptr(), o.obs_next.data_ptr(),
+                                               self.d_events[s].data_ptr(), self.d_pos[s].data_ptr(),
+                                               self.d_vel[s].data_ptr(), self.s_run.cuda_stream), "ah_pack_host", env._h)
+            self.e_run[s].record(self.s_run)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(self.e_run[s])
+            h = self.h[s]
+            h.events.copy_(self.d_events[s], non_blocking=True)
+            h.obs_pos.copy_(self.d_pos[s], non_blocking=True)
+            h.obs_vel.copy_(self.d_vel[s], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.s_out)
+            self.e_out[s] = ev
+            h._event = ev
+        return h
+
+    def drain(self) -> None:
+        for ev in self.e_out:
+            if ev is not None:
+                ev.synchronize()

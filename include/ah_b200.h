@@ -173,6 +173,17 @@ int ah_rewards(ah_env* env, void* d_reward, int8_t* d_score, uint8_t* d_done, vo
  *   update_state("computer"); 10-goal game over.            1 <= K <= 4096 */
 int ah_step(ah_env* env, const ah_step_io* io, int K, void* stream);
 
+/* Compact, lossless host-transfer encoding of one step's results (for callers that consume them on the HOST, where
+ * PCIe, not the kernel, is the bound).  Inputs are the device outputs of ah_step:
+ *   reward real [K][n] (integer-valued, -4..6: lib/rewards.py:118-142), done u8 [K][n], obs_next real [n][8].
+ * Outputs (device, then copied to the host by the caller):
+ *   events   u8    [K][n]   low nibble = reward + 4, bit 4 = done
+ *   obs_pos  int16 [n][4]   the int()-truncated agent / puck locations of the observation (airhockey.py:136-147)
+ *   obs_vel  f32   [n][4]   agent / puck velocities, rounded to binary32
+ * 33 bytes instead of 72 per env for K = 8. */
+int ah_pack_host(ah_env* env, int K, const void* d_reward, const uint8_t* d_done, const void* d_obs_next,
+                 uint8_t* d_events, int16_t* d_obs_pos, float* d_obs_vel, void* stream);
+
 /* Copy the int64[AH_NSTATS] statistics block to a caller device buffer, optionally clearing it. */
 int ah_stats(ah_env* env, int64_t* d_out, int clear, void* stream);
 

@@ -261,3 +261,27 @@ def test_full_size_properties_1m_envs_fp32_k8():
     assert torch.equal(o[:, 0:4], o[:, 0:4].trunc())     # positions are int()-truncated in the observation
     rate = (st["robot_goals"] + st["opponent_goals"]) / st["frames"]
     assert 0.004 < rate < 0.012                          # reference: 7.9 goals per 1,000 frames
+
+
+# ---------------------------------------------------------------- host-buffer front end
+def test_host_stepper_round_trip_is_lossless():
+    from air_hockey_training_environment_b200.host import HostStepper
+    n, K = 8192, 8
+    env, twin = make_env(n, seed=31), make_env(n, seed=31)
+    for e in (env, twin):
+        e.step(None, K=300, out=e.make_outputs(300, ()))              # decorrelate, get some dones / goals
+    st = HostStepper(env, K=K, slots=3)
+    acts = [torch.randint(0, 4, (K, n), dtype=torch.int8).pin_memory() for _ in range(5)]
+    results = []
+    for a in acts:
+        r = st.submit(a).wait()
+        results.append((r.reward.clone(), r.done.clone(), r.obs.clone()))
+    st.drain()
+    dones = 0
+    for a, (rw, dn, ob) in zip(acts, results):
+        out = twin.step(a.cuda(), K=K)
+        assert torch.equal(rw.float(), out.reward.cpu()) and torch.equal(dn, out.done.cpu().bool())
+        assert torch.equal(ob, out.obs_next.cpu())
+        dones += int(dn.sum())
+    assert st.d2h_bytes_per_step == n * (K + 8 + 16) and st.h2d_bytes_per_step == n * K
+    assert dones > 0
