@@ -15,13 +15,14 @@ AH_F32, AH_F64 = 0, 1
 AH_AGENT_ROBOT, AH_AGENT_HUMAN, AH_AGENT_COMPUTER = 0, 1, 2
 AH_ACT_NONE, AH_ACT_DISCRETE, AH_ACT_CONTINUOUS, AH_ACT_PHILOX, AH_ACT_DISCRETE_REPEAT, AH_ACT_CONTINUOUS_REPEAT = range(6)
 AH_NSTATS = 16
+AH_ACTOR_NWEIGHTS = 114
 STAT_NAMES = ("frames", "robot_goals", "opponent_goals", "robot_wins", "opponent_wins", "dones", "reward_sum",
               "reward_sq_sum", "games", "game_len_sum", "game_len_sq_sum", "game_return_sum", "nonfinite",
               "reset_table_overflow", "contacts_robot", "contacts_opponent")
 
 # every symbol include/ah_b200.h declares (tests/test_capi_symbols.py checks header <-> library <-> this list)
 SYMBOLS = ("ah_strerror", "ah_abi_version", "ah_last_cuda_error", "ah_create", "ah_destroy", "ah_bind_state",
-           "ah_init_state", "ah_reset", "ah_update_state", "ah_get_state", "ah_update_score", "ah_rewards", "ah_step", "ah_pack_host", "ah_stats",
+           "ah_init_state", "ah_reset", "ah_update_state", "ah_get_state", "ah_update_score", "ah_rewards", "ah_step", "ah_pack_host", "ah_actor_sample", "ah_stats",
            "ah_set_counters", "ah_get_counters", "ah_launch_info", "ah_selftest_nofma")
 
 
@@ -94,6 +95,8 @@ def lib() -> C.CDLL:
     L.ah_step.argtypes = [vp, C.POINTER(AhStepIO), i32, vp]
     L.ah_pack_host.restype = i32
     L.ah_pack_host.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp]
+    L.ah_actor_sample.restype = i32
+    L.ah_actor_sample.argtypes = [vp, vp, vp, vp, vp, i32, vp]
     L.ah_stats.restype = i32
     L.ah_stats.argtypes = [vp, vp, i32, vp]
     L.ah_set_counters.restype = i32

@@ -444,6 +444,68 @@ __global__ void rewards_kernel(StatePtrs<R> st, int64_t n, int dot_fma, R* rewar
     if (done) done[i] = dn ? 1 : 0;
 }
 
+// ---- on-device action selection: the reference's discrete PPO actor + softmax sampling, one thread per env.
+// Weights (114 floats) are staged in shared memory once per block and read as warp-uniform LDS.128 broadcasts.
+template <typename R>
+__global__ void __launch_bounds__(256) actor_sample_kernel(int64_t n, const float* __restrict__ w, const R* __restrict__ obs,
+                                                           R* __restrict__ probs, int8_t* __restrict__ actions, int greedy,
+                                                           uint64_t seed, uint64_t env_id0, const DevBlock* blk) {
+    __shared__ __align__(16) float sw[128];
+    if (threadIdx.x < AH_ACTOR_NWEIGHTS) sw[threadIdx.x] = w[threadIdx.x];
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    using V = typename Vec4T<R>::type;
+    const V o0 = reinterpret_cast<const V*>(obs)[2 * i], o1 = reinterpret_cast<const V*>(obs)[2 * i + 1];
+    const float x[8] = {(float)o0.x, (float)o0.y, (float)o0.z, (float)o0.w, (float)o1.x, (float)o1.y, (float)o1.z, (float)o1.w};
+    const float *W1 = sw, *B1 = sw + 32, *W2 = sw + 36, *B2 = sw + 60, *W3 = sw + 66, *B3 = sw + 90, *W4 = sw + 94, *B4 = sw + 110;
+    float h1[4], h2[6], h3[4], z[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { float s = B1[j];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) s = fmaf(W1[j * 8 + c], x[c], s);
+        h1[j] = fmaxf(s, 0.f); }
+#pragma unroll
+    for (int j = 0; j < 6; ++j) { float s = B2[j];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) s = fmaf(W2[j * 4 + c], h1[c], s);
+        h2[j] = fmaxf(s, 0.f); }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { float s = B3[j];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) s = fmaf(W3[j * 6 + c], h2[c], s);
+        h3[j] = fmaxf(s, 0.f); }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { float s = B4[j];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) s = fmaf(W4[j * 4 + c], h3[c], s);
+        z[j] = s; }
+    const float m = fmaxf(fmaxf(z[0], z[1]), fmaxf(z[2], z[3]));
+    float p[4], sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { p[j] = __expf(z[j] - m); sum += p[j]; }
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) p[j] *= inv;
+    int act;
+    if (greedy) {
+        act = 0; float best = p[0];
+#pragma unroll
+        for (int j = 1; j < 4; ++j) if (p[j] > best) { best = p[j]; act = j; }
+    } else {
+        // uniform in [0,1) keyed on (seed, global env id), counter = (current frame, stream 2)
+        const unsigned long long f = blk->frame;
+        const uint64_t id = env_id0 + (uint64_t)i;
+        const Philox4 r = philox4x32_10((uint32_t)id, (uint32_t)(id >> 32), (uint32_t)f, 2u ^ ((uint32_t)(f >> 32) << 8),
+                                        (uint32_t)seed, (uint32_t)(seed >> 32));
+        const float u = (float)(r.x >> 8) * (1.0f / 16777216.0f);
+        const float c0 = p[0], c1 = c0 + p[1], c2 = c1 + p[2];
+        act = (u >= c0) + (u >= c1) + (u >= c2);
+    }
+    actions[i] = (int8_t)act;
+    if (probs) { V q; q.x = p[0]; q.y = p[1]; q.z = p[2]; q.w = p[3]; reinterpret_cast<V*>(probs)[i] = q; }
+}
+
 // host-transfer packing (see ah_pack_host in include/ah_b200.h): 4 envs per thread, 128-bit loads of the rewards
 template <typename R>
 __global__ void pack_host_kernel(int64_t n, int K, const R* __restrict__ reward, const uint8_t* __restrict__ done,
@@ -731,6 +793,16 @@ int ah_step(ah_env* env, const ah_step_io* io, int K, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     if (env->dtype == AH_F32) return launch_step<float>(env, io, K, s);
     return launch_step<double>(env, io, K, s);
+}
+
+int ah_actor_sample(ah_env* env, const float* d_weights, const void* d_obs, void* d_probs, int8_t* d_actions,
+                    int greedy, void* stream) {
+    if (!env || !d_weights || !d_obs || !d_actions || !aligned16(d_obs) || !aligned16(d_probs)) return AH_EINVAL;
+    DeviceGuard g(env->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    AH_DISPATCH(env, (ah::actor_sample_kernel<float><<<small_grid(env->n), 256, 0, s>>>(env->n, d_weights, (const float*)d_obs, (float*)d_probs, d_actions, greedy, env->seed, env->env_id0, env->blk)),
+                (ah::actor_sample_kernel<double><<<small_grid(env->n), 256, 0, s>>>(env->n, d_weights, (const double*)d_obs, (double*)d_probs, d_actions, greedy, env->seed, env->env_id0, env->blk)));
+    AH_LAUNCH_RC(env);
 }
 
 int ah_pack_host(ah_env* env, int K, const void* d_reward, const uint8_t* d_done, const void* d_obs_next,

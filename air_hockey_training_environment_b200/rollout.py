@@ -20,6 +20,7 @@ from typing import Callable, Dict, Optional
 import torch
 from torch import nn
 
+from . import _capi
 from .env import BatchedAirHockey, StepOutputs
 
 
@@ -42,6 +43,44 @@ class ActorMLP(nn.Module):
         return torch.softmax(self.net(obs), dim=-1)
 
 
+class FusedActor:
+    """Inference-only twin of ``ActorMLP`` running in ONE kernel together with the action sampling
+    (``ah_actor_sample``): obs -> probabilities + sampled action, no intermediate tensors.  The torch module stays
+    the owner of the parameters (a learner trains it with autograd); ``refresh()`` re-reads them, folding the
+    BatchNorm's affine map into the second Dense layer."""
+
+    def __init__(self, module: ActorMLP, env: BatchedAirHockey):
+        self.module, self.env = module, env
+        self.weights = torch.zeros(_capi.AH_ACTOR_NWEIGHTS, dtype=torch.float32, device=env.device)
+        self._lib = _capi.lib()
+        self.refresh()
+
+    @torch.no_grad()
+    def refresh(self) -> None:
+        l1, _, bn, l2, _, l3, _, l4 = self.module.net
+        if l4.out_features != 4:
+            raise ValueError("the fused actor implements the reference's 4-action discrete actor")
+        s = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+        t = bn.bias - bn.running_mean * s
+        w2 = l2.weight * s[None, :]
+        b2 = l2.bias + l2.weight @ t
+        flat = torch.cat([l1.weight.flatten(), l1.bias, w2.flatten(), b2, l3.weight.flatten(), l3.bias,
+                          l4.weight.flatten(), l4.bias]).to(torch.float32)
+        assert flat.numel() == _capi.AH_ACTOR_NWEIGHTS
+        self.weights.copy_(flat)
+
+    def sample(self, obs: torch.Tensor, probs: Optional[torch.Tensor], actions: torch.Tensor, greedy: bool = False) -> None:
+        """obs real [N,8] -> probs real [N,4] (optional), actions int8 [N]; sampled with the env's Philox stream."""
+        env = self.env
+        env._check_tensor(obs, (env.n, 8), env.dtype, "obs")
+        env._check_tensor(actions, (env.n,), torch.int8, "actions")
+        if probs is not None:
+            env._check_tensor(probs, (env.n, 4), env.dtype, "probs")
+        _capi.check(self._lib.ah_actor_sample(env._h, self.weights.data_ptr(), obs.data_ptr(),
+                                              None if probs is None else probs.data_ptr(), actions.data_ptr(), int(greedy),
+                                              env._stream()), "ah_actor_sample", env._h)
+
+
 class RolloutCollector:
     """Collects ``T`` frames from ``env`` under ``policy`` into preallocated device tensors.
 
@@ -52,10 +91,12 @@ class RolloutCollector:
     """
 
     def __init__(self, env: BatchedAirHockey, T: int, policy: Optional[Callable[[torch.Tensor], torch.Tensor]] = None,
-                 action_size: int = 4, use_graph: bool = True, seed: int = 0):
+                 action_size: int = 4, use_graph: bool = True, seed: int = 0, fused_actor: bool = True):
         self.env, self.T, self.A = env, int(T), int(action_size)
         n, dt, dev = env.n, env.dtype, env.device
         self.policy = policy if policy is not None else ActorMLP(8, action_size).to(device=dev, dtype=dt)
+        # the reference-shaped actor runs fused with the sampling in one kernel; any other callable goes through torch
+        self.fused = FusedActor(self.policy, env) if (fused_actor and isinstance(self.policy, ActorMLP)) else None
         self.obs = torch.zeros(T + 1, n, 8, dtype=dt, device=dev)
         self.actions = torch.zeros(T, n, dtype=torch.int8, device=dev)
         self.rewards = torch.zeros(T, n, dtype=dt, device=dev)
@@ -75,6 +116,10 @@ class RolloutCollector:
     def _loop(self, collect_stats: bool = True) -> None:
         with torch.no_grad():
             for t in range(self.T):
+                if self.fused is not None:
+                    self.fused.sample(self.obs[t], self.probs[t], self.actions[t])
+                    self.env.step(self.actions[t], K=1, out=self._outs[t], collect_stats=collect_stats)
+                    continue
                 p = self.policy(self.obs[t])
                 self.probs[t].copy_(p)
                 a = torch.multinomial(p.float(), 1, generator=self.gen).squeeze(1)

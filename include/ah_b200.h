@@ -173,6 +173,17 @@ int ah_rewards(ah_env* env, void* d_reward, int8_t* d_score, uint8_t* d_done, vo
  *   update_state("computer"); 10-goal game over.            1 <= K <= 4096 */
 int ah_step(ah_env* env, const ah_step_io* io, int K, void* stream);
 
+/* On-device action selection for rollouts (the hand-off the reference does on the host: Agent.get_action,
+ * lib/agents/agent.py:42-48 -> actor.predict -> exploration strategy, lib/agents/ppo/ppo.py:100-121).
+ * Evaluates the reference's discrete PPO actor (lib/agents/ppo/model.py:56-74: Dense 4 relu, BatchNorm, Dense 6 relu,
+ * Dense 4 relu, Dense 4 softmax) on obs real [n][8] and samples one action per env from the softmax with an in-kernel
+ * Philox uniform (or takes the arg-max when `greedy`, as the reference does when not training, ppo.py:114).
+ * d_weights: device float[AH_ACTOR_NWEIGHTS], row-major W1[4][8] b1[4] W2[6][4] b2[6] W3[4][6] b3[4] W4[4][4] b4[4]
+ * with the BatchNorm already folded into W2/b2.  d_probs (real [n][4], PPO's `old_prediction`) may be NULL. */
+#define AH_ACTOR_NWEIGHTS 114
+int ah_actor_sample(ah_env* env, const float* d_weights, const void* d_obs, void* d_probs, int8_t* d_actions,
+                    int greedy, void* stream);
+
 /* Compact, lossless host-transfer encoding of one step's results (for callers that consume them on the HOST, where
  * PCIe, not the kernel, is the bound).  Inputs are the device outputs of ah_step:
  *   reward real [K][n] (integer-valued, -4..6: lib/rewards.py:118-142), done u8 [K][n], obs_next real [n][8].

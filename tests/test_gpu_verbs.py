@@ -112,3 +112,41 @@ def test_rollout_collector_is_zero_copy_and_consistent(use_graph):
     ret = col.discounted_returns(0.8)
     assert torch.allclose(ret[-1], col.rewards[-1]) and torch.allclose(ret[-2], col.rewards[-2] + 0.8 * col.rewards[-1])
     assert env.stats()["frames"] == 3 * T * n
+
+
+def test_fused_actor_matches_torch_module():
+    """`ah_actor_sample` (actor MLP + softmax + sampling in one kernel) against the torch fp32 module it mirrors:
+    probabilities within 1e-6, greedy actions identical, sampled actions distributed as the probabilities say."""
+    from air_hockey_training_environment_b200 import BatchedAirHockey
+    from air_hockey_training_environment_b200.rollout import ActorMLP, FusedActor
+    torch.manual_seed(0)
+    n = 1 << 16
+    env = BatchedAirHockey(n, seed=9)
+    env.step(None, K=200, out=env.make_outputs(200, ()))
+    obs = env.get_state()
+    actor = ActorMLP().to(env.device)
+    with torch.no_grad():                                   # make the net non-trivial (incl. the BatchNorm statistics)
+        for m in actor.net:
+            if isinstance(m, torch.nn.Linear):
+                m.weight.normal_(0, 0.3); m.bias.normal_(0, 0.3)
+        actor.net[0].weight.mul_(0.01)                      # raw observations are O(100)
+        actor.net[2].running_mean.normal_(0, 0.5); actor.net[2].running_var.uniform_(0.5, 2.0)
+        actor.net[2].weight.normal_(1, 0.2); actor.net[2].bias.normal_(0, 0.2)
+    fused = FusedActor(actor, env)
+    probs = torch.empty(n, 4, device=env.device)
+    acts = torch.empty(n, dtype=torch.int8, device=env.device)
+    with torch.no_grad():
+        ref = actor(obs)
+    fused.sample(obs, probs, acts, greedy=True)
+    assert torch.allclose(probs, ref, atol=1e-6, rtol=1e-5), (probs - ref).abs().max()
+    margin = ref.topk(2, dim=1).values
+    clear = (margin[:, 0] - margin[:, 1]) > 1e-5
+    assert torch.equal(acts[clear].long(), ref.argmax(1)[clear])
+    assert len(torch.unique(acts)) > 1
+    counts = torch.zeros(4, device=env.device)
+    for rep in range(8):                                    # fresh uniforms every frame (the Philox counter is the frame)
+        env.set_counters(frame=1000 + rep)
+        fused.sample(obs, None, acts)
+        counts += torch.bincount(acts.long(), minlength=4).float()
+    expect = ref.sum(0) * 8
+    assert torch.all((counts - expect).abs() < 6 * torch.sqrt(expect + 1) + 50), (counts, expect)
