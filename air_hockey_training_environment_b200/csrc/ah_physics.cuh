@@ -51,6 +51,11 @@ template <> struct Math<double> {
         return (x < lo) ? lo : ((x > hi) ? hi : x);
     }
     static __device__ __forceinline__ double abs_(double v) { return fabs(v); }
+    // (x, y) +/- (bx, by): plain IEEE adds
+    static __device__ __forceinline__ void add2(double& x, double& y, double bx, double by) { x = x + bx; y = y + by; }
+    static __device__ __forceinline__ void sub2(double& ox, double& oy, double ax, double ay, double bx, double by) {
+        ox = ax - bx; oy = ay - by;
+    }
 };
 
 template <> struct Math<float> {
@@ -71,6 +76,17 @@ template <> struct Math<float> {
     static __device__ __forceinline__ float trunc_(float v) { return truncf(v); }
     static __device__ __forceinline__ float clamp(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
     static __device__ __forceinline__ float abs_(float v) { return fabsf(v); }
+    // Blackwell packed FP32: one FADD2 / FFMA2 (sm_100+ `add.f32x2` / `fma.rn.f32x2`) advances both coordinates of a
+    // body -- every position/velocity here is an (x, y) pair, so the pairing is natural and halves the issue slots
+    // of the additive part of the update.  a - b is fma(b, -1, a): one rounding, identical to a plain subtraction.
+    static __device__ __forceinline__ void add2(float& x, float& y, float bx, float by) {
+        const float2 r = __fadd2_rn(make_float2(x, y), make_float2(bx, by));
+        x = r.x; y = r.y;
+    }
+    static __device__ __forceinline__ void sub2(float& ox, float& oy, float ax, float ay, float bx, float by) {
+        const float2 r = __ffma2_rn(make_float2(bx, by), make_float2(-1.0f, -1.0f), make_float2(ax, ay));
+        ox = r.x; oy = r.y;
+    }
 };
 
 // All state of one game, in registers.
@@ -87,8 +103,9 @@ template <typename R> struct Env {
 // ---- Mallet.update  environment/mallet.py:54-76 ----
 template <typename R>
 __device__ __forceinline__ void mallet_update(R& x, R& y, R dx, R dy, R lo, R hi) {
-    x = Math<R>::clamp(x + dx, lo, hi);
-    y = Math<R>::clamp(y + dy, K<R>::y_lo, K<R>::y_hi);
+    Math<R>::add2(x, y, dx, dy);
+    x = Math<R>::clamp(x, lo, hi);
+    y = Math<R>::clamp(y, K<R>::y_lo, K<R>::y_hi);
 }
 
 // ---- AirHockey._move  environment/airhockey.py:65-94 ----
@@ -104,17 +121,11 @@ __device__ __forceinline__ void action_nudge(int ia, R& nx, R& ny) {
 // continuous: (ax, ay) is added to the velocity (:69-71); discrete: (ax, ay) is the position nudge
 template <typename R>
 __device__ __forceinline__ void move_robot(Env<R>& e, bool continuous, R ax, R ay) {
-    if (continuous) {
-        e.rdx += ax;
-        e.rdy += ay;
-    } else {
-        e.ry += ay;
-        e.rx += ax;
-    }
+    if (continuous) Math<R>::add2(e.rdx, e.rdy, ax, ay);
+    else Math<R>::add2(e.rx, e.ry, ax, ay);
     const R lx = e.rx, ly = e.ry;                  // mallet.py:57-58 (last_x, last_y)
     mallet_update<R>(e.rx, e.ry, e.rdx, e.rdy, K<R>::robot_lo, K<R>::robot_hi);   // :87
-    e.rdx = e.rx - lx;                             // :90
-    e.rdy = e.ry - ly;                             // :91
+    Math<R>::sub2(e.rdx, e.rdy, e.rx, e.ry, lx, ly);                              // :90-91
     mallet_update<R>(e.rx, e.ry, e.rdx, e.rdy, K<R>::robot_lo, K<R>::robot_hi);   // :92
 }
 
@@ -123,8 +134,7 @@ __device__ __forceinline__ void move_robot(Env<R>& e, bool continuous, R ax, R a
 // for ~0.5 % of the tests.  `d = mallet - puck` and `dist_sq = np.dot(d, d)` are handed over from the test.
 template <typename R>
 __device__ __forceinline__ R contact_dist_sq(R px, R py, R mx, R my, bool dot_fma, R& d_x, R& d_y) {
-    d_x = mx - px;                                                 // :198
-    d_y = my - py;                                                 // :199
+    Math<R>::sub2(d_x, d_y, mx, my, px, py);                       // :198-199
     return Math<R>::dot2(d_x, d_y, d_x, d_y, dot_fma);             // :203
 }
 
@@ -132,37 +142,26 @@ template <typename R>
 __device__ __forceinline__ void contact_response(R& px, R& py, R& pdx, R& pdy, R& mx, R& my, R& mdx, R& mdy,
                                                  R d_x, R d_y, R dist_sq, bool dot_fma) {
     using M = Math<R>;
-    R n_x, n_y;
     if (M::exact) {
+        R n_x, n_y;
         const R distance = M::sqrt_(dist_sq);                      // :214
         if (distance > R(0)) { n_x = d_x / distance; n_y = d_y / distance; }   // :217
         else { n_x = d_x; n_y = d_y; }
-    } else {
-        const R inv = dist_sq > R(0) ? (R)Math<float>::rsqrt_((float)dist_sq) : R(1);
-        n_x = d_x * inv; n_y = d_y * inv;
-    }
-    // :220 `dcoll = radius - d` is a 2-VECTOR in the reference and :230 `np.max(dcoll - slop, 0)` is the
-    // axis-0 maximum of its two components (not a clamp at zero).  Reproduced as written.
-    const R a = (K<R>::radius - d_x) - R(0.01);
-    const R b = (K<R>::radius - d_y) - R(0.01);
-    const R m = (a >= b) ? a : b;
-    if (M::exact) {
+        // :220 `dcoll = radius - d` is a 2-VECTOR in the reference and :230 `np.max(dcoll - slop, 0)` is the
+        // axis-0 maximum of its two components (not a clamp at zero).  Reproduced as written.
+        const R a = (K<R>::radius - d_x) - R(0.01);
+        const R b = (K<R>::radius - d_y) - R(0.01);
+        const R m = (a >= b) ? a : b;
         const R s = (m / K<R>::imass_sum) * R(0.2);                // :230 ((max / imass_sum) * percent)
         const R sep_x = s * n_x, sep_y = s * n_y;
         px -= sep_x * K<R>::puck_imass;                            // :235
         py -= sep_y * K<R>::puck_imass;                            // :236
         mx += sep_x * K<R>::mallet_imass;                          // :237
         my += sep_y * K<R>::mallet_imass;                          // :238
-    } else {
-        const float sp = (float)m * (float)(-10.0 * 0.2 / 12.0), sm = (float)m * (float)(2.0 * 0.2 / 12.0);
-        px = fmaf(sp, n_x, px); py = fmaf(sp, n_y, py);
-        mx = fmaf(sm, n_x, mx); my = fmaf(sm, n_y, my);
-    }
-    const R v_x = mdx - pdx;                                       // :241
-    const R v_y = mdy - pdy;                                       // :242
-    const R vn = M::dot2(v_x, v_y, n_x, n_y, dot_fma);             // :246
-    if (vn > R(0)) return;                                         // :249 moving apart
-    if (M::exact) {
+        const R v_x = mdx - pdx;                                   // :241
+        const R v_y = mdy - pdy;                                   // :242
+        const R vn = M::dot2(v_x, v_y, n_x, n_y, dot_fma);         // :246
+        if (vn > R(0)) return;                                     // :249 moving apart
         const R j = -(R(1.0) + R(0.9)) * (vn / K<R>::imass_sum);   // :256
         const R i_x = j * n_x, i_y = j * n_y;                      // :259
         pdx -= i_x * K<R>::puck_imass;                             // :262
@@ -170,9 +169,25 @@ __device__ __forceinline__ void contact_response(R& px, R& py, R& pdx, R& pdy, R
         mdx += i_x * K<R>::mallet_imass;                           // :265
         mdy += i_y * K<R>::mallet_imass;                           // :266
     } else {
-        const float jp = (float)vn * (float)(10.0 * 1.9 / 12.0), jm = (float)vn * (float)(-2.0 * 1.9 / 12.0);
-        pdx = fmaf(jp, n_x, pdx); pdy = fmaf(jp, n_y, pdy);
-        mdx = fmaf(jm, n_x, mdx); mdy = fmaf(jm, n_y, mdy);
+        // FP32 build: the same response with MUFU.RSQ for the normal, the constant factors folded
+        // ((m / 12) * 0.2 * 10 etc.), and both coordinates of every update in one packed FFMA2 / FMUL2
+        const float inv = (float)dist_sq > 0.0f ? Math<float>::rsqrt_((float)dist_sq) : 1.0f;
+        const float2 n = __fmul2_rn(make_float2((float)d_x, (float)d_y), make_float2(inv, inv));
+        const float2 ab = __fadd2_rn(__ffma2_rn(make_float2((float)d_x, (float)d_y), make_float2(-1.0f, -1.0f), make_float2(35.0f, 35.0f)),
+                                     make_float2(-0.01f, -0.01f));       // (35 - d) - 0.01, per component
+        const float m = fmaxf(ab.x, ab.y);
+        const float sp = m * (float)(-10.0 * 0.2 / 12.0), sm = m * (float)(2.0 * 0.2 / 12.0);
+        const float2 p = __ffma2_rn(make_float2(sp, sp), n, make_float2((float)px, (float)py));
+        const float2 q = __ffma2_rn(make_float2(sm, sm), n, make_float2((float)mx, (float)my));
+        px = (R)p.x; py = (R)p.y; mx = (R)q.x; my = (R)q.y;
+        float v_x, v_y;
+        Math<float>::sub2(v_x, v_y, (float)mdx, (float)mdy, (float)pdx, (float)pdy);
+        const float vn = fmaf(v_y, n.y, v_x * n.x);
+        if (vn > 0.0f) return;
+        const float jp = vn * (float)(10.0 * 1.9 / 12.0), jm = vn * (float)(-2.0 * 1.9 / 12.0);
+        const float2 pv = __ffma2_rn(make_float2(jp, jp), n, make_float2((float)pdx, (float)pdy));
+        const float2 mv = __ffma2_rn(make_float2(jm, jm), n, make_float2((float)mdx, (float)mdy));
+        pdx = (R)pv.x; pdy = (R)pv.y; mdx = (R)mv.x; mdy = (R)mv.y;
     }
 }
 
@@ -202,14 +217,30 @@ __device__ __forceinline__ void limit_puck_speed(R& pdx, R& pdy) {
 // ---- Puck.update  environment/puck.py:45-71: clamp + reflect FIRST, then advance ----
 template <typename R>
 __device__ __forceinline__ void puck_update(R& px, R& py, R& pdx, R& pdy) {
-    const bool in_x = (px > K<R>::puck_x_lo) && (px < K<R>::puck_x_hi);     // not (x <= 15 or x >= 885)
-    px = Math<R>::clamp(px, K<R>::puck_x_lo, K<R>::puck_x_hi);
-    pdx = in_x ? pdx : -pdx;                                       // `dx *= -1`
-    const bool in_y = (py > K<R>::puck_y_lo) && (py < K<R>::puck_y_hi);
-    py = Math<R>::clamp(py, K<R>::puck_y_lo, K<R>::puck_y_hi);
-    pdy = in_y ? pdy : -pdy;
-    px += pdx;                                                     // :68
-    py += pdy;                                                     // :69
+    if (Math<R>::exact) {
+        const bool in_x = (px > K<R>::puck_x_lo) && (px < K<R>::puck_x_hi);     // not (x <= 15 or x >= 885)
+        px = Math<R>::clamp(px, K<R>::puck_x_lo, K<R>::puck_x_hi);
+        pdx = in_x ? pdx : -pdx;                                       // `dx *= -1`
+        const bool in_y = (py > K<R>::puck_y_lo) && (py < K<R>::puck_y_hi);
+        py = Math<R>::clamp(py, K<R>::puck_y_lo, K<R>::puck_y_hi);
+        pdy = in_y ? pdy : -pdy;
+    } else {
+        // FP32 build: the same predicate without compares.  t = (lo - x) * (x - hi) is positive strictly inside
+        // the table and has its SIGN BIT set when x <= lo or x >= hi (at x == lo or x == hi one factor is +0 and the
+        // other negative, so t = -0).  IEEE subtraction and multiplication give exact signs, so
+        // `reflect == signbit(t)` is the reference's `x <= lo or x >= hi`; the velocity flip is one LOP3
+        // (v ^ (t & 0x80000000)) on the ALU pipe instead of two FSETP and an FSEL, and the products pair into
+        // FADD2/FMUL2 on the FMA pipes.
+        float ax, ay, bx, by;
+        Math<float>::sub2(ax, ay, (float)K<R>::puck_x_lo, (float)K<R>::puck_y_lo, (float)px, (float)py);   // lo - x
+        Math<float>::sub2(bx, by, (float)px, (float)py, (float)K<R>::puck_x_hi, (float)K<R>::puck_y_hi);   // x - hi
+        const float2 t = __fmul2_rn(make_float2(ax, ay), make_float2(bx, by));
+        pdx = (R)__uint_as_float(__float_as_uint((float)pdx) ^ (__float_as_uint(t.x) & 0x80000000u));
+        pdy = (R)__uint_as_float(__float_as_uint((float)pdy) ^ (__float_as_uint(t.y) & 0x80000000u));
+        px = Math<R>::clamp(px, K<R>::puck_x_lo, K<R>::puck_x_hi);
+        py = Math<R>::clamp(py, K<R>::puck_y_lo, K<R>::puck_y_hi);
+    }
+    Math<R>::add2(px, py, pdx, pdy);                               // :68-69
 }
 
 // ---- AirHockey.computerAI  environment/airhockey.py:270-308 (written with selects: no divergence) ----
@@ -225,9 +256,12 @@ __device__ __forceinline__ void computer_ai(Env<R>& e) {
     const R dy_gt = (e.py <= R(360)) ? R(6) : ((e.oy > R(200)) ? R(-2) : R(0));   // :292-300
     e.ody = y_lt ? dy_lt : (y_gt ? dy_gt : e.ody);
     // :303-305, only inside the `puck.y > opponent.y` branch
-    const bool near = y_gt && (M::abs_(e.py - e.oy) < R(40)) && (M::abs_(e.px - e.ox) < R(40));
-    e.pdx = near ? e.pdx + R(2) : e.pdx;
-    e.pdy = near ? e.pdy + R(2) : e.pdy;
+    R gx, gy, nvx = e.pdx, nvy = e.pdy;
+    M::sub2(gx, gy, e.px, e.py, e.ox, e.oy);
+    const bool near = y_gt && (M::abs_(gy) < R(40)) && (M::abs_(gx) < R(40));
+    M::add2(nvx, nvy, R(2), R(2));
+    e.pdx = near ? nvx : e.pdx;
+    e.pdy = near ? nvy : e.pdy;
     mallet_update<R>(e.ox, e.oy, e.odx, e.ody, K<R>::opp_lo, K<R>::opp_hi);    // :307
 }
 
@@ -302,7 +336,8 @@ __device__ __forceinline__ void rewards_call(Env<R>& e, bool dot_fma, int& rewar
     const bool left = (M::abs_(R(0) - e.px) < R(30)) && in_y;
     score = left ? -1 : (right ? 1 : 0);
     // compute_mallet_hit_puck  rewards.py:83-89 with Puck.__and__  puck.py:135-146
-    const R ex = e.px - e.rx, ey = e.py - e.ry;
+    R ex, ey;
+    M::sub2(ex, ey, e.px, e.py, e.rx, e.ry);
     const R dsq = M::dot2(ex, ey, ex, ey, dot_fma);
     if (M::exact) {
         // sqrt((px-mx)**2 + (py-my)**2) < 35 : plain (non-fused) sum of squares; `** 2` is libm pow() in the
