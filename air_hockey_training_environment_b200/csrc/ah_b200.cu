@@ -45,20 +45,33 @@ struct StatePtrs {
 };
 
 template <typename R>
-__device__ __forceinline__ Env<R> load_env(const StatePtrs<R>& s, int64_t i) {
+struct RawEnv {                       // one env's rows exactly as they sit in HBM
+    typename Vec4T<R>::type p, r, o;
+    int4 m;
+    R prev;
+};
+
+template <typename R>
+__device__ __forceinline__ RawEnv<R> load_raw(const StatePtrs<R>& s, int64_t i) {
+    RawEnv<R> w;
+    w.p = s.puck[i]; w.r = s.robot[i]; w.o = s.opp[i]; w.m = s.meta[i]; w.prev = s.prev_dist[i];
+    return w;
+}
+
+template <typename R>
+__device__ __forceinline__ Env<R> unpack_env(const RawEnv<R>& w) {
     Env<R> e;
-    const auto p = s.puck[i];
-    const auto r = s.robot[i];
-    const auto o = s.opp[i];
-    const int4 m = s.meta[i];
-    e.px = p.x; e.py = p.y; e.pdx = p.z; e.pdy = p.w;
-    e.rx = r.x; e.ry = r.y; e.rdx = r.z; e.rdy = r.w;
-    e.ox = o.x; e.oy = o.y; e.odx = o.z; e.ody = o.w;
-    e.prev_dist = s.prev_dist[i];
-    e.robot_score = m.x & 0xffff; e.opp_score = (m.x >> 16) & 0xffff;
-    e.resets = (uint32_t)m.y; e.game_frames = m.z; e.game_return = m.w;
+    e.px = w.p.x; e.py = w.p.y; e.pdx = w.p.z; e.pdy = w.p.w;
+    e.rx = w.r.x; e.ry = w.r.y; e.rdx = w.r.z; e.rdy = w.r.w;
+    e.ox = w.o.x; e.oy = w.o.y; e.odx = w.o.z; e.ody = w.o.w;
+    e.prev_dist = w.prev;
+    e.robot_score = w.m.x & 0xffff; e.opp_score = (w.m.x >> 16) & 0xffff;
+    e.resets = (uint32_t)w.m.y; e.game_frames = w.m.z; e.game_return = w.m.w;
     return e;
 }
+
+template <typename R>
+__device__ __forceinline__ Env<R> load_env(const StatePtrs<R>& s, int64_t i) { return unpack_env<R>(load_raw<R>(s, i)); }
 
 template <typename R>
 __device__ __forceinline__ void store_env(const StatePtrs<R>& s, int64_t i, const Env<R>& e) {
@@ -160,8 +173,13 @@ template <> struct Occ<double> { static constexpr int blocks = 2; };
 //   MODE_GENERIC  every output nullable, per-frame observations, fused ring append, friction flag
 enum { MODE_LEAN = 0, MODE_SIM = 1, MODE_GENERIC = 2 };
 
-template <typename R, int ACT, int MODE>   // ACT: 1 discrete, 2 continuous, 3 philox
-__global__ void __launch_bounds__(kThreads, Occ<R>::blocks) step_kernel(const StepArgs<R> a) {
+// PF ("prefetch"): the variant for small K, where the launch is HBM-bound (176 B per env-step at K = 1 against
+// ~300 instructions).  One env per thread keeps loads in flight only during each block's short load phase
+// (measured 4.4 TB/s); the PF variant runs a persistent grid (SMs x 3 blocks) and requests the NEXT env's rows
+// (4 x LDG.128 + LDG.32 + the action byte) before computing the current one, so every resident thread always has
+// 69 bytes in flight.  Costs 18 registers (64 -> ~84, 3 blocks/SM), which K = 1 can afford.
+template <typename R, int ACT, int MODE, bool PF = false>   // ACT: 1 discrete, 2 continuous, 3 philox
+__global__ void __launch_bounds__(kThreads, PF ? 3 : Occ<R>::blocks) step_kernel(const StepArgs<R> a) {
     using V2 = typename std::conditional<sizeof(R) == 4, float2, double2>::type;
     __shared__ BlockStats bs;
     // discrete action -> position nudge (airhockey.py:74-84) as a 5-entry shared table: one clamp + one LDS.64
@@ -190,8 +208,23 @@ __global__ void __launch_bounds__(kThreads, Occ<R>::blocks) step_kernel(const St
     const size_t act_step = repeat ? 0 : (size_t)n;           // elements between frame k and k+1 of the action tensor
     int reward_sum = 0, reward_sq = 0, frames = 0, dones = 0;
 
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        Env<R> e = load_env<R>(a.st, i);
+    const uint32_t i_first = blockIdx.x * blockDim.x + threadIdx.x;
+    RawEnv<R> raw = {}, raw_next = {};
+    int ia_pf = -1, ia_pf_next = -1;
+    if (PF && i_first < n) { raw = load_raw<R>(a.st, i_first); ia_pf = reinterpret_cast<const int8_t*>(a.actions)[i_first]; }
+
+    for (uint32_t i = i_first; i < n; i += stride) {
+        Env<R> e;
+        if (PF) {
+            e = unpack_env<R>(raw);
+            const uint32_t i_next = i + stride;
+            if (i_next < n && i_next > i) {
+                raw_next = load_raw<R>(a.st, i_next);
+                ia_pf_next = reinterpret_cast<const int8_t*>(a.actions)[i_next];
+            }
+        } else {
+            e = load_env<R>(a.st, i);
+        }
         // 10-goal flag carried into the frame (only reachable through injected state; see game.py:169-177)
         int go = (e.robot_score == 10) ? 1 : ((e.opp_score == 10) ? 2 : 0);
         int contacts_r = 0, contacts_o = 0;
@@ -209,7 +242,7 @@ __global__ void __launch_bounds__(kThreads, Occ<R>::blocks) step_kernel(const St
         R* reward_k = a.reward; uint8_t* done_k = a.done; int8_t* score_k = a.score; uint8_t* over_k = a.game_over;
         // software-pipelined action fetch: frame k+1's action is requested before frame k is computed
         int ia_next = -1; V2 av_next = {};
-        if (ACT == 1) ia_next = act_i8[i];
+        if (ACT == 1) ia_next = PF ? ia_pf : (int)act_i8[i];
         if (ACT == 2) av_next = act_v2[i];
         for (int k = 0; k < K; ++k) {
             // ---- the robot's action for this frame
@@ -310,6 +343,7 @@ __global__ void __launch_bounds__(kThreads, Occ<R>::blocks) step_kernel(const St
         if (!(isfinite((double)e.px) && isfinite((double)e.py) && isfinite((double)e.pdx) && isfinite((double)e.pdy)))
             stat_add(bs, AH_STAT_NONFINITE, 1);
         store_env<R>(a.st, i, e);
+        if (PF) { raw = raw_next; ia_pf = ia_pf_next; }
     }
 
     // ---- epilogue WITHOUT block barriers: warps finish at different times (contact / goal branches), so each warp
@@ -622,7 +656,17 @@ int launch_step(ah_env* env, const ah_step_io* io, int K, cudaStream_t s) {
 #define AH_LAUNCH(ACT_, MODE_) ah::step_kernel<R, ACT_, MODE_><<<grid, ah::kThreads, 0, s>>>(a)
 #define AH_LAUNCH_MODE(ACT_) do { if (mode == ah::MODE_LEAN) AH_LAUNCH(ACT_, ah::MODE_LEAN); \
         else if (mode == ah::MODE_SIM) AH_LAUNCH(ACT_, ah::MODE_SIM); else AH_LAUNCH(ACT_, ah::MODE_GENERIC); } while (0)
-    if (act == 1) AH_LAUNCH_MODE(1); else if (act == 2) AH_LAUNCH_MODE(2); else AH_LAUNCH_MODE(3);
+    bool launched = false;
+    if constexpr (sizeof(R) == 4) {
+        if (act == 1 && mode == ah::MODE_LEAN && K <= 2 && env->n >= 65536 && !getenv("AH_NO_PREFETCH")) {
+            // HBM-bound regime: persistent grid with next-env prefetch (see step_kernel<..., PF>)
+            const unsigned pf_grid = (unsigned)(env->sms * 3 < want ? env->sms * 3 : want);
+            ah::step_kernel<R, 1, ah::MODE_LEAN, true><<<pf_grid, ah::kThreads, 0, s>>>(a);
+            launched = true;
+        }
+    }
+    if (launched) {
+    } else if (act == 1) AH_LAUNCH_MODE(1); else if (act == 2) AH_LAUNCH_MODE(2); else AH_LAUNCH_MODE(3);
 #undef AH_LAUNCH_MODE
 #undef AH_LAUNCH
     const cudaError_t e = cudaGetLastError();
