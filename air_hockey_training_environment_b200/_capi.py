@@ -13,7 +13,8 @@ LIB_PATH = os.environ.get("AH_B200_LIB", os.path.join(HERE, "libah_b200.so"))   
 AH_OK, AH_EINVAL, AH_ECUDA, AH_ENOMEM, AH_EAGENT, AH_ESTATE = 0, -1, -2, -3, -4, -5
 AH_F32, AH_F64 = 0, 1
 AH_AGENT_ROBOT, AH_AGENT_HUMAN, AH_AGENT_COMPUTER = 0, 1, 2
-AH_ACT_NONE, AH_ACT_DISCRETE, AH_ACT_CONTINUOUS, AH_ACT_PHILOX, AH_ACT_DISCRETE_REPEAT, AH_ACT_CONTINUOUS_REPEAT = range(6)
+(AH_ACT_NONE, AH_ACT_DISCRETE, AH_ACT_CONTINUOUS, AH_ACT_PHILOX, AH_ACT_DISCRETE_REPEAT, AH_ACT_CONTINUOUS_REPEAT,
+ AH_ACT_POLICY) = range(7)
 AH_NSTATS = 16
 AH_ACTOR_NWEIGHTS = 114
 STAT_NAMES = ("frames", "robot_goals", "opponent_goals", "robot_wins", "opponent_wins", "dones", "reward_sum",
@@ -41,7 +42,7 @@ class AhStepIO(C.Structure):
                 ("obs_state", C.c_void_p), ("obs_new_state", C.c_void_p), ("reward", C.c_void_p),
                 ("done", C.c_void_p), ("score", C.c_void_p), ("game_over", C.c_void_p),
                 ("obs_next", C.c_void_p), ("obs_next_per_frame", C.c_int32), ("collect_stats", C.c_int32),
-                ("ring", C.POINTER(AhRing))]
+                ("ring", C.POINTER(AhRing)), ("actions_out", C.c_void_p), ("probs_out", C.c_void_p)]
 
 
 class AhError(RuntimeError):

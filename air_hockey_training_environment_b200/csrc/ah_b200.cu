@@ -135,6 +135,7 @@ struct StepArgs {
     R* ring_state; R* ring_new_state; void* ring_action; R* ring_reward; uint8_t* ring_done; int64_t ring_capacity;
     int dot_fma, friction;
     DevBlock* blk;
+    int8_t* actions_out; R* probs_out;     // GENERIC mode: the actions applied / the in-kernel actor's distribution
 };
 
 // Block-level statistics: rare events (goals, wins, contacts ...) are counted with shared-memory atomics right
@@ -152,6 +153,51 @@ struct BlockStats {
 __device__ __forceinline__ void stat_add(BlockStats& bs, int which, int x) {
     const unsigned addr = (unsigned)__cvta_generic_to_shared(&bs.v[which]);
     asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(addr), "r"(x) : "memory");
+}
+
+// ---- the reference's discrete PPO actor (lib/agents/ppo/model.py:56-74; BatchNorm folded into layer 2) and
+// sampling from its softmax.  `sw` = the 114 weights in shared memory (warp-uniform reads -> LDS broadcasts).
+__device__ __forceinline__ void actor_forward(const float* __restrict__ sw, const float (&x)[8], float (&p)[4]) {
+    const float *W1 = sw, *B1 = sw + 32, *W2 = sw + 36, *B2 = sw + 60, *W3 = sw + 66, *B3 = sw + 90, *W4 = sw + 94, *B4 = sw + 110;
+    float h1[4], h2[6], h3[4], z[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { float s = B1[j];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) s = fmaf(W1[j * 8 + c], x[c], s);
+        h1[j] = fmaxf(s, 0.f); }
+#pragma unroll
+    for (int j = 0; j < 6; ++j) { float s = B2[j];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) s = fmaf(W2[j * 4 + c], h1[c], s);
+        h2[j] = fmaxf(s, 0.f); }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { float s = B3[j];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) s = fmaf(W3[j * 6 + c], h2[c], s);
+        h3[j] = fmaxf(s, 0.f); }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { float s = B4[j];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) s = fmaf(W4[j * 4 + c], h3[c], s);
+        z[j] = s; }
+    const float m = fmaxf(fmaxf(z[0], z[1]), fmaxf(z[2], z[3]));
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { p[j] = __expf(z[j] - m); sum += p[j]; }
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) p[j] *= inv;
+}
+
+__device__ __forceinline__ int actor_pick(const float (&p)[4], bool greedy, float u) {
+    if (greedy) {                                   // np.argmax(q_values) when not training   ppo.py:114
+        int act = 0; float best = p[0];
+#pragma unroll
+        for (int j = 1; j < 4; ++j) if (p[j] > best) { best = p[j]; act = j; }
+        return act;
+    }
+    const float c0 = p[0], c1 = c0 + p[1], c2 = c1 + p[2];
+    return (u >= c0) + (u >= c1) + (u >= c2);
 }
 
 #ifndef AH_THREADS
@@ -178,13 +224,16 @@ enum { MODE_LEAN = 0, MODE_SIM = 1, MODE_GENERIC = 2 };
 // (measured 4.4 TB/s); the PF variant runs a persistent grid (SMs x 3 blocks) and requests the NEXT env's rows
 // (4 x LDG.128 + LDG.32 + the action byte) before computing the current one, so every resident thread always has
 // 69 bytes in flight.  Costs 18 registers (64 -> ~84, 3 blocks/SM), which K = 1 can afford.
-template <typename R, int ACT, int MODE, bool PF = false>   // ACT: 1 discrete, 2 continuous, 3 philox
-__global__ void __launch_bounds__(kThreads, PF ? 3 : Occ<R>::blocks) step_kernel(const StepArgs<R> a) {
+template <typename R, int ACT, int MODE, bool PF = false>   // ACT: 1 discrete, 2 continuous, 3 philox, 4 in-kernel actor
+__global__ void __launch_bounds__(kThreads, ACT == 4 ? 2 : (PF ? 3 : Occ<R>::blocks))
+step_kernel(const StepArgs<R> a) {
     using V2 = typename std::conditional<sizeof(R) == 4, float2, double2>::type;
     __shared__ BlockStats bs;
     // discrete action -> position nudge (airhockey.py:74-84) as a 5-entry shared table: one clamp + one LDS.64
     // instead of four compares and four selects per frame.  Entry 4 = "any other int": no nudge.
     __shared__ V2 s_nudge[8];
+    __shared__ __align__(16) float s_actor[ACT == 4 ? 128 : 4];     // AH_ACT_POLICY: the actor's 114 weights
+    if (ACT == 4 && threadIdx.x < AH_ACTOR_NWEIGHTS) s_actor[threadIdx.x] = reinterpret_cast<const float*>(a.actions)[threadIdx.x];
     if (threadIdx.x < AH_NSTATS) bs.v[threadIdx.x] = 0;
     if (threadIdx.x == 0) { bs.len_sq = 0ull; bs.warps_done = 0; }
     if (threadIdx.x < 8) {
@@ -198,7 +247,7 @@ __global__ void __launch_bounds__(kThreads, PF ? 3 : Occ<R>::blocks) step_kernel
     // the device-side counters are read up front only by the variants that need them in the frame loop (Philox
     // actions, ring append): a dependent L2 round-trip at the head of every thread is what the others avoid
     unsigned long long frame0 = 0ull, ring0 = 0ull;
-    if (ACT == 3) frame0 = a.blk->frame;
+    if (ACT == 3 || ACT == 4) frame0 = a.blk->frame;
     if (MODE == MODE_GENERIC) ring0 = a.blk->ring_appended;
     const bool repeat = (a.action_kind == AH_ACT_DISCRETE_REPEAT) || (a.action_kind == AH_ACT_CONTINUOUS_REPEAT);
     const bool dot_fma = a.dot_fma != 0;
@@ -236,6 +285,7 @@ __global__ void __launch_bounds__(kThreads, PF ? 3 : Occ<R>::blocks) step_kernel
         unsigned overflow = 0;
         Philox4 ablock = {};
         uint32_t ablock_id = 0xffffffffu;
+        unsigned long long sblock_id = ~0ull;                  // AH_ACT_POLICY: cached block of 4 sampling uniforms
         // warp-uniform per-frame base pointers (advanced by n per frame); the thread adds its 32-bit env index
         const int8_t* act_i8 = reinterpret_cast<const int8_t*>(a.actions);
         const V2* act_v2 = reinterpret_cast<const V2*>(a.actions);
@@ -257,6 +307,23 @@ __global__ void __launch_bounds__(kThreads, PF ? 3 : Occ<R>::blocks) step_kernel
                 ax = av_next.x; ay = av_next.y;
                 act_v2 += act_step;
                 if (k + 1 < K) av_next = act_v2[i];
+            } else if (ACT == 4) {
+                // closed loop: Agent.get_action (agent.py:42-48) -- the actor is evaluated on the env's current
+                // observation straight from the registers, and an action is sampled from its softmax
+                const Obs<R> ob = get_state<R>(e, true);
+                const float x[8] = {(float)ob.v[0], (float)ob.v[1], (float)ob.v[2], (float)ob.v[3],
+                                    (float)ob.v[4], (float)ob.v[5], (float)ob.v[6], (float)ob.v[7]};
+                float p[4];
+                actor_forward(s_actor, x, p);
+                const unsigned long long f = frame0 + (unsigned long long)k;
+                if ((f >> 2) != sblock_id) { ablock = sample_block(a.rs.seed, a.rs.env_id0 + (uint64_t)i, f); sblock_id = f >> 2; }
+                ia = actor_pick(p, false, sample_uniform(ablock, f));
+                const V2 nd = s_nudge[ia];
+                ax = nd.x; ay = nd.y;
+                if (a.probs_out) {
+                    typename Vec4T<R>::type q; q.x = p[0]; q.y = p[1]; q.z = p[2]; q.w = p[3];
+                    reinterpret_cast<typename Vec4T<R>::type*>(a.probs_out)[(int64_t)k * n + i] = q;
+                }
             } else {
                 const unsigned long long f = frame0 + (unsigned long long)k;
                 const uint32_t bid = (uint32_t)(f >> 6);
@@ -302,6 +369,7 @@ __global__ void __launch_bounds__(kThreads, PF ? 3 : Occ<R>::blocks) step_kernel
                 if (a.done) a.done[row] = dn ? 1 : 0;
                 if (a.score) a.score[row] = (int8_t)sc;
                 if (a.game_over) a.game_over[row] = (uint8_t)go;
+                if (ACT != 2 && a.actions_out) a.actions_out[row] = (int8_t)ia;
                 if (a.obs_state) store_obs<R>(a.obs_state, row, s0);
                 if (a.obs_new_state) store_obs<R>(a.obs_new_state, row, s1);
                 if (a.ring_capacity > 0) {      // fused MemoryBuffer.append(Observation(...))   lib/buffer.py:24-32
@@ -492,50 +560,14 @@ __global__ void __launch_bounds__(256) actor_sample_kernel(int64_t n, const floa
     using V = typename Vec4T<R>::type;
     const V o0 = reinterpret_cast<const V*>(obs)[2 * i], o1 = reinterpret_cast<const V*>(obs)[2 * i + 1];
     const float x[8] = {(float)o0.x, (float)o0.y, (float)o0.z, (float)o0.w, (float)o1.x, (float)o1.y, (float)o1.z, (float)o1.w};
-    const float *W1 = sw, *B1 = sw + 32, *W2 = sw + 36, *B2 = sw + 60, *W3 = sw + 66, *B3 = sw + 90, *W4 = sw + 94, *B4 = sw + 110;
-    float h1[4], h2[6], h3[4], z[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { float s = B1[j];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) s = fmaf(W1[j * 8 + c], x[c], s);
-        h1[j] = fmaxf(s, 0.f); }
-#pragma unroll
-    for (int j = 0; j < 6; ++j) { float s = B2[j];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) s = fmaf(W2[j * 4 + c], h1[c], s);
-        h2[j] = fmaxf(s, 0.f); }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { float s = B3[j];
-#pragma unroll
-        for (int c = 0; c < 6; ++c) s = fmaf(W3[j * 6 + c], h2[c], s);
-        h3[j] = fmaxf(s, 0.f); }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { float s = B4[j];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) s = fmaf(W4[j * 4 + c], h3[c], s);
-        z[j] = s; }
-    const float m = fmaxf(fmaxf(z[0], z[1]), fmaxf(z[2], z[3]));
-    float p[4], sum = 0.f;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { p[j] = __expf(z[j] - m); sum += p[j]; }
-    const float inv = 1.0f / sum;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) p[j] *= inv;
-    int act;
-    if (greedy) {
-        act = 0; float best = p[0];
-#pragma unroll
-        for (int j = 1; j < 4; ++j) if (p[j] > best) { best = p[j]; act = j; }
-    } else {
-        // uniform in [0,1) keyed on (seed, global env id), counter = (current frame, stream 2)
+    float p[4];
+    actor_forward(sw, x, p);
+    float u = 0.f;
+    if (!greedy) {      // uniform in [0,1) keyed on (seed, global env id), counter = the current frame (stream 2)
         const unsigned long long f = blk->frame;
-        const uint64_t id = env_id0 + (uint64_t)i;
-        const Philox4 r = philox4x32_10((uint32_t)id, (uint32_t)(id >> 32), (uint32_t)f, 2u ^ ((uint32_t)(f >> 32) << 8),
-                                        (uint32_t)seed, (uint32_t)(seed >> 32));
-        const float u = (float)(r.x >> 8) * (1.0f / 16777216.0f);
-        const float c0 = p[0], c1 = c0 + p[1], c2 = c1 + p[2];
-        act = (u >= c0) + (u >= c1) + (u >= c2);
+        u = sample_uniform(sample_block(seed, env_id0 + (uint64_t)i, f), f);
     }
+    const int act = actor_pick(p, greedy != 0, u);
     actions[i] = (int8_t)act;
     if (probs) { V q; q.x = p[0]; q.y = p[1]; q.z = p[2]; q.w = p[3]; reinterpret_cast<V*>(probs)[i] = q; }
 }
@@ -636,13 +668,15 @@ int launch_step(ah_env* env, const ah_step_io* io, int K, cudaStream_t s) {
         a.ring_reward = (R*)io->ring->reward; a.ring_done = io->ring->done; a.ring_capacity = io->ring->capacity;
     }
     a.dot_fma = env->cfg.dot_fma; a.friction = env->cfg.friction; a.blk = env->blk;
+    a.actions_out = io->actions_out; a.probs_out = (R*)io->probs_out;
     const int max_blocks = sizeof(R) == 4 ? env->blocks_f32 : env->blocks_f64;
     int64_t want = (env->n + ah::kThreads - 1) / ah::kThreads;
     const unsigned grid = (unsigned)(want < max_blocks ? want : max_blocks);
     // pick the specialised variant the given pointers allow
     const bool per_frame_any = io->reward || io->done || io->score || io->game_over;
     const bool per_frame_all = io->reward && io->done && io->score && io->game_over;
-    const bool heavy = io->obs_state || io->obs_new_state || io->ring || env->cfg.friction || (io->obs_next && io->obs_next_per_frame);
+    const bool heavy = io->obs_state || io->obs_new_state || io->ring || env->cfg.friction || (io->obs_next && io->obs_next_per_frame) ||
+                       io->actions_out || io->probs_out || io->action_kind == AH_ACT_POLICY;
     int mode = ah::MODE_GENERIC;
     if (!heavy && per_frame_all && io->obs_next) mode = ah::MODE_LEAN;
     else if (!heavy && !per_frame_any) mode = ah::MODE_SIM;
@@ -651,6 +685,7 @@ int launch_step(ah_env* env, const ah_step_io* io, int K, cudaStream_t s) {
         case AH_ACT_DISCRETE: case AH_ACT_DISCRETE_REPEAT: act = 1; break;
         case AH_ACT_CONTINUOUS: case AH_ACT_CONTINUOUS_REPEAT: act = 2; break;
         case AH_ACT_PHILOX: act = 3; break;
+        case AH_ACT_POLICY: act = 4; break;
         default: return AH_EINVAL;
     }
 #define AH_LAUNCH(ACT_, MODE_) ah::step_kernel<R, ACT_, MODE_><<<grid, ah::kThreads, 0, s>>>(a)
@@ -666,6 +701,8 @@ int launch_step(ah_env* env, const ah_step_io* io, int K, cudaStream_t s) {
         }
     }
     if (launched) {
+    } else if (act == 4) {
+        ah::step_kernel<R, 4, ah::MODE_GENERIC><<<grid, ah::kThreads, 0, s>>>(a);
     } else if (act == 1) AH_LAUNCH_MODE(1); else if (act == 2) AH_LAUNCH_MODE(2); else AH_LAUNCH_MODE(3);
 #undef AH_LAUNCH_MODE
 #undef AH_LAUNCH
@@ -822,7 +859,8 @@ int ah_step(ah_env* env, const ah_step_io* io, int K, void* stream) {
     if (!io || K < 1 || K > 4096) return AH_EINVAL;
     const int kind = io->action_kind;
     if (kind != AH_ACT_DISCRETE && kind != AH_ACT_CONTINUOUS && kind != AH_ACT_PHILOX &&
-        kind != AH_ACT_DISCRETE_REPEAT && kind != AH_ACT_CONTINUOUS_REPEAT) return AH_EINVAL;
+        kind != AH_ACT_DISCRETE_REPEAT && kind != AH_ACT_CONTINUOUS_REPEAT && kind != AH_ACT_POLICY) return AH_EINVAL;
+    if (!aligned16(io->probs_out) || (io->probs_out && kind != AH_ACT_POLICY)) return AH_EINVAL;
     if (kind != AH_ACT_PHILOX && !io->actions) return AH_EINVAL;
     if ((kind == AH_ACT_CONTINUOUS || kind == AH_ACT_CONTINUOUS_REPEAT) &&
         (reinterpret_cast<uintptr_t>(io->actions) & (env->dtype == AH_F32 ? 7u : 15u))) return AH_EINVAL;

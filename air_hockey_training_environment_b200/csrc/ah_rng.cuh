@@ -57,4 +57,15 @@ __device__ __forceinline__ int action_from_block(const Philox4& b, uint32_t fram
     return (int)((v >> (2u * (frame_in_block & 15u))) & 3u);
 }
 
+// stream 2: uniforms for sampling an action from a policy's distribution; one 128-bit block serves 4 frames
+__device__ __forceinline__ Philox4 sample_block(uint64_t seed, uint64_t env_id, unsigned long long frame) {
+    return philox4x32_10((uint32_t)env_id, (uint32_t)(env_id >> 32), (uint32_t)(frame >> 2), 2u ^ ((uint32_t)(frame >> 34) << 8),
+                         (uint32_t)seed, (uint32_t)(seed >> 32));
+}
+__device__ __forceinline__ float sample_uniform(const Philox4& b, unsigned long long frame) {
+    const uint32_t w = (uint32_t)(frame & 3u);
+    const uint32_t v = w == 0 ? b.x : w == 1 ? b.y : w == 2 ? b.z : b.w;
+    return (float)(v >> 8) * (1.0f / 16777216.0f);       // 24-bit uniform in [0, 1)
+}
+
 }  // namespace ah

@@ -26,7 +26,7 @@ from .exceptions import InvalidAgentError
 
 _AGENTS = {"robot": _capi.AH_AGENT_ROBOT, "human": _capi.AH_AGENT_HUMAN, "computer": _capi.AH_AGENT_COMPUTER}
 
-STEP_FIELDS = ("obs_state", "obs_new_state", "reward", "done", "score", "game_over", "obs_next")
+STEP_FIELDS = ("obs_state", "obs_new_state", "reward", "done", "score", "game_over", "obs_next", "actions", "probs")
 
 
 @dataclass
@@ -39,6 +39,8 @@ class StepOutputs:
     score: Optional[torch.Tensor] = None           # i8   [K,N]
     game_over: Optional[torch.Tensor] = None       # u8   [K,N]    0 / 1 robot won / 2 opponent won
     obs_next: Optional[torch.Tensor] = None        # real [N,8] or [K,N,8]: the next frame's policy input
+    actions: Optional[torch.Tensor] = None         # i8   [K,N]    the discrete actions applied (Philox / in-kernel policy)
+    probs: Optional[torch.Tensor] = None           # real [K,N,4]  the in-kernel actor's distribution (policy mode only)
 
 
 class ReplayRing:
@@ -257,11 +259,16 @@ class BatchedAirHockey:
             o.game_over = torch.empty(K, self.n, dtype=torch.uint8, device=self.device)
         if "obs_next" in fields:
             o.obs_next = torch.empty((K, self.n, 8) if obs_next_per_frame else (self.n, 8), **r)
+        if "actions" in fields:
+            o.actions = torch.empty(K, self.n, dtype=torch.int8, device=self.device)
+        if "probs" in fields:
+            o.probs = torch.empty(K, self.n, 4, **r)
         return o
 
     def step(self, actions: Optional[torch.Tensor] = None, K: int = 1, *, repeat: bool = False,
              out: Optional[StepOutputs] = None, reset_table: Optional[torch.Tensor] = None,
-             ring: Optional[ReplayRing] = None, collect_stats: bool = True) -> StepOutputs:
+             ring: Optional[ReplayRing] = None, collect_stats: bool = True,
+             policy_weights: Optional[torch.Tensor] = None) -> StepOutputs:
         """K fused frames of ``Game.play`` for every env, in ONE kernel launch (state stays in registers).
 
         actions: None                -> uniform random {0,1,2,3} drawn in-kernel (Philox)
@@ -269,11 +276,20 @@ class BatchedAirHockey:
                  real [K,N,2]        -> one continuous action per frame ([N,2] when K == 1 or ``repeat``)
         repeat:  apply the single given action to all K frames (frame-skip)
         out:     preallocated ``StepOutputs`` (see ``make_outputs``); default: reward/done/score/game_over/obs_next
+        policy_weights: float32 [114] device tensor (``rollout.FusedActor.weights``): closed loop -- every frame the
+                 reference-shaped actor is evaluated IN the kernel on the env's current observation and the action
+                 is sampled from its softmax (``actions`` must be None); ``out.actions`` / ``out.probs`` receive them
         """
         if out is None:
             out = self.make_outputs(K)
         io = _capi.AhStepIO()
-        if actions is None:
+        if policy_weights is not None:
+            if actions is not None:
+                raise ValueError("give either actions or policy_weights")
+            self._check_tensor(policy_weights, (_capi.AH_ACTOR_NWEIGHTS,), torch.float32, "policy_weights")
+            io.action_kind = _capi.AH_ACT_POLICY
+            io.actions = policy_weights.data_ptr()
+        elif actions is None:
             io.action_kind = _capi.AH_ACT_PHILOX
         else:
             per_env = repeat or K == 1
@@ -307,6 +323,12 @@ class BatchedAirHockey:
             per_frame = out.obs_next.dim() == 3
             io.obs_next = self._check_tensor(out.obs_next, (K, self.n, 8) if per_frame else (self.n, 8), r, "obs_next").data_ptr()
             io.obs_next_per_frame = int(per_frame)
+        if out.actions is not None:
+            io.actions_out = self._check_tensor(out.actions, (K, self.n), torch.int8, "actions").data_ptr()
+        if out.probs is not None:
+            if policy_weights is None:
+                raise ValueError("out.probs is only produced in policy mode")
+            io.probs_out = self._check_tensor(out.probs, (K, self.n, 4), r, "probs").data_ptr()
         io.collect_stats = int(collect_stats)
         if ring is not None:
             if ring.n != self.n or ring.state.dtype != self.dtype or ring.state.device != self.device:

@@ -91,7 +91,8 @@ class RolloutCollector:
     """
 
     def __init__(self, env: BatchedAirHockey, T: int, policy: Optional[Callable[[torch.Tensor], torch.Tensor]] = None,
-                 action_size: int = 4, use_graph: bool = True, seed: int = 0, fused_actor: bool = True):
+                 action_size: int = 4, use_graph: bool = True, seed: int = 0, fused_actor: bool = True,
+                 single_launch: bool = False):
         self.env, self.T, self.A = env, int(T), int(action_size)
         n, dt, dev = env.n, env.dtype, env.device
         self.policy = policy if policy is not None else ActorMLP(8, action_size).to(device=dev, dtype=dt)
@@ -109,7 +110,12 @@ class RolloutCollector:
                                   game_over=self.game_over[t:t + 1], obs_next=self.obs[t + 1]) for t in range(T)]
         self.gen = torch.Generator(device=dev)
         self.gen.manual_seed(seed)
-        self.use_graph = use_graph
+        # single_launch: the whole T-frame closed loop (actor forward, sampling, physics, reward, resets) runs in ONE
+        # kernel launch with the env state in registers (BatchedAirHockey.step(policy_weights=...)); needs the fused actor
+        self.single_launch = bool(single_launch and self.fused is not None)
+        self._out_all = StepOutputs(reward=self.rewards, done=self.dones, score=self.scores, game_over=self.game_over,
+                                    obs_next=self.obs[1:], actions=self.actions, probs=self.probs)
+        self.use_graph = use_graph and not self.single_launch
         self._graph = None
         self.env.get_state("robot", out=self.obs[0])
 
@@ -146,7 +152,11 @@ class RolloutCollector:
 
     def collect(self) -> Dict[str, torch.Tensor]:
         """Run T frames.  The previous rollout's last observation becomes obs[0]."""
-        if self.use_graph:
+        if self.single_launch:
+            if self._ran:
+                self.obs[0].copy_(self.obs[self.T])
+            self.env.step(None, K=self.T, out=self._out_all, policy_weights=self.fused.weights)
+        elif self.use_graph:
             if self._graph is None:
                 self._capture()
             else:

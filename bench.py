@@ -366,26 +366,34 @@ def run_philox_sim(env, dev, n, K):
 
 
 def run_ppo_rollout(dev):
-    """BASELINE config 5: 65,536 envs x 128 frames, reference-shaped actor MLP, sampling and env.step in one CUDA graph."""
+    """BASELINE config 5: 65,536 envs x 128 frames under the reference-shaped actor MLP, three ways:
+    (a) torch module + torch.multinomial + env.step per frame in one CUDA graph, (b) the fused actor+sampling kernel
+    + env.step per frame in one CUDA graph, (c) the whole closed loop in ONE launch (in-kernel actor)."""
     import torch
     from air_hockey_training_environment_b200 import BatchedAirHockey
     from air_hockey_training_environment_b200.rollout import RolloutCollector
     n, T = 65536, 128
-    env = BatchedAirHockey(n, dtype=torch.float32, device=dev, seed=7)
-    col = RolloutCollector(env, T, use_graph=True, seed=7)
-    for _ in range(3):
-        col.collect()
-    torch.cuda.synchronize(dev)
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    reps = 10
-    for _ in range(reps):
-        col.collect()
-    b.record()
-    torch.cuda.synchronize(dev)
-    ms = a.elapsed_time(b) / reps
-    return {"value": n * T / (ms * 1e-3), "unit": UNIT, "ms_per_rollout": ms, "envs": n, "frames": T,
-            "note": "policy forward + multinomial sampling + env.step per frame, one CUDA graph per rollout"}
+    res = {"envs": n, "frames": T, "unit": UNIT}
+    for name, kw in (("torch_policy_graph", dict(fused_actor=False)), ("fused_actor_graph", dict()),
+                     ("single_launch", dict(single_launch=True))):
+        env = BatchedAirHockey(n, dtype=torch.float32, device=dev, seed=7)
+        col = RolloutCollector(env, T, seed=7, **kw)
+        for _ in range(3):
+            col.collect()
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        reps = 10
+        for _ in range(reps):
+            col.collect()
+        b.record()
+        torch.cuda.synchronize(dev)
+        ms = a.elapsed_time(b) / reps
+        res[name] = {"value": n * T / (ms * 1e-3), "ms_per_rollout": ms}
+    res["value"] = res["single_launch"]["value"]
+    res["note"] = ("obs[T+1,n,8], actions, probs[T,n,4], rewards, dones, scores, game_over written zero-copy into the "
+                   "rollout tensors in all three variants")
+    return res
 
 
 def run_fp64(dev):

@@ -42,6 +42,7 @@ extern "C" {
 #endif
 
 #define AH_ABI_VERSION 1
+#define AH_ACTOR_NWEIGHTS 114   /* W1[4][8] b1[4] W2[6][4] b2[6] W3[4][6] b3[4] W4[4][4] b4[4], see ah_actor_sample */
 
 typedef struct ah_env ah_env;
 
@@ -67,7 +68,10 @@ enum {
                              /* agent "human": real [n][2] = the new mallet location (airhockey.py:104)   */
     AH_ACT_PHILOX = 3,       /* uniform {0,1,2,3} drawn in-kernel (synthetic random-action workload)     */
     AH_ACT_DISCRETE_REPEAT = 4,   /* int8 [n]: one action applied to all K frames (frame-skip)            */
-    AH_ACT_CONTINUOUS_REPEAT = 5  /* real [n][2]: one action applied to all K frames                      */
+    AH_ACT_CONTINUOUS_REPEAT = 5, /* real [n][2]: one action applied to all K frames                      */
+    AH_ACT_POLICY = 6        /* closed loop: every frame the reference's discrete PPO actor is evaluated IN the  */
+                             /* kernel on the env's current observation and an action is sampled from its       */
+                             /* softmax (see ah_actor_sample); `actions` = device float[AH_ACTOR_NWEIGHTS]       */
 };
 
 /* indices into the statistics vector (int64[AH_NSTATS]); the device-side equivalent of the per-frame
@@ -132,6 +136,9 @@ typedef struct ah_step_io {
     int32_t obs_next_per_frame;
     int32_t collect_stats;        /* accumulate the AH_STAT_* vector (warp-reduced, one atomic set per block) */
     const ah_ring* ring;          /* NULL => no append */
+    /* the actions actually applied and, for AH_ACT_POLICY, the actor's distribution (PPO's old_prediction) */
+    int8_t* actions_out;          /* i8   [K][n], nullable (discrete / Philox / policy actions) */
+    void* probs_out;              /* real [K][n][4], nullable (AH_ACT_POLICY only) */
 } ah_step_io;
 
 const char* ah_strerror(int code);
@@ -180,7 +187,6 @@ int ah_step(ah_env* env, const ah_step_io* io, int K, void* stream);
  * Philox uniform (or takes the arg-max when `greedy`, as the reference does when not training, ppo.py:114).
  * d_weights: device float[AH_ACTOR_NWEIGHTS], row-major W1[4][8] b1[4] W2[6][4] b2[6] W3[4][6] b3[4] W4[4][4] b4[4]
  * with the BatchNorm already folded into W2/b2.  d_probs (real [n][4], PPO's `old_prediction`) may be NULL. */
-#define AH_ACTOR_NWEIGHTS 114
 int ah_actor_sample(ah_env* env, const float* d_weights, const void* d_obs, void* d_probs, int8_t* d_actions,
                     int greedy, void* stream);
 

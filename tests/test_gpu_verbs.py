@@ -150,3 +150,32 @@ def test_fused_actor_matches_torch_module():
         counts += torch.bincount(acts.long(), minlength=4).float()
     expect = ref.sum(0) * 8
     assert torch.all((counts - expect).abs() < 6 * torch.sqrt(expect + 1) + 50), (counts, expect)
+
+
+def test_single_launch_policy_rollout_equals_frame_by_frame():
+    """AH_ACT_POLICY: actor forward + sampling + the whole frame loop in ONE launch must reproduce, bit for bit, the
+    frame-by-frame loop (ah_actor_sample kernel, then one step launch per frame)."""
+    from air_hockey_training_environment_b200 import BatchedAirHockey
+    from air_hockey_training_environment_b200.rollout import ActorMLP, RolloutCollector
+    torch.manual_seed(1)
+    n, T = 8192, 32
+    ea, eb = BatchedAirHockey(n, seed=21), BatchedAirHockey(n, seed=21)
+    for e in (ea, eb):
+        e.step(None, K=300, out=e.make_outputs(300, ()))
+    actor = ActorMLP().to(ea.device)
+    with torch.no_grad():
+        for m in actor.net:
+            if isinstance(m, torch.nn.Linear):
+                m.weight.normal_(0, 0.3); m.bias.normal_(0, 0.3)
+        actor.net[0].weight.mul_(0.01)
+    ca = RolloutCollector(ea, T, policy=actor, single_launch=True)
+    cb = RolloutCollector(eb, T, policy=actor, use_graph=False)
+    for it in range(3):
+        ra, rb = ca.collect(), cb.collect()
+        for k in ("obs", "actions", "rewards", "dones", "scores", "game_over"):
+            assert torch.equal(ra[k], rb[k]), (it, k)
+        assert torch.allclose(ra["probs"], rb["probs"], atol=1e-6)
+        assert len(torch.unique(ra["actions"])) == 4
+    for name in ("puck", "robot", "opponent", "prev_dist", "meta"):
+        assert torch.equal(getattr(ea, name), getattr(eb, name))
+    assert ea.stats() == eb.stats() and ea.counters()["frame"] == eb.counters()["frame"] == 300 + 3 * T
