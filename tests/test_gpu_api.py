@@ -307,3 +307,54 @@ def test_prefetch_variant_is_bitwise_identical(K, monkeypatch):
             assert torch.equal(getattr(oa, f), getattr(ob, f)), (it, f)
     assert same(snapshot(a), snapshot(b))
     assert a.stats() == b.stats() and a.stats()["frames"] == 40 * K * n
+
+
+# ---------------------------------------------------------------- edge cases and error paths
+def test_invalid_k_and_pointer_errors():
+    from air_hockey_training_environment_b200 import AhError
+    env = make_env(64)
+    for K in (0, 4097):
+        with pytest.raises(AhError):
+            env.step(None, K=K, out=env.make_outputs(max(K, 1), ()))
+    with pytest.raises(ValueError):
+        env.step(torch.zeros(64, dtype=torch.int8, device=env.device), K=1, policy_weights=torch.zeros(114, device=env.device))
+    with pytest.raises(ValueError):
+        env.step(None, K=1, out=env.make_outputs(1, ("probs",)))      # probs only exist in policy mode
+    with pytest.raises(ValueError):
+        make_env(16, dtype=torch.float16)
+
+
+def test_reset_table_overflow_and_nonfinite_are_counted():
+    env = make_env(256, torch.float64, seed=2)
+    table = torch.zeros(256, 1, 2, dtype=torch.float64, device=env.device)       # room for ONE reset per env
+    env.step(None, K=2000, out=env.make_outputs(2000, ()), reset_table=table)
+    st = env.stats()
+    assert st["reset_table_overflow"] > 0 and st["nonfinite"] == 0
+    env2 = make_env(64, torch.float64, seed=3)      # (the FP32 build's FMNMX clamps turn a NaN into a table bound)
+    env2.puck[5, 0] = float("nan")
+    env2.step(None, K=4)
+    assert env2.stats()["nonfinite"] == 1
+
+
+def test_ragged_sizes_and_single_env():
+    """n = 1, 31, 33, 257: partial warps and partial blocks; each env must equal the same env inside a big batch."""
+    big = make_env(257, torch.float64, seed=8)
+    big.step(None, K=300, out=big.make_outputs(300, ()))
+    for n in (1, 31, 33, 257):
+        e = make_env(n, torch.float64, seed=8)
+        e.step(None, K=300, out=e.make_outputs(300, ()))
+        assert torch.equal(e.puck, big.puck[:n]) and torch.equal(e.meta, big.meta[:n])
+
+
+def test_continuous_repeat_and_ring_with_continuous_actions():
+    from air_hockey_training_environment_b200 import ReplayRing
+    n, K = 128, 3
+    a, b = make_env(n, seed=6), make_env(n, seed=6)
+    act = (torch.rand(n, 2, device=a.device) * 6 - 3).contiguous()              # game.py:122 range
+    ring = ReplayRing(4, n, a.dtype, a.device, continuous=True)
+    a.step(act, K=K, repeat=True, ring=ring, out=a.make_outputs(K, ("reward",)))
+    b.step(act[None].repeat(K, 1, 1).contiguous(), K=K, out=b.make_outputs(K, ("reward",)))
+    assert same(snapshot(a), snapshot(b))
+    assert len(ring) == 3 and torch.equal(ring.retreive()["action"][0], act)
+    with pytest.raises(ValueError):
+        a.step(torch.zeros(n, dtype=torch.int8, device=a.device), K=1, ring=ring)   # discrete actions into a continuous ring

@@ -309,3 +309,38 @@ def test_fp32_score_distribution_matches_oracle():
     wins_g = (g["robot_wins"] + g["opponent_wins"]) / frames
     wins_o = (o["robot_wins"] + o["opponent_wins"]) / frames
     assert abs(wins_g - wins_o) < 0.15 * wins_o + 1e-5
+
+
+# ------------------------------------------------------------------------------ configuration switches vs the oracle
+@pytest.mark.parametrize("dot_fma,friction", [(False, False), (True, True), (False, True)])
+def test_fp64_switches_match_oracle(dot_fma, friction):
+    """`dot_fma = 0` (a numpy build whose ddot tail is not FMA-contracted) and `friction = 1` (the reference's dead
+    Puck.friction_on_puck, opt-in) are restated in the oracle too: the FP64 build must stay bit-exact under both."""
+    n, T = 512, 400
+    rng = np.random.default_rng(11)
+    actions = rng.integers(0, 4, (T, n)).astype(np.int8)
+    table = rng.uniform(-10, 10, (n, 32, 2))
+    st, sc = oracle.initial_state(n)
+    ref = oracle.run_frames(st, sc, T, actions=actions, reset_table=table, dot_fma=int(dot_fma), friction=friction,
+                            record_every=50, want=("reward", "score", "done", "game_over"))
+    env = make_env(n, dot_fma=dot_fma, friction=friction)
+    res = run_gpu(env, T, actions, table, 50)
+    assert np.array_equal(bits(ref["states_rec"]), bits(res["states"]))
+    assert np.array_equal(ref["reward"], res["reward"].astype(np.int32))
+    assert np.array_equal(ref["score"], res["score"]) and np.array_equal(ref["game_over"], res["game_over"])
+    base, _ = oracle.initial_state(n)
+    sc0 = np.zeros((n, 2), np.int32)
+    oracle.run_frames(base, sc0, T, actions=actions, reset_table=table, want=())
+    assert not np.array_equal(bits(base), bits(st)), "the switch must actually change the trajectories"
+
+
+def test_fp64_contact_statistics_match_oracle():
+    n, T = 2048, 300
+    st, sc = oracle.initial_state(n)
+    ref = oracle.run_frames(st, sc, T, seed=5, want=())
+    env = make_env(n, seed=5)
+    env.step(None, K=T, out=env.make_outputs(T, ()))
+    g, o = env.stats(), dict(zip(oracle.STAT_NAMES, ref["stats"]))
+    for k in ("frames", "robot_goals", "opponent_goals", "dones", "reward_sum", "reward_sq_sum", "contacts_robot", "contacts_opponent"):
+        assert g[k] == o[k], k
+    assert g["contacts_robot"] > 0 and g["contacts_opponent"] > 0
