@@ -344,3 +344,36 @@ def test_fp64_contact_statistics_match_oracle():
     for k in ("frames", "robot_goals", "opponent_goals", "dones", "reward_sum", "reward_sq_sum", "contacts_robot", "contacts_opponent"):
         assert g[k] == o[k], k
     assert g["contacts_robot"] > 0 and g["contacts_opponent"] > 0
+
+
+def test_fp32_long_rollout_matches_reference_behaviour_statistics():
+    """Free-running FP32 build, uniform-random robot vs computerAI, 65,536 envs x 6,000 frames (3.9e8 frames), against
+    the statistics of the LIVE Python reference measured in the survey (BASELINE.md §5, 8 seeds x 200,000 frames;
+    per-seed spread in brackets there).  The first 2,000 frames are discarded on our side: all envs start from the
+    same constructor state, the reference's numbers are long-run averages."""
+    n = 65536
+    env = make_env(n, dtype=torch.float32, seed=2718)
+    env.step(None, K=2000, out=env.make_outputs(2000, ()))
+    env.stats(clear=True)
+    hist = torch.zeros(16, dtype=torch.int64, device=env.device)
+    for _ in range(4000 // 40):
+        out = env.make_outputs(40, ("reward",))
+        env.step(None, K=40, out=out)
+        hist += torch.bincount((out.reward.flatten().long() + 8), minlength=16)
+    s = env.stats()
+    f = s["frames"]
+    assert f == n * 4000
+    per_k = lambda k: 1e3 * s[k] / f
+    assert 2.6 < per_k("robot_goals") < 3.0, per_k("robot_goals")               # reference 2.79 (2.69-2.90)
+    assert 4.9 < per_k("opponent_goals") < 5.5, per_k("opponent_goals")         # reference 5.14 (4.99-5.41)
+    assert 2.6 < per_k("dones") < 3.2, per_k("dones")                           # reference 2.89
+    assert 10.5 < per_k("contacts_robot") < 14.0, per_k("contacts_robot")       # reference 12.2
+    assert 14.0 < per_k("contacts_opponent") < 17.5, per_k("contacts_opponent") # reference 15.7
+    games = s["games"]
+    assert games > 50000
+    assert 0.05 < s["robot_wins"] / games < 0.11, s["robot_wins"] / games       # reference 67 / (67 + 769) = 8.0 %
+    assert 1800 < s["game_len_sum"] / games < 2010, s["game_len_sum"] / games   # reference mean game length 1,905 frames
+    h = (hist.cpu().numpy() / f)
+    ref = {-4: 0.0099, -2: 0.5048, 0: 0.4788, 2: 0.0038, 4: 0.0027}             # reference reward histogram
+    for r, p in ref.items():
+        assert abs(h[r + 8] - p) < 0.01 + 0.1 * p, (r, h[r + 8], p)
