@@ -277,6 +277,7 @@ def main():
     extras = {}
     if world == 1 and not args.no_extras:
         extras["rollout_k1"] = run_rollout_k1(env, dev, n)
+        extras["rollout_k1_4m"] = run_rollout_k1(None, dev, 1 << 22)
         extras["philox_sim_k8"] = run_philox_sim(env, dev, n, K)
         extras["ppo_rollout_cfg5"] = run_ppo_rollout(dev)
         extras["fp64_validation_cfg2"] = run_fp64(dev)
@@ -349,17 +350,26 @@ def _time_loop(dev, fn, warm, reps):
 
 
 def run_rollout_k1(env, dev, n):
-    """K = 1: one policy decision per launch, every output written -- the HBM-bound mode a PPO collector uses."""
+    """K = 1: one policy decision per launch, every output written -- the HBM-bound mode a PPO collector uses.
+    `env` None => a fresh env of n games (used for the n = 2^22 point whose state does not fit in L2)."""
     import torch
+    if env is None:
+        from air_hockey_training_environment_b200 import BatchedAirHockey
+        env = BatchedAirHockey(n, dtype=torch.float32, device=dev, seed=99)
+        env.step(None, K=400, out=env.make_outputs(400, ()))
     out = env.make_outputs(1, ("reward", "done", "score", "game_over", "obs_next"))
     acts = [torch.randint(0, 4, (n,), dtype=torch.int8, device=dev) for _ in range(4)]
     ms = _time_loop(dev, lambda i: env.step(acts[i % 4], K=1, out=out), 20, 200)
     hbm_peak, src, _ = peaks()
     b = n * (2 * STATE_BYTES + 32 + (1 + 4 + 1 + 1 + 1))
     ach = b / (ms * 1e-3) / 1e9
-    return {"value": n / (ms * 1e-3), "unit": UNIT, "kernel_ms": ms,
+    return {"value": n / (ms * 1e-3), "unit": UNIT, "kernel_ms": ms, "envs": n,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                         "traffic": None, "algorithmic_bytes_per_launch": b, "bytes_per_env_step": b / n}}
+                         "traffic": 127331072.0 if n == (1 << 20) else None,
+                         "algorithmic_bytes_per_launch": b, "bytes_per_env_step": b / n,
+                         "note": ("state (71 MB) < L2 (126 MB): ncu shows 127 MB of DRAM traffic for the 184.5 MB algorithmic "
+                                  "bytes (profiles/r1f_other_variants.md); see rollout_k1_4m for the L2-proof point")
+                         if n == (1 << 20) else "state 285 MB > 126 MB L2: algorithmic bytes are DRAM bytes"}}
 
 
 def run_philox_sim(env, dev, n, K):

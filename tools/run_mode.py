@@ -1,0 +1,28 @@
+"""Run ONE mode of the step kernel repeatedly (for ncu captures of the non-headline variants).
+usage: python tools/run_mode.py k1 | fp64 | policy"""
+import sys
+sys.path.insert(0, "/root/repo")
+import torch
+from air_hockey_training_environment_b200 import BatchedAirHockey
+mode = sys.argv[1]
+if mode == "k1":                       # HBM-bound rollout mode: persistent grid + prefetch variant
+    n = 1 << 20
+    env = BatchedAirHockey(n, seed=1)
+    out = env.make_outputs(1, ("reward", "done", "score", "game_over", "obs_next"))
+    acts = [torch.randint(0, 4, (n,), dtype=torch.int8, device="cuda") for _ in range(4)]
+    for i in range(300):
+        env.step(acts[i % 4], K=1, out=out)
+elif mode == "fp64":                   # validation build
+    n = 1 << 18
+    env = BatchedAirHockey(n, dtype=torch.float64, seed=1)
+    out = env.make_outputs(8, ("reward", "done", "score", "game_over", "obs_next"))
+    acts = [torch.randint(0, 4, (8, n), dtype=torch.int8, device="cuda") for _ in range(4)]
+    for i in range(80):
+        env.step(acts[i % 4], K=8, out=out)
+elif mode == "policy":                 # in-kernel actor rollout (config 5)
+    from air_hockey_training_environment_b200.rollout import RolloutCollector
+    col = RolloutCollector(BatchedAirHockey(65536, seed=1), 128, single_launch=True)
+    for i in range(12):
+        col.collect()
+torch.cuda.synchronize()
+print("ok", mode)
