@@ -358,3 +358,56 @@ def test_continuous_repeat_and_ring_with_continuous_actions():
     assert len(ring) == 3 and torch.equal(ring.retreive()["action"][0], act)
     with pytest.raises(ValueError):
         a.step(torch.zeros(n, dtype=torch.int8, device=a.device), K=1, ring=ring)   # discrete actions into a continuous ring
+
+
+# ---------------------------------------------------------------- out-of-bounds writes: guard bands (compute-sanitizer is closed on this pool)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_guard_bands_survive_every_kernel(dtype):
+    """Every state and output buffer is carved out of a larger allocation whose margins hold a sentinel; after running
+    all kernels / variants on a ragged n the margins must be untouched and the kernels must have written the interior."""
+    n, K, G = 1000, 5, 64                                  # G guard elements on both sides
+    env = make_env(n, dtype, seed=4)
+    dev = env.device
+    guards = []
+
+    def carve(shape, dt, fill=None):
+        numel = int(np.prod(shape))
+        el = torch.empty((), dtype=dt).element_size()
+        pad = (G * 16) // el                              # keep 16-byte alignment of the interior
+        raw = torch.full((numel + 2 * pad,), 77, dtype=dt, device=dev)
+        inner = raw[pad:pad + numel].view(*shape)
+        if fill is not None:
+            inner.copy_(fill)
+        guards.append((raw, pad, numel))
+        return inner
+
+    env.puck, env.robot, env.opponent = carve((n, 4), dtype, env.puck), carve((n, 4), dtype, env.robot), carve((n, 4), dtype, env.opponent)
+    env.prev_dist, env.meta = carve((n,), dtype, env.prev_dist), carve((n, 4), torch.int32, env.meta)
+    env._bind()
+    from air_hockey_training_environment_b200 import ReplayRing, StepOutputs
+    out = StepOutputs(obs_state=carve((K, n, 8), dtype), obs_new_state=carve((K, n, 8), dtype), reward=carve((K, n), dtype),
+                      done=carve((K, n), torch.uint8), score=carve((K, n), torch.int8), game_over=carve((K, n), torch.uint8),
+                      obs_next=carve((K, n, 8), dtype), actions=carve((K, n), torch.int8))
+    ring = ReplayRing(3, n, dtype, dev)
+    ring.state, ring.new_state = carve((3, n, 8), dtype), carve((3, n, 8), dtype)
+    ring.action, ring.reward, ring.done = carve((3, n), torch.int8), carve((3, n), dtype), carve((3, n), torch.uint8)
+    from air_hockey_training_environment_b200 import _capi
+    ring._c = _capi.AhRing(ring.state.data_ptr(), ring.new_state.data_ptr(), ring.action.data_ptr(), ring.reward.data_ptr(),
+                           ring.done.data_ptr(), 3)
+    acts = torch.randint(0, 4, (K, n), dtype=torch.int8, device=dev)
+    for _ in range(40):
+        env.step(acts, K=K, out=out, ring=ring)                                   # GENERIC
+    lean = StepOutputs(reward=out.reward, done=out.done, score=out.score, game_over=out.game_over, obs_next=carve((n, 8), dtype))
+    env.step(acts, K=K, out=lean)                                                 # LEAN
+    env.step(None, K=K, out=StepOutputs(obs_next=lean.obs_next))                  # SIM + Philox
+    env.update_state(acts[0].contiguous(), "robot"); env.update_state(agent_name="computer")
+    obs = carve((n, 8), dtype); env.get_state("robot", out=obs)
+    r, s, d = env.rewards(); env.update_score(s); env.reset(total=False, mask=(s != 0))
+    pw = torch.randn(114, device=dev) * 0.1
+    pol = StepOutputs(reward=out.reward, done=out.done, obs_next=out.obs_next, actions=out.actions, probs=carve((K, n, 4), dtype))
+    env.step(None, K=K, out=pol, policy_weights=pw)                               # in-kernel policy
+    torch.cuda.synchronize()
+    for raw, pad, numel in guards:
+        assert bool((raw[:pad] == 77).all()) and bool((raw[pad + numel:] == 77).all()), "guard band overwritten"
+    assert not bool((out.reward == 77).any()) and not bool((pol.probs == 77).any())    # interiors were written
+    assert env.stats()["frames"] == n * K * 43 and env.stats()["nonfinite"] == 0
