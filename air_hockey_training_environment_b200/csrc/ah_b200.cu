@@ -225,7 +225,7 @@ enum { MODE_LEAN = 0, MODE_SIM = 1, MODE_GENERIC = 2 };
 // (4 x LDG.128 + LDG.32 + the action byte) before computing the current one, so every resident thread always has
 // 69 bytes in flight.  Costs 18 registers (64 -> ~84, 3 blocks/SM), which K = 1 can afford.
 template <typename R, int ACT, int MODE, bool PF = false>   // ACT: 1 discrete, 2 continuous, 3 philox, 4 in-kernel actor
-__global__ void __launch_bounds__(kThreads, ACT == 4 ? 2 : (PF ? 3 : Occ<R>::blocks))
+__global__ void __launch_bounds__(kThreads, ACT == 4 ? 2 : ((PF || MODE == MODE_GENERIC) ? (Occ<R>::blocks < 3 ? Occ<R>::blocks : 3) : Occ<R>::blocks))
 step_kernel(const StepArgs<R> a) {
     using V2 = typename std::conditional<sizeof(R) == 4, float2, double2>::type;
     __shared__ BlockStats bs;
@@ -256,6 +256,7 @@ step_kernel(const StepArgs<R> a) {
     const int K = a.K;
     const size_t act_step = repeat ? 0 : (size_t)n;           // elements between frame k and k+1 of the action tensor
     int reward_sum = 0, reward_sq = 0, frames = 0, dones = 0;
+    const int64_t ring_slot0 = (MODE == MODE_GENERIC && a.ring_capacity > 0) ? (int64_t)(ring0 % (unsigned long long)a.ring_capacity) : 0;
 
     const uint32_t i_first = blockIdx.x * blockDim.x + threadIdx.x;
     RawEnv<R> raw = {}, raw_next = {};
@@ -286,6 +287,7 @@ step_kernel(const StepArgs<R> a) {
         Philox4 ablock = {};
         uint32_t ablock_id = 0xffffffffu;
         unsigned long long sblock_id = ~0ull;                  // AH_ACT_POLICY: cached block of 4 sampling uniforms
+        int64_t ring_slot = ring_slot0;                        // slot of frame k: (appended so far + k) mod capacity
         // warp-uniform per-frame base pointers (advanced by n per frame); the thread adds its 32-bit env index
         const int8_t* act_i8 = reinterpret_cast<const int8_t*>(a.actions);
         const V2* act_v2 = reinterpret_cast<const V2*>(a.actions);
@@ -335,12 +337,22 @@ step_kernel(const StepArgs<R> a) {
             // ---- robot.move(a): sub-update #1                      game.py:136 -> agent.py:32-36
             move_robot<R>(e, ACT == 2, ax, ay);
             physics_tail<R, false>(e, dot_fma, friction, speed_dirty, contacts_r, contacts_o);
-            Obs<R> s0, s1;
-            if (MODE == MODE_GENERIC && want_obs) s0 = get_state<R>(e, true);   // Observation.state      agent.py:61
+            // observations are stored the moment they exist (not held in registers until the end of the frame)
+            const int64_t row = (int64_t)k * n + i;
+            const int64_t rrow = ring_slot * (int64_t)n + i;
+            if (MODE == MODE_GENERIC && want_obs) {                             // Observation.state      agent.py:61
+                const Obs<R> s0 = get_state<R>(e, true);
+                if (a.obs_state) store_obs<R>(a.obs_state, row, s0);
+                if (a.ring_capacity > 0) store_obs<R>(a.ring_state, rrow, s0);
+            }
             // ---- robot.step(a) -> self.move(a): sub-update #2      agent.py:64
             move_robot<R>(e, ACT == 2, ax, ay);
             physics_tail<R, false>(e, dot_fma, friction, speed_dirty, contacts_r, contacts_o);
-            if (MODE == MODE_GENERIC && want_obs) s1 = get_state<R>(e, true);   // Observation.new_state  agent.py:67
+            if (MODE == MODE_GENERIC && want_obs) {                             // Observation.new_state  agent.py:67
+                const Obs<R> s1 = get_state<R>(e, true);
+                if (a.obs_new_state) store_obs<R>(a.obs_new_state, row, s1);
+                if (a.ring_capacity > 0) store_obs<R>(a.ring_new_state, rrow, s1);
+            }
             // ---- Rewards                                           agent.py:70-71
             int rw, sc; bool dn;
             rewards_call<R>(e, dot_fma, rw, sc, dn);
@@ -364,19 +376,13 @@ step_kernel(const StepArgs<R> a) {
                 reward_k[i] = (R)rw; done_k[i] = dn ? 1 : 0; score_k[i] = (int8_t)sc; over_k[i] = (uint8_t)go;
                 reward_k += n; done_k += n; score_k += n; over_k += n;
             } else if (MODE == MODE_GENERIC) {
-                const int64_t row = (int64_t)k * n + i;
                 if (a.reward) a.reward[row] = (R)rw;
                 if (a.done) a.done[row] = dn ? 1 : 0;
                 if (a.score) a.score[row] = (int8_t)sc;
                 if (a.game_over) a.game_over[row] = (uint8_t)go;
                 if (ACT != 2 && a.actions_out) a.actions_out[row] = (int8_t)ia;
-                if (a.obs_state) store_obs<R>(a.obs_state, row, s0);
-                if (a.obs_new_state) store_obs<R>(a.obs_new_state, row, s1);
                 if (a.ring_capacity > 0) {      // fused MemoryBuffer.append(Observation(...))   lib/buffer.py:24-32
-                    const int64_t slot = (int64_t)((ring0 + (unsigned long long)k) % (unsigned long long)a.ring_capacity);
-                    const int64_t rrow = slot * n + i;
-                    store_obs<R>(a.ring_state, rrow, s0);
-                    store_obs<R>(a.ring_new_state, rrow, s1);
+                    ring_slot = (ring_slot + 1 == a.ring_capacity) ? 0 : ring_slot + 1;
                     if (ACT == 2) reinterpret_cast<V2*>(a.ring_action)[rrow] = V2{ax, ay};
                     else reinterpret_cast<int8_t*>(a.ring_action)[rrow] = (int8_t)ia;
                     a.ring_reward[rrow] = (R)rw;

@@ -279,6 +279,7 @@ def main():
         extras["rollout_k1"] = run_rollout_k1(env, dev, n)
         extras["rollout_k1_4m"] = run_rollout_k1(None, dev, 1 << 22)
         extras["philox_sim_k8"] = run_philox_sim(env, dev, n, K)
+        extras["ring_append_k8_cfg4"] = run_ring_append(env, dev, n, K)
         extras["ppo_rollout_cfg5"] = run_ppo_rollout(dev)
         extras["fp64_validation_cfg2"] = run_fp64(dev)
 
@@ -370,6 +371,23 @@ def run_rollout_k1(env, dev, n):
                          "note": ("state (71 MB) < L2 (126 MB): ncu shows 127 MB of DRAM traffic for the 184.5 MB algorithmic "
                                   "bytes (profiles/r1f_other_variants.md); see rollout_k1_4m for the L2-proof point")
                          if n == (1 << 20) else "state 285 MB > 126 MB L2: algorithmic bytes are DRAM bytes"}}
+
+
+def run_ring_append(env, dev, n, K):
+    """BASELINE config 4's per-GPU work: the headline step PLUS the fused replay-ring append of the Observation tuple
+    (state 8 reals, action, reward, done, new_state 8 reals = 70 B per env-frame; replaces MemoryBuffer.append)."""
+    import torch
+    from air_hockey_training_environment_b200 import ReplayRing
+    ring = ReplayRing(2 * K, n, env.dtype, dev)
+    out = env.make_outputs(K, ("reward", "done", "score", "game_over", "obs_next"))
+    acts = [torch.randint(0, 4, (K, n), dtype=torch.int8, device=dev) for _ in range(4)]
+    ms = _time_loop(dev, lambda i: env.step(acts[i % 4], K=K, out=out, ring=ring), 10, 100)
+    hbm_peak, src, _ = peaks()
+    b = n * (2 * STATE_BYTES + 32 + K * (1 + 4 + 1 + 1 + 1) + K * 70)
+    ach = b / (ms * 1e-3) / 1e9
+    return {"value": n * K / (ms * 1e-3), "unit": UNIT, "kernel_ms": ms, "ring_capacity_frames": 2 * K,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                         "traffic": None, "algorithmic_bytes_per_launch": b, "bytes_per_env_step": b / (n * K)}}
 
 
 def run_philox_sim(env, dev, n, K):
