@@ -236,6 +236,16 @@ class BatchedAirHockey:
                     "ah_rewards", self._h)
         return reward, score, done
 
+    def first_frame(self, actions: torch.Tensor, reset_table: Optional[torch.Tensor] = None) -> None:
+        """The reference's very first frame (``Game.robot_player`` with ``self.init``, game.py:118-130, followed by
+        the rest of ``Game.play``, game.py:162-177): the robot only MOVES (no ``Agent.step``: no reward, no score),
+        then the opponent's sub-update and the two 10-goal checks.  Every later frame is ``step``."""
+        self.update_state(actions, "robot")                          # game.py:128
+        self.update_state(agent_name="computer")                     # game.py:166
+        for col in (1, 0):                                           # opponent first, then robot (game.py:169-177)
+            over = self.scores[:, col] == 10
+            self.reset(total=True, mask=over, reset_table=reset_table)
+
     # ------------------------------------------------------------------ the fused frame
     def make_outputs(self, K: int = 1, fields: Sequence[str] = ("reward", "done", "score", "game_over", "obs_next"),
                      obs_next_per_frame: bool = False) -> StepOutputs:

@@ -156,6 +156,17 @@ def gen_substeps(seed=505, n_seq=24, L=40):
                         names=np.array(names), **_header(seed))
 
 
+def gen_init_frame(seed=606, n=8, T=80):
+    """Game.play from its very first call: frame 0 is move-only (game.py:118-130)."""
+    rng = np.random.default_rng(seed)
+    actions = rng.integers(0, 4, (T, n)).astype(np.int8)
+    table = rng.uniform(-10, 10, (n, 8, 2))
+    ref = ref_loop.run_reference(actions, table, init_frame=True)
+    np.savez_compressed(os.path.join(GOLDEN, "init_frame_8x80.npz"), actions=actions, reset_table=table,
+                        states=ref["states"], scores=ref["scores"], obs_next=ref["obs_next"],
+                        reward=ref["reward"].astype(np.int8), score=ref["score"], done=ref["done"], **_header(seed))
+
+
 def main():
     refshim.install()
     os.makedirs(GOLDEN, exist_ok=True)
@@ -164,6 +175,7 @@ def main():
     gen_scrambled()
     gen_continuous()
     gen_substeps()
+    gen_init_frame()
     for f in sorted(os.listdir(GOLDEN)):
         print(f, os.path.getsize(os.path.join(GOLDEN, f)))
 

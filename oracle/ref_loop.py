@@ -60,7 +60,7 @@ def snapshot(env, tracker) -> np.ndarray:
 def run_reference(actions: np.ndarray, reset_table: np.ndarray,
                   init_state: Optional[np.ndarray] = None,
                   init_scores: Optional[np.ndarray] = None,
-                  record_every: int = 1) -> Dict[str, np.ndarray]:
+                  record_every: int = 1, init_frame: bool = False) -> Dict[str, np.ndarray]:
     """Run ``T`` frames of ``N`` independent reference games.
 
     actions      int   [T, N]      discrete actions (any int; 0..3 nudge, others no nudge)
@@ -68,6 +68,8 @@ def run_reference(actions: np.ndarray, reset_table: np.ndarray,
     reset_table  f64   [N, R, 2]   (dx, dy) per reset, consumed in order per env
     init_state   f64   [N, 13]     optional initial 13 reals (see ``snapshot``)
     init_scores  int   [N, 2]      optional (robot_score, opponent_score)
+    init_frame   frame 0 is the reference's move-only first frame (game.py:118-130): `robot.move(a)` without
+                 `robot.step`, then the opponent's sub-update; its reward / score / done rows are left at zero
     """
     refshim.install()
     refshim.silence_side_channels()
@@ -112,6 +114,12 @@ def run_reference(actions: np.ndarray, reset_table: np.ndarray,
             feed.bind(reset_table[e].reshape(-1))
             for t in range(T):
                 a = (float(actions[t, e, 0]), float(actions[t, e, 1])) if continuous else int(actions[t, e])
+                if init_frame and t == 0:
+                    robot.move(a)                               # game.py:128 (self.init: move only)
+                    env.update_state(agent_name="computer")     # game.py:166
+                    out["obs_next"][t, e] = _obs8(env.get_state("robot"))
+                    out["states"][0, e] = snapshot(env, tracker)
+                    continue
                 robot.move(a)                                   # game.py:136
                 score, obs = robot.step(a)                      # game.py:139
                 env.update_score(score)                         # game.py:142

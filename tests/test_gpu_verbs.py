@@ -179,3 +179,23 @@ def test_single_launch_policy_rollout_equals_frame_by_frame():
     for name in ("puck", "robot", "opponent", "prev_dist", "meta"):
         assert torch.equal(getattr(ea, name), getattr(eb, name))
     assert ea.stats() == eb.stats() and ea.counters()["frame"] == eb.counters()["frame"] == 300 + 3 * T
+
+
+def test_first_frame_then_step_matches_reference(golden_dir):
+    """`first_frame` (the reference's move-only init frame, game.py:118-130) followed by fused steps, FP64, vs the
+    live reference's trajectory."""
+    from air_hockey_training_environment_b200 import BatchedAirHockey
+    g = np.load(os.path.join(golden_dir, "init_frame_8x80.npz"))
+    T, n = g["actions"].shape
+    env = BatchedAirHockey(n, dtype=torch.float64)
+    acts = torch.as_tensor(g["actions"]).to(env.device)
+    table = torch.as_tensor(g["reset_table"]).to(env.device)
+    env.first_frame(acts[0].contiguous(), reset_table=table)
+    assert np.array_equal(bits(g["states"][0]), bits(state13(env)))
+    assert np.array_equal(bits(g["obs_next"][0]), bits(env.get_state().cpu().numpy()))
+    out = env.make_outputs(T - 1, ("reward", "score", "done", "obs_next"), obs_next_per_frame=True)
+    env.step(acts[1:].contiguous(), K=T - 1, out=out, reset_table=table)
+    assert np.array_equal(bits(g["states"][-1]), bits(state13(env)))
+    assert np.array_equal(bits(g["obs_next"][1:]), bits(out.obs_next.cpu().numpy()))
+    assert np.array_equal(g["reward"][1:].astype(np.float64), out.reward.cpu().numpy())
+    assert np.array_equal(g["score"][1:], out.score.cpu().numpy()) and np.array_equal(g["done"][1:], out.done.cpu().numpy())
