@@ -255,7 +255,8 @@ step_kernel(const StepArgs<R> a) {
     const bool want_obs = (MODE == MODE_GENERIC) && (a.obs_state || a.obs_new_state || a.ring_capacity > 0);
     const int K = a.K;
     const size_t act_step = repeat ? 0 : (size_t)n;           // elements between frame k and k+1 of the action tensor
-    int reward_sum = 0, reward_sq = 0, frames = 0, dones = 0;
+    int reward_sum = 0, reward_sq = 0, frames = 0, dones = 0, contacts_r = 0, contacts_o = 0, bad = 0;
+    unsigned overflow = 0;
     const int64_t ring_slot0 = (MODE == MODE_GENERIC && a.ring_capacity > 0) ? (int64_t)(ring0 % (unsigned long long)a.ring_capacity) : 0;
 
     const uint32_t i_first = blockIdx.x * blockDim.x + threadIdx.x;
@@ -277,13 +278,11 @@ step_kernel(const StepArgs<R> a) {
         }
         // 10-goal flag carried into the frame (only reachable through injected state; see game.py:169-177)
         int go = (e.robot_score == 10) ? 1 : ((e.opp_score == 10) ? 2 : 0);
-        int contacts_r = 0, contacts_o = 0;
         bool speed_dirty = speed_out_of_limits<R>(e.pdx, e.pdy);   // only injected states can start out of limits
         // game_frames / reward_sum are not incremented per frame: frames-in-game = gf_base + frames done in this
         // launch, and the launch's reward sum is recovered from game_return (+ the returns of finished games)
         int gf_base = e.game_frames;
         int ret_credit = -e.game_return;
-        unsigned overflow = 0;
         Philox4 ablock = {};
         uint32_t ablock_id = 0xffffffffu;
         unsigned long long sblock_id = ~0ull;                  // AH_ACT_POLICY: cached block of 4 sampling uniforms
@@ -411,11 +410,7 @@ step_kernel(const StepArgs<R> a) {
         frames += K;
         e.game_frames = gf_base + K;
         reward_sum += e.game_return + ret_credit;
-        if (contacts_r) stat_add(bs, AH_STAT_CONTACTS_ROBOT, contacts_r);
-        if (contacts_o) stat_add(bs, AH_STAT_CONTACTS_OPPONENT, contacts_o);
-        if (overflow) stat_add(bs, AH_STAT_RESET_TABLE_OVERFLOW, (int)overflow);
-        if (!(isfinite((double)e.px) && isfinite((double)e.py) && isfinite((double)e.pdx) && isfinite((double)e.pdy)))
-            stat_add(bs, AH_STAT_NONFINITE, 1);
+        bad += (isfinite(e.px) && isfinite(e.py) && isfinite(e.pdx) && isfinite(e.pdy)) ? 0 : 1;
         store_env<R>(a.st, i, e);
         if (PF) { raw = raw_next; ia_pf = ia_pf_next; }
     }
@@ -429,6 +424,10 @@ step_kernel(const StepArgs<R> a) {
     const int rs = __reduce_add_sync(0xffffffffu, reward_sum);
     const int rq = __reduce_add_sync(0xffffffffu, reward_sq);
     const int dd = __reduce_add_sync(0xffffffffu, dones);
+    const int cr = __reduce_add_sync(0xffffffffu, contacts_r);
+    const int co = __reduce_add_sync(0xffffffffu, contacts_o);
+    const int ov = __reduce_add_sync(0xffffffffu, (int)overflow);
+    const int nf = __reduce_add_sync(0xffffffffu, bad);
     const int lane = threadIdx.x & 31;
     int arrived = 0;
     if (lane == 0) {
@@ -436,6 +435,10 @@ step_kernel(const StepArgs<R> a) {
         stat_add(bs, AH_STAT_FRAMES, fs);
         stat_add(bs, AH_STAT_REWARD_SUM, rs);
         stat_add(bs, AH_STAT_REWARD_SQ_SUM, rq);
+        if (cr) stat_add(bs, AH_STAT_CONTACTS_ROBOT, cr);
+        if (co) stat_add(bs, AH_STAT_CONTACTS_OPPONENT, co);
+        if (ov) stat_add(bs, AH_STAT_RESET_TABLE_OVERFLOW, ov);
+        if (nf) stat_add(bs, AH_STAT_NONFINITE, nf);
         __threadfence_block();
         arrived = atomicAdd(&bs.warps_done, 1);
     }
