@@ -326,8 +326,14 @@ def main():
         }
     if not args.no_cpu_baseline and world == 1:
         v, cores, dt, calls, envs = cpu_port_run(0, 1, seconds=args.cpu_seconds)
+        v1, _, dt1, calls1, envs1 = cpu_port_run(0, 1, envs=1 << 15, threads=1, seconds=min(3.0, args.cpu_seconds))
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"{envs} envs x {FRAMES_PER_STEP} frames x {calls} calls ({dt:.1f} s), OpenMP"}
+                                "sample": f"{envs} envs x {FRAMES_PER_STEP} frames x {calls} calls ({dt:.1f} s), OpenMP over {cores} threads",
+                                "one_thread_value": v1,
+                                "one_thread_sample": f"{envs1} envs x {FRAMES_PER_STEP} frames x {calls1} calls ({dt1:.1f} s), 1 thread",
+                                "python_reference_note": "the Python reference itself cannot travel to this box; in the development "
+                                                         "container it ran at 1.0-1.8e4 env-steps/s per process and 1.4e5 with an "
+                                                         "8-process pool (BASELINE.md section 2)"}
     if extras:
         line["extras"] = extras
     print(json.dumps(line))
