@@ -256,12 +256,16 @@ __device__ __forceinline__ void computer_ai(Env<R>& e) {
     const R dy_gt = (e.py <= R(360)) ? R(6) : ((e.oy > R(200)) ? R(-2) : R(0));   // :292-300
     e.ody = y_lt ? dy_lt : (y_gt ? dy_gt : e.ody);
     // :303-305, only inside the `puck.y > opponent.y` branch
-    R gx, gy, nvx = e.pdx, nvy = e.pdy;
+    R gx, gy;
     M::sub2(gx, gy, e.px, e.py, e.ox, e.oy);
     const bool near = y_gt && (M::abs_(gy) < R(40)) && (M::abs_(gx) < R(40));
-    M::add2(nvx, nvy, R(2), R(2));
-    e.pdx = near ? nvx : e.pdx;
-    e.pdy = near ? nvy : e.pdy;
+    if (M::exact) {
+        e.pdx = near ? e.pdx + R(2) : e.pdx;
+        e.pdy = near ? e.pdy + R(2) : e.pdy;
+    } else {
+        const R inc = near ? R(2) : R(0);          // one select, one packed add with a broadcast operand
+        M::add2(e.pdx, e.pdy, inc, inc);
+    }
     mallet_update<R>(e.ox, e.oy, e.odx, e.ody, K<R>::opp_lo, K<R>::opp_hi);    // :307
 }
 
