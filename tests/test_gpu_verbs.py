@@ -199,3 +199,19 @@ def test_first_frame_then_step_matches_reference(golden_dir):
     assert np.array_equal(bits(g["obs_next"][1:]), bits(out.obs_next.cpu().numpy()))
     assert np.array_equal(g["reward"][1:].astype(np.float64), out.reward.cpu().numpy())
     assert np.array_equal(g["score"][1:], out.score.cpu().numpy()) and np.array_equal(g["done"][1:], out.done.cpu().numpy())
+
+
+def test_observability_payloads_have_the_reference_wire_format():
+    import json
+    from air_hockey_training_environment_b200 import BatchedAirHockey
+    from air_hockey_training_environment_b200.observability import components_payload, scores_csv_aggregate, scores_payload
+    env = BatchedAirHockey(64, dtype=torch.float64, seed=1)
+    c = components_payload(env, 3)
+    assert c == {"puck": {"location": [450, 240], "velocity": [-3.0, 0.0]},                 # airhockey.py:124-132
+                 "robot": {"location": [350, 240], "velocity": [0.0, 0.0]},
+                 "opponent": {"location": [550, 240], "velocity": [0.0, 0.0]}}
+    assert scores_payload(env, 3) == {"robot_score": 0, "opponent_score": 0}                # airhockey.py:57
+    env.step(None, K=500, out=env.make_outputs(500, ()))
+    json.dumps({"components": components_payload(env, 5), "scores": scores_payload(env, 5)})
+    agg = scores_csv_aggregate(env.stats())
+    assert agg["frames"] == 64 * 500 and agg["robot_goal"] + agg["opponent_goal"] > 0
