@@ -28,7 +28,7 @@ SYMBOLS = ("ah_strerror", "ah_abi_version", "ah_last_cuda_error", "ah_create", "
 
 
 class AhConfig(C.Structure):
-    _fields_ = [("dot_fma", C.c_int32), ("friction", C.c_int32), ("reserved", C.c_int32 * 6)]
+    _fields_ = [("dot_fma", C.c_int32), ("friction", C.c_int32), ("no_prefetch", C.c_int32), ("reserved", C.c_int32 * 5)]
 
 
 class AhRing(C.Structure):

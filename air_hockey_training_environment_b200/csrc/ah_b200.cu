@@ -702,7 +702,7 @@ int launch_step(ah_env* env, const ah_step_io* io, int K, cudaStream_t s) {
         else if (mode == ah::MODE_SIM) AH_LAUNCH(ACT_, ah::MODE_SIM); else AH_LAUNCH(ACT_, ah::MODE_GENERIC); } while (0)
     bool launched = false;
     if constexpr (sizeof(R) == 4) {
-        if (act == 1 && mode == ah::MODE_LEAN && K <= 2 && env->n >= 65536 && !getenv("AH_NO_PREFETCH")) {
+        if (act == 1 && mode == ah::MODE_LEAN && K <= 2 && env->n >= 65536 && !env->cfg.no_prefetch) {
             // HBM-bound regime: persistent grid with next-env prefetch (see step_kernel<..., PF>)
             const unsigned pf_grid = (unsigned)(env->sms * 3 < want ? env->sms * 3 : want);
             ah::step_kernel<R, 1, ah::MODE_LEAN, true><<<pf_grid, ah::kThreads, 0, s>>>(a);

@@ -101,7 +101,8 @@ typedef struct ah_config {
     int32_t dot_fma;    /* 1: the 2-vector dot products are fma(b,d,fl(a*c)) like numpy/OpenBLAS (default) */
     int32_t friction;   /* 1: apply Puck.friction_on_puck (puck.py:73-88) before the speed clamp; the      */
                         /*    reference never calls it (dead code), so the default is 0                    */
-    int32_t reserved[6];
+    int32_t no_prefetch; /* 1: never use the small-K persistent/prefetching variant of the step kernel (tuning / tests) */
+    int32_t reserved[5];
 } ah_config;
 
 /* ---- optional fused replay/rollout ring (replaces MemoryBuffer.append, lib/buffer.py:24-32, fed with the

@@ -289,19 +289,17 @@ def test_host_stepper_round_trip_is_lossless():
 
 # ---------------------------------------------------------------- the HBM-bound small-K variant (persistent grid + prefetch)
 @pytest.mark.parametrize("K", [1, 2])
-def test_prefetch_variant_is_bitwise_identical(K, monkeypatch):
+def test_prefetch_variant_is_bitwise_identical(K):
     """For K <= 2 and n >= 65,536 the FP32 LEAN launch uses a persistent grid that prefetches the next env's rows;
-    it must produce exactly what the one-env-per-thread kernel produces (AH_NO_PREFETCH=1 selects the latter)."""
+    it must produce exactly what the one-env-per-thread kernel produces (`prefetch=False` selects the latter)."""
     n = (1 << 17) + 1000                                   # not a multiple of the grid: exercises the loop tail
-    a, b = make_env(n, seed=17), make_env(n, seed=17)
+    a, b = make_env(n, seed=17), make_env(n, seed=17, prefetch=False)
     fields = ("reward", "done", "score", "game_over", "obs_next")
     gen = torch.Generator(device=a.device).manual_seed(3)
     for it in range(40):
         acts = torch.randint(0, 4, (K, n), dtype=torch.int8, device=a.device, generator=gen)
         acts = acts[0].contiguous() if K == 1 else acts
-        monkeypatch.delenv("AH_NO_PREFETCH", raising=False)
         oa = a.step(acts, K=K, out=a.make_outputs(K, fields))
-        monkeypatch.setenv("AH_NO_PREFETCH", "1")
         ob = b.step(acts, K=K, out=b.make_outputs(K, fields))
         for f in fields:
             assert torch.equal(getattr(oa, f), getattr(ob, f)), (it, f)
