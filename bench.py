@@ -375,7 +375,7 @@ def run_rollout_k1(env, dev, n):
                          "traffic": 127331072.0 if n == (1 << 20) else None,
                          "algorithmic_bytes_per_launch": b, "bytes_per_env_step": b / n,
                          "note": ("state (71 MB) < L2 (126 MB): ncu shows 127 MB of DRAM traffic for the 184.5 MB algorithmic "
-                                  "bytes (profiles/r1f_other_variants.md); see rollout_k1_4m for the L2-proof point")
+                                  "bytes (profiles/r1g_other_variants.md); see rollout_k1_4m for the L2-proof point")
                          if n == (1 << 20) else "state 285 MB > 126 MB L2: algorithmic bytes are DRAM bytes"}}
 
 
