@@ -233,7 +233,8 @@ step_kernel(const StepArgs<R> a) {
     // instead of four compares and four selects per frame.  Entry 4 = "any other int": no nudge.
     __shared__ V2 s_nudge[8];
     __shared__ __align__(16) float s_actor[ACT == 4 ? 128 : 4];     // AH_ACT_POLICY: the actor's 114 weights
-    if (ACT == 4 && threadIdx.x < AH_ACTOR_NWEIGHTS) s_actor[threadIdx.x] = reinterpret_cast<const float*>(a.actions)[threadIdx.x];
+    if (ACT == 4)
+        for (int t = threadIdx.x; t < AH_ACTOR_NWEIGHTS; t += blockDim.x) s_actor[t] = reinterpret_cast<const float*>(a.actions)[t];
     if (threadIdx.x < AH_NSTATS) bs.v[threadIdx.x] = 0;
     if (threadIdx.x == 0) { bs.len_sq = 0ull; bs.warps_done = 0; }
     if (threadIdx.x < 8) {
@@ -679,7 +680,11 @@ int launch_step(ah_env* env, const ah_step_io* io, int K, cudaStream_t s) {
     a.dot_fma = env->cfg.dot_fma; a.friction = env->cfg.friction; a.blk = env->blk;
     a.actions_out = io->actions_out; a.probs_out = (R*)io->probs_out;
     const int max_blocks = sizeof(R) == 4 ? env->blocks_f32 : env->blocks_f64;
-    int64_t want = (env->n + ah::kThreads - 1) / ah::kThreads;
+    // block size: 256 threads, halved (down to 64) while the grid would leave SMs unevenly filled (< 4 blocks per SM):
+    // a 65,536-env rollout is 256 blocks of 256 (1.7 per SM: some SMs get twice the work of others) but 1,024 of 64
+    int threads = ah::kThreads;
+    while (threads > 64 && (env->n + threads - 1) / threads < 4 * (int64_t)env->sms) threads >>= 1;
+    int64_t want = (env->n + threads - 1) / threads;
     const unsigned grid = (unsigned)(want < max_blocks ? want : max_blocks);
     // pick the specialised variant the given pointers allow
     const bool per_frame_any = io->reward || io->done || io->score || io->game_over;
@@ -697,21 +702,22 @@ int launch_step(ah_env* env, const ah_step_io* io, int K, cudaStream_t s) {
         case AH_ACT_POLICY: act = 4; break;
         default: return AH_EINVAL;
     }
-#define AH_LAUNCH(ACT_, MODE_) ah::step_kernel<R, ACT_, MODE_><<<grid, ah::kThreads, 0, s>>>(a)
+#define AH_LAUNCH(ACT_, MODE_) ah::step_kernel<R, ACT_, MODE_><<<grid, threads, 0, s>>>(a)
 #define AH_LAUNCH_MODE(ACT_) do { if (mode == ah::MODE_LEAN) AH_LAUNCH(ACT_, ah::MODE_LEAN); \
         else if (mode == ah::MODE_SIM) AH_LAUNCH(ACT_, ah::MODE_SIM); else AH_LAUNCH(ACT_, ah::MODE_GENERIC); } while (0)
     bool launched = false;
     if constexpr (sizeof(R) == 4) {
         if (act == 1 && mode == ah::MODE_LEAN && K <= 2 && env->n >= 65536 && !env->cfg.no_prefetch) {
             // HBM-bound regime: persistent grid with next-env prefetch (see step_kernel<..., PF>)
-            const unsigned pf_grid = (unsigned)(env->sms * 3 < want ? env->sms * 3 : want);
+            const int64_t pf_want = (env->n + ah::kThreads - 1) / ah::kThreads;
+            const unsigned pf_grid = (unsigned)(env->sms * 3 < pf_want ? env->sms * 3 : pf_want);
             ah::step_kernel<R, 1, ah::MODE_LEAN, true><<<pf_grid, ah::kThreads, 0, s>>>(a);
             launched = true;
         }
     }
     if (launched) {
     } else if (act == 4) {
-        ah::step_kernel<R, 4, ah::MODE_GENERIC><<<grid, ah::kThreads, 0, s>>>(a);
+        ah::step_kernel<R, 4, ah::MODE_GENERIC><<<grid, threads, 0, s>>>(a);
     } else if (act == 1) AH_LAUNCH_MODE(1); else if (act == 2) AH_LAUNCH_MODE(2); else AH_LAUNCH_MODE(3);
 #undef AH_LAUNCH_MODE
 #undef AH_LAUNCH
@@ -930,10 +936,12 @@ int ah_get_counters(ah_env* env, uint64_t* d_out2, void* stream) {
 
 int ah_launch_info(const ah_env* env, int* blocks, int* threads, int* sms) {
     if (!env) return AH_EINVAL;
-    int64_t want = (env->n + ah::kThreads - 1) / ah::kThreads;
+    int th = ah::kThreads;                     // same rule as launch_step
+    while (th > 64 && (env->n + th - 1) / th < 4 * (int64_t)env->sms) th >>= 1;
+    int64_t want = (env->n + th - 1) / th;
     const int max_blocks = env->dtype == AH_F32 ? env->blocks_f32 : env->blocks_f64;
     if (blocks) *blocks = (int)(want < max_blocks ? want : max_blocks);
-    if (threads) *threads = ah::kThreads;
+    if (threads) *threads = th;
     if (sms) *sms = env->sms;
     return AH_OK;
 }
