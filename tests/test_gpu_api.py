@@ -409,3 +409,23 @@ def test_guard_bands_survive_every_kernel(dtype):
         assert bool((raw[:pad] == 77).all()) and bool((raw[pad + numel:] == 77).all()), "guard band overwritten"
     assert not bool((out.reward == 77).any()) and not bool((pol.probs == 77).any())    # interiors were written
     assert env.stats()["frames"] == n * K * 43 and env.stats()["nonfinite"] == 0
+
+
+def test_8m_envs_on_one_gpu():
+    """BASELINE config 4's TOTAL size (2^23 envs) on a single GPU: 64-bit row offsets, stats, invariants."""
+    n, K = 1 << 23, 8
+    env = make_env(n, seed=5)
+    out = env.make_outputs(K, ("reward", "done", "score", "game_over", "obs_next"))
+    for _ in range(6):
+        env.step(None, K=K, out=out)
+    st = env.stats()
+    assert st["frames"] == 6 * K * n and st["nonfinite"] == 0
+    assert int((out.score != 0).sum()) > 0 and int(out.reward[-1, -1000:].abs().sum()) > 0      # the far end was written
+    small = make_env(4096, seed=5)                         # the first 4096 games of the big batch, alone
+    for _ in range(6):
+        small.step(None, K=K)
+    assert torch.equal(env.puck[:4096], small.puck) and torch.equal(env.meta[:4096], small.meta)
+    tail = make_env(4096, seed=5, env_id0=n - 4096)        # and the last 4096
+    for _ in range(6):
+        tail.step(None, K=K)
+    assert torch.equal(env.puck[-4096:], tail.puck) and torch.equal(env.meta[-4096:], tail.meta)

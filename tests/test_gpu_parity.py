@@ -377,3 +377,19 @@ def test_fp32_long_rollout_matches_reference_behaviour_statistics():
     ref = {-4: 0.0099, -2: 0.5048, 0: 0.4788, 2: 0.0038, 4: 0.0027}             # reference reward histogram
     for r, p in ref.items():
         assert abs(h[r + 8] - p) < 0.01 + 0.1 * p, (r, h[r + 8], p)
+
+
+def test_fp64_max_k_single_launch_vs_oracle():
+    """K = 4096 (the ABI's maximum) in ONE launch, Philox actions and resets: bit-exact vs the oracle."""
+    n, K, seed = 384, 4096, 77
+    st, sc = oracle.initial_state(n)
+    ref = oracle.run_frames(st, sc, K, seed=seed, nthreads=4, want=("reward", "score", "game_over"))
+    env = make_env(n, seed=seed)
+    out = env.make_outputs(K, ("reward", "score", "game_over", "actions"))
+    env.step(None, K=K, out=out)
+    assert np.array_equal(bits(st), bits(get_state13(env))) and np.array_equal(sc, get_scores(env))
+    assert np.array_equal(ref["reward"], out.reward.cpu().numpy().astype(np.int32))
+    assert np.array_equal(ref["score"], out.score.cpu().numpy()) and np.array_equal(ref["game_over"], out.game_over.cpu().numpy())
+    want_actions = np.array([[oracle.rng_action(seed, e, f) for e in range(4)] for f in range(0, K, 97)], np.int8)
+    assert np.array_equal(want_actions, out.actions.cpu().numpy()[::97, :4])      # the Philox action stream itself
+    assert (ref["game_over"] != 0).sum() > 100
