@@ -269,6 +269,9 @@ __device__ __forceinline__ void computer_ai(Env<R>& e) {
     mallet_update<R>(e.ox, e.oy, e.odx, e.ody, K<R>::opp_lo, K<R>::opp_hi);    // :307
 }
 
+__device__ __forceinline__ void opaque(float& v) { asm volatile("" : "+f"(v)); }
+__device__ __forceinline__ void opaque(double& v) { asm volatile("" : "+d"(v)); }
+
 // ---- the common tail of AirHockey.update_state  environment/airhockey.py:112-122 ----
 // The two contact tests (robot first, then opponent, :113-114) share ONE rarely-taken branch; inside it the
 // opponent's test is re-evaluated against the puck as the robot's response left it, as the reference does.
@@ -285,9 +288,12 @@ __device__ __forceinline__ void physics_tail(Env<R>& e, bool dot_fma, bool frict
     R dq = contact_dist_sq<R>(e.px, e.py, e.ox, e.oy, dot_fma, odx_, ody_);
     const bool slow = !(dr > K<R>::radius_sq) || !(dq > K<R>::radius_sq) || (!ALWAYS_LIMIT && (speed_dirty || friction));
     if (slow) {                                                                  // :210 (touching counts as contact)
-        if (!(dr > K<R>::radius_sq)) {
+        // (opaque copies: keep the two inner compares INSIDE the rare branch instead of hoisted onto the common path)
+        R dr_in = dr;
+        opaque(dr_in); opaque(dq);
+        if (!(dr_in > K<R>::radius_sq)) {
             c_robot += 1;
-            contact_response<R>(e.px, e.py, e.pdx, e.pdy, e.rx, e.ry, e.rdx, e.rdy, rdx_, rdy_, dr, dot_fma);
+            contact_response<R>(e.px, e.py, e.pdx, e.pdy, e.rx, e.ry, e.rdx, e.rdy, rdx_, rdy_, dr_in, dot_fma);
             dq = contact_dist_sq<R>(e.px, e.py, e.ox, e.oy, dot_fma, odx_, ody_);
         }
         if (!(dq > K<R>::radius_sq)) {
