@@ -393,3 +393,21 @@ def test_fp64_max_k_single_launch_vs_oracle():
     want_actions = np.array([[oracle.rng_action(seed, e, f) for e in range(4)] for f in range(0, K, 97)], np.int8)
     assert np.array_equal(want_actions, out.actions.cpu().numpy()[::97, :4])      # the Philox action stream itself
     assert (ref["game_over"] != 0).sum() > 100
+
+
+def test_fp64_soak_65536_envs_2000_frames_vs_oracle():
+    """1.3e8 env-steps, Philox actions + resets, FP64: final state, scores, RNG counters and every tally bit-exact."""
+    n, T, seed = 65536, 2000, 4242
+    st, sc = oracle.initial_state(n)
+    ref = oracle.run_frames(st, sc, T, seed=seed, nthreads=16, want=())
+    env = make_env(n, seed=seed)
+    for _ in range(T // 250):
+        env.step(None, K=250, out=env.make_outputs(250, ()))
+    assert np.array_equal(bits(st), bits(get_state13(env)))
+    assert np.array_equal(sc, get_scores(env))
+    assert np.array_equal(ref["reset_cursor"], env.reset_count.cpu().numpy())
+    g, o = env.stats(), dict(zip(oracle.STAT_NAMES, ref["stats"]))
+    for k in ("frames", "robot_goals", "opponent_goals", "robot_wins", "opponent_wins", "dones", "reward_sum",
+              "reward_sq_sum", "contacts_robot", "contacts_opponent"):
+        assert g[k] == o[k], k
+    assert g["games"] == g["robot_wins"] + g["opponent_wins"] > 10000
