@@ -92,7 +92,7 @@ class RolloutCollector:
 
     def __init__(self, env: BatchedAirHockey, T: int, policy: Optional[Callable[[torch.Tensor], torch.Tensor]] = None,
                  action_size: int = 4, use_graph: bool = True, seed: int = 0, fused_actor: bool = True,
-                 single_launch: bool = False):
+                 single_launch: Optional[bool] = None):
         self.env, self.T, self.A = env, int(T), int(action_size)
         n, dt, dev = env.n, env.dtype, env.device
         self.policy = policy if policy is not None else ActorMLP(8, action_size).to(device=dev, dtype=dt)
@@ -112,6 +112,8 @@ class RolloutCollector:
         self.gen.manual_seed(seed)
         # single_launch: the whole T-frame closed loop (actor forward, sampling, physics, reward, resets) runs in ONE
         # kernel launch with the env state in registers (BatchedAirHockey.step(policy_weights=...)); needs the fused actor
+        if single_launch is None:                 # default: the fastest path the policy allows
+            single_launch = self.fused is not None
         self.single_launch = bool(single_launch and self.fused is not None)
         self._out_all = StepOutputs(reward=self.rewards, done=self.dones, score=self.scores, game_over=self.game_over,
                                     obs_next=self.obs[1:], actions=self.actions, probs=self.probs)

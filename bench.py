@@ -412,7 +412,7 @@ def run_ppo_rollout(dev):
     from air_hockey_training_environment_b200.rollout import RolloutCollector
     n, T = 65536, 128
     res = {"envs": n, "frames": T, "unit": UNIT}
-    for name, kw in (("torch_policy_graph", dict(fused_actor=False)), ("fused_actor_graph", dict()),
+    for name, kw in (("torch_policy_graph", dict(fused_actor=False)), ("fused_actor_graph", dict(single_launch=False)),
                      ("single_launch", dict(single_launch=True))):
         env = BatchedAirHockey(n, dtype=torch.float32, device=dev, seed=7)
         col = RolloutCollector(env, T, seed=7, **kw)

@@ -93,7 +93,7 @@ def test_rollout_collector_is_zero_copy_and_consistent(use_graph):
     n, T = 4096, 16
     env = BatchedAirHockey(n, seed=5)
     twin = BatchedAirHockey(n, seed=5)
-    col = RolloutCollector(env, T, use_graph=use_graph, seed=1)
+    col = RolloutCollector(env, T, use_graph=use_graph, seed=1, single_launch=False)
     for it in range(3):
         r = col.collect()
         torch.cuda.synchronize()
@@ -169,7 +169,7 @@ def test_single_launch_policy_rollout_equals_frame_by_frame():
                 m.weight.normal_(0, 0.3); m.bias.normal_(0, 0.3)
         actor.net[0].weight.mul_(0.01)
     ca = RolloutCollector(ea, T, policy=actor, single_launch=True)
-    cb = RolloutCollector(eb, T, policy=actor, use_graph=False)
+    cb = RolloutCollector(eb, T, policy=actor, use_graph=False, single_launch=False)
     for it in range(3):
         ra, rb = ca.collect(), cb.collect()
         for k in ("obs", "actions", "rewards", "dones", "scores", "game_over"):

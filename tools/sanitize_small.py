@@ -24,7 +24,7 @@ for dt in (torch.float32, torch.float64):
     env.get_state("robot"); env.get_state("opponent")
     r, s, d = env.rewards(); env.update_score(s); env.reset(total=True, mask=(s != 0))
     env.stats(clear=True); env.counters(); env.compiled_without_fma_contraction()
-    col = RolloutCollector(env, 6, use_graph=False); col.collect()
+    col = RolloutCollector(env, 6, use_graph=False, single_launch=False); col.collect()
     col2 = RolloutCollector(env, 6, single_launch=True); col2.collect()
 big = BatchedAirHockey(70000, seed=2)              # prefetch variant (K <= 2, n >= 65536)
 big.step(torch.randint(0, 4, (70000,), dtype=torch.int8, device=big.device), K=1)
