@@ -79,3 +79,19 @@ def test_product_package_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.replace("no oracle", ""), f"{f} mentions the oracle"
+
+
+def test_header_is_plain_c_and_struct_sizes_agree(tmp_path):
+    """include/ah_b200.h must compile as C99 (no C++/torch types on the boundary) and its struct sizes must equal
+    the ctypes mirrors'."""
+    import subprocess
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "ah_b200.h"\n'
+                   'int main(void){ printf("%zu %zu %zu %d %d\\n", sizeof(ah_config), sizeof(ah_ring), sizeof(ah_step_io), '
+                   'AH_NSTATS, AH_ACTOR_NWEIGHTS); return 0; }\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                    str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert [int(v) for v in out] == [C.sizeof(_capi.AhConfig), C.sizeof(_capi.AhRing), C.sizeof(_capi.AhStepIO),
+                                     _capi.AH_NSTATS, _capi.AH_ACTOR_NWEIGHTS]
