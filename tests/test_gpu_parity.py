@@ -411,3 +411,32 @@ def test_fp64_soak_65536_envs_2000_frames_vs_oracle():
               "reward_sq_sum", "contacts_robot", "contacts_opponent"):
         assert g[k] == o[k], k
     assert g["games"] == g["robot_wins"] + g["opponent_wins"] > 10000
+
+
+def test_fp64_scrambled_states_at_scale_vs_oracle():
+    """65,536 random non-integer initial states (mallets overlapping the puck, coincident centres, speeds beyond the
+    limits, scores one goal from game over, out-of-range actions): every rare branch many times; bit-exact for 300 frames."""
+    from oracle.gen_golden import scrambled_states
+    n, T = 65536, 300
+    rng = np.random.default_rng(909)
+    init = scrambled_states(rng, n)
+    init_scores = rng.integers(0, 10, (n, 2)).astype(np.int32)
+    init_scores[: n // 4] = rng.integers(8, 10, (n // 4, 2))
+    actions = rng.integers(-2, 7, (T, n)).astype(np.int8)
+    table = rng.uniform(-12, 12, (n, 24, 2))                  # beyond the speed limits on purpose (speed_dirty path)
+    st, sc = init.copy(), init_scores.copy()
+    ref = oracle.run_frames(st, sc, T, actions=actions, reset_table=table, record_every=100, nthreads=16,
+                            want=("reward", "score", "done", "game_over"))
+    assert not ref["reset_overflow"]
+    env = make_env(n)
+    put_state(env, init, init_scores)
+    res = run_gpu(env, T, actions, table, 100)
+    assert np.array_equal(bits(ref["states_rec"]), bits(res["states"]))
+    assert np.array_equal(ref["scores_rec"], res["scores"])
+    assert np.array_equal(ref["reward"], res["reward"].astype(np.int32))
+    for k in ("score", "done", "game_over"):
+        assert np.array_equal(ref[k], res[k]), k
+    o = dict(zip(oracle.STAT_NAMES, ref["stats"]))
+    g = env.stats()
+    assert g["contacts_robot"] == o["contacts_robot"] > 20000 and g["contacts_opponent"] == o["contacts_opponent"] > 20000
+    assert (ref["game_over"] != 0).sum() > 5000
