@@ -116,3 +116,77 @@ class PPOLearner:
         if c.fused is not None:
             c.fused.refresh()                  # the in-kernel actor reads the new weights from the next launch on
         return {"actor_loss": la, "critic_loss": lc, "mean_return": float(returns.mean()), "mean_reward": float(c.rewards.mean())}
+
+
+# ------------------------------------------------------------------------------------------------ A2C
+class A2CActor(nn.Module):
+    """lib/agents/a2c/model.py:50-60: Dense(8, relu) - BatchNorm - Dense(4, softmax)."""
+
+    def __init__(self, state_size: int = 8, action_size: int = 4):
+        super().__init__()
+        self.net = nn.Sequential(nn.Linear(state_size, state_size), nn.ReLU(), nn.BatchNorm1d(state_size),
+                                 nn.Linear(state_size, action_size))
+        for m in self.net:
+            if isinstance(m, nn.Linear):
+                nn.init.normal_(m.weight, std=0.05)
+                nn.init.zeros_(m.bias)
+        self.eval()
+
+    def forward(self, obs: torch.Tensor) -> torch.Tensor:
+        return torch.softmax(self.net(obs), dim=-1)
+
+
+class A2CCritic(nn.Module):
+    """lib/agents/a2c/model.py:64-75: Dense(8, relu) - BatchNorm - Dense(1, linear)."""
+
+    def __init__(self, state_size: int = 8):
+        super().__init__()
+        self.net = nn.Sequential(nn.Linear(state_size, state_size), nn.ReLU(), nn.BatchNorm1d(state_size), nn.Linear(state_size, 1))
+
+    def forward(self, obs: torch.Tensor) -> torch.Tensor:
+        return self.net(obs).squeeze(-1)
+
+
+def a2c_actor_loss(advantage_targets: torch.Tensor, y_pred: torch.Tensor) -> torch.Tensor:
+    """Keras ``categorical_crossentropy(y_true, y_pred)`` with the reference's targets: a one-hot row whose "1" is replaced
+    by the advantage (lib/agents/a2c/a2c.py:137-143).  Keras renormalises y_pred, clips it to [1e-7, 1 - 1e-7] and
+    returns -sum_j y_true_j * log(y_pred_j) per sample; the fit minimises its mean."""
+    p = y_pred / y_pred.sum(dim=-1, keepdim=True)
+    p = p.clamp(1e-7, 1 - 1e-7)
+    return -(advantage_targets * torch.log(p)).sum(dim=-1).mean()
+
+
+class A2CLearner:
+    """Monte-Carlo returns (gamma 0.95, a2c/model.py:33), advantage-weighted cross-entropy for the actor, Huber for the
+    critic, Adam(eps=1e-3) -- lib/agents/a2c/a2c.py:107-148.  The policy is an ordinary torch module, so the collector
+    runs it through the CUDA-graph path (any torch policy works zero-copy; only the PPO-shaped actor is in-kernel)."""
+
+    def __init__(self, collector: RolloutCollector, gamma: float = 0.95, actor_lr: float = 1e-5, critic_lr: float = 1e-5,
+                 epochs: int = 10):
+        self.col, self.gamma, self.epochs = collector, gamma, epochs
+        self.actor = collector.policy
+        dev, dt = collector.env.device, collector.env.dtype
+        self.critic = A2CCritic().to(device=dev, dtype=dt)
+        self.opt_actor = torch.optim.Adam(self.actor.parameters(), lr=actor_lr, eps=1e-3)
+        self.opt_critic = torch.optim.Adam(self.critic.parameters(), lr=critic_lr, eps=1e-3)
+
+    def update(self) -> Dict[str, float]:
+        c = self.col
+        T, n = c.T, c.env.n
+        obs = c.obs[:T].reshape(T * n, 8)
+        returns = discounted_returns(c.rewards, self.gamma).reshape(T * n)
+        self.critic.eval()
+        with torch.no_grad():
+            adv = returns - self.critic(obs)
+        targets = torch.zeros(T * n, c.A, dtype=obs.dtype, device=obs.device)
+        targets.scatter_(1, c.actions.reshape(T * n, 1).long(), adv.unsqueeze(1))
+        self.actor.train(); self.critic.train()
+        la = lc = 0.0
+        for _ in range(self.epochs):
+            loss_a = a2c_actor_loss(targets, self.actor(obs))
+            self.opt_actor.zero_grad(set_to_none=True); loss_a.backward(); self.opt_actor.step()
+            loss_c = huber_loss(returns, self.critic(obs)).mean()
+            self.opt_critic.zero_grad(set_to_none=True); loss_c.backward(); self.opt_critic.step()
+            la, lc = float(loss_a.detach()), float(loss_c.detach())
+        self.actor.eval(); self.critic.eval()
+        return {"actor_loss": la, "critic_loss": lc, "mean_reward": float(c.rewards.mean())}

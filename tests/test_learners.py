@@ -71,3 +71,40 @@ def test_ppo_update_loop_runs_on_device_and_refreshes_the_kernel_actor():
         ref = col.policy(r["obs"][5])
     assert torch.allclose(r["probs"][5], ref, atol=1e-5)
     assert env.stats()["frames"] == 4 * 32 * 4096
+
+
+def test_a2c_actor_loss_matches_keras_categorical_crossentropy():
+    from air_hockey_training_environment_b200.learners import a2c_actor_loss
+    rng = np.random.default_rng(2)
+    B, A = 256, 4
+    pred = rng.dirichlet(np.ones(A), B)
+    act = rng.integers(0, A, B)
+    adv = rng.normal(0, 2, B)
+    y_true = np.zeros((B, A)); y_true[np.arange(B), act] = adv                  # a2c.py:137-141
+    p = np.clip(pred / pred.sum(-1, keepdims=True), 1e-7, 1 - 1e-7)
+    want = np.mean(-np.sum(y_true * np.log(p), axis=-1))
+    got = a2c_actor_loss(torch.tensor(y_true), torch.tensor(pred)).item()
+    assert abs(got - want) < 1e-12
+
+
+@pytest.mark.gpu
+def test_a2c_update_loop_with_a_plain_torch_policy_through_the_graph_path():
+    from air_hockey_training_environment_b200 import BatchedAirHockey
+    from air_hockey_training_environment_b200.learners import A2CActor, A2CLearner
+    from air_hockey_training_environment_b200.rollout import RolloutCollector
+    torch.manual_seed(0)
+    env = BatchedAirHockey(4096, seed=4)
+    actor = A2CActor().to(env.device)
+    col = RolloutCollector(env, 16, policy=actor, use_graph=True)
+    assert col.fused is None and not col.single_launch                        # an arbitrary torch policy: graph path
+    learner = A2CLearner(col, actor_lr=1e-3, critic_lr=1e-3, epochs=3)
+    w0 = actor.net[0].weight.clone()
+    logs = []
+    for _ in range(3):
+        col.collect()
+        logs.append(learner.update())
+    assert all(np.isfinite(v) for log in logs for v in log.values())
+    assert not torch.equal(w0, actor.net[0].weight)
+    r = col.collect()                                                         # the captured graph reads the updated weights
+    with torch.no_grad():
+        assert torch.allclose(r["probs"][3], actor(r["obs"][3]), atol=1e-6)
