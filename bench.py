@@ -181,7 +181,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n, K = args.envs_per_gpu, FRAMES_PER_STEP
-    W = max(3, args.warmup)
+    # warm-up: never fewer than 260 steps (2,080 frames): all games start from the same constructor state and stay
+    # correlated (warp-uniform branches => optimistic timings) until about one mean game length (~1,900 frames) has passed
+    W = max(260, args.warmup)
 
     env = BatchedAirHockey(n, dtype=torch.float32, device=dev, seed=1234, env_id0=rank * n)
     out = env.make_outputs(K, ("reward", "done", "score", "game_over", "obs_next"))
