@@ -223,6 +223,9 @@ def main():
         sampler.start()
         time.sleep(0.3)
     barrier()
+    for i in range(50):                       # the GPU idled while the sampler started: bring the clocks back up (untimed)
+        one_step(i)
+    barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.time()
     ev0.record(stream)
@@ -365,7 +368,7 @@ def run_rollout_k1(env, dev, n):
     if env is None:
         from air_hockey_training_environment_b200 import BatchedAirHockey
         env = BatchedAirHockey(n, dtype=torch.float32, device=dev, seed=99)
-        env.step(None, K=400, out=env.make_outputs(400, ()))
+        env.step(None, K=2000, out=env.make_outputs(2000, ()))        # decorrelate the games
     out = env.make_outputs(1, ("reward", "done", "score", "game_over", "obs_next"))
     acts = [torch.randint(0, 4, (n,), dtype=torch.int8, device=dev) for _ in range(4)]
     ms = _time_loop(dev, lambda i: env.step(acts[i % 4], K=1, out=out), 20, 200)
@@ -417,6 +420,7 @@ def run_ppo_rollout(dev):
     for name, kw in (("torch_policy_graph", dict(fused_actor=False)), ("fused_actor_graph", dict(single_launch=False)),
                      ("single_launch", dict(single_launch=True))):
         env = BatchedAirHockey(n, dtype=torch.float32, device=dev, seed=7)
+        env.step(None, K=2000, out=env.make_outputs(2000, ()))        # decorrelate the games
         col = RolloutCollector(env, T, seed=7, **kw)
         for _ in range(3):
             col.collect()
@@ -442,6 +446,7 @@ def run_fp64(dev):
     from air_hockey_training_environment_b200 import BatchedAirHockey
     n = 4096
     env = BatchedAirHockey(n, dtype=torch.float64, device=dev, seed=3)
+    env.step(None, K=2000, out=env.make_outputs(2000, ()))            # decorrelate the games
     out = env.make_outputs(100, ("reward", "done", "score", "game_over", "obs_next"))
     acts = torch.randint(0, 4, (100, n), dtype=torch.int8, device=dev)
     ms = _time_loop(dev, lambda i: env.step(acts, K=100, out=out), 2, 10)
