@@ -146,7 +146,8 @@ class RolloutCollector:
         self.env.get_state("robot", out=self.obs[0])
         g = torch.cuda.CUDAGraph()
         g.register_generator_state(self.gen)
-        with torch.cuda.graph(g):
+        # thread_local: other threads (NCCL's watchdog at world_size > 1) may issue CUDA calls during the capture
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
             self._loop()
         self._graph = g
         self.env.load_state_dict(saved)                          # the capture pass itself ran nothing, but be explicit

@@ -127,19 +127,95 @@ def cpu_port_run(steps: int, warmup: int, envs: int = 1 << 18, threads: int = 0,
     return envs * FRAMES_PER_STEP * calls / dt, threads, dt, calls, envs
 
 
+def cpu_baseline(port_seconds: float):
+    """The reference's CPU path on THIS box's host cores, timed beside the GPU numbers (rank 0, N = 1).  `value` is the
+    reference's own Python implementation (kind "reference": oracle/_ref, BASELINE config 1 = 10,000 frames per
+    process) with a multiprocessing pool over all cores, pure-simulation variant (the most favourable to it); the
+    one-process figure, the socket-stub variant and the C port (kind "port") are reported beside it."""
+    v, cores, dt, calls, envs = cpu_port_run(0, 1, seconds=port_seconds)
+    v1, _, dt1, calls1, envs1 = cpu_port_run(0, 1, envs=1 << 15, threads=1, seconds=min(2.0, port_seconds))
+    port = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{envs} envs x {FRAMES_PER_STEP} frames x {calls} calls ({dt:.1f} s), OpenMP over {cores} threads "
+                      "(oracle/ah_oracle.c: C restatement, bit-exact vs the Python reference)",
+            "one_thread_value": v1,
+            "one_thread_sample": f"{envs1} envs x {FRAMES_PER_STEP} frames x {calls1} calls ({dt1:.1f} s), 1 thread"}
+    ref = python_reference_timing(10000)
+    if "pure_sim" not in ref:
+        return dict(port, python_reference=ref)
+    ps, ss = ref["pure_sim"], ref["socket_stub"]
+    return {"value": ps["pool_sum_of_rates"], "unit": UNIT, "cores": ref["host_cores"], "kind": "reference",
+            "language": "python", "reference_build": ref["reference"],
+            "sample": f"BASELINE config 1: single AirHockey env, random robot vs computerAI, {ref['frames_per_process']} frames "
+                      f"per process; multiprocessing.Pool({ref['host_cores']}) = all host cores, one env per worker, sum of "
+                      "per-worker rates; Redis posts + CSV rows no-op'd (pure simulation, most favourable to the reference)",
+            "one_process_value": ps["one_process"], "pool_wall_clock_value": ps["pool_wall_clock_rate"],
+            "socket_stub": {"one_process_value": ss["one_process"], "pool_sum_of_rates": ss["pool_sum_of_rates"],
+                            "pool_wall_clock_value": ss["pool_wall_clock_rate"],
+                            "what": "Redis stubbed at the client class: the JSON payload of every sub-update is still built "
+                                    "and encoded, the per-done CSV row still written (closest to shipped behaviour)"},
+            "sub_updates_per_s_one_process": ps["sub_updates_per_s_one_process"],
+            "goals_per_1000_frames": ps["goals_per_1000_frames"], "python": ref["python"], "numpy": ref["numpy"],
+            "port": port}
+
+
+def python_reference_timing(frames: int = 10000, timeout: float = 240.0):
+    """the reference's own Python loop (oracle/_ref, byte-compiled from /root/reference by
+    oracle/fetch_ref.py; the live sources where present) on THIS host: one process, then a pool over all cores, in the
+    socket-stub and pure-simulation variants.  Separate process tree: no fork after CUDA initialisation."""
+    try:
+        res = subprocess.run([sys.executable, "-m", "oracle.time_reference", "--frames", str(frames)], cwd=ROOT,
+                             capture_output=True, text=True, timeout=timeout)
+        if res.returncode != 0:
+            return {"unavailable": (res.stderr or "").strip().splitlines()[-1:]}
+        return json.loads(res.stdout.strip().splitlines()[-1])
+    except Exception as e:                                   # reference absent: the C port is reported alone
+        return {"unavailable": repr(e)}
+
+
 def run_reference_arm(args):
+    """`--impl reference`: the reference's own CPU implementation of the path on this box's host cores.  The Python
+    reference (oracle/_ref) with a multiprocessing pool over every core, one env per worker, each bench "step" =
+    `--ref-frames` frames of the Game.play loop on every worker (a bounded sample of the workload: the reference has no
+    batched form, so its throughput does not depend on how many envs the GPU arm carries).  Variant "pure_sim" (Redis
+    posts and CSV rows no-op'd) is the line's value: the most favourable to the reference.  The C port's number (kind
+    "port", ~10^3 x faster per core than the reference) is reported beside it, never as the value."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    v, threads, dt, calls, envs = cpu_port_run(args.steps, min(args.warmup, 5))
-    sample = (f"{envs} envs x {FRAMES_PER_STEP} frames per step, {calls} steps: a bounded sample of the "
-              f"{ENVS_PER_GPU}-envs-per-GPU workload; C port of the reference step (oracle/ah_oracle.c, bit-exact vs the "
-              "Python reference), OpenMP over all host threads")
+    from oracle import refshim
+    W = max(1, min(args.warmup, 5))
+    port_v, port_threads, _, _, port_envs = cpu_port_run(0, 2, seconds=2.0)
+    port = {"value": port_v, "unit": UNIT, "cores": port_threads, "kind": "port",
+            "sample": f"{port_envs} envs x {FRAMES_PER_STEP} frames per call for 2 s, OpenMP (oracle/ah_oracle.c)"}
+    if refshim.reference_available():
+        from oracle.time_reference import ReferencePool
+        frames = args.ref_frames
+        rates = {}
+        for variant in ("socket_stub", "pure_sim"):
+            pool = ReferencePool(variant=variant)
+            for _ in range(W):
+                pool.step(frames)
+            steps = args.steps if variant == "pure_sim" else max(2, min(args.steps, 5))
+            done, t0 = 0, time.perf_counter()
+            for _ in range(steps):
+                done += pool.step(frames)
+            dt = time.perf_counter() - t0
+            rates[variant] = (done / dt, dt, steps, pool.procs)
+            pool.close()
+        v, dt, steps, cores = rates["pure_sim"]
+        kind = "reference"
+        sample = (f"{cores} worker processes (all host cores) x 1 AirHockey env each x {frames} frames per step, {steps} steps; "
+                  f"the reference's own Python classes ({refshim.reference_kind()} from {os.path.relpath(refshim.REFERENCE_ROOT, ROOT) if refshim.REFERENCE_ROOT.startswith(ROOT) else refshim.REFERENCE_ROOT}), "
+                  "Game.play loop of BASELINE config 1, side channels no-op'd (most favourable variant)")
+        extra = {"language": "python", "variant": "pure_sim", "socket_stub_value": rates["socket_stub"][0], "port": port}
+    else:                                                     # should not happen: oracle/_ref ships with the snapshot
+        v, cores, dt, steps, envs = cpu_port_run(args.steps, W)
+        kind, sample, extra = "port", port["sample"], {"port": port, "note": "oracle/_ref absent: C port timed instead"}
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": calls,
-        "warmup": min(args.warmup, 5), "ms_per_step": 1e3 * dt / calls, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": W, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args.gpus), "sample": sample},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": dict({"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}, **extra),
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -152,6 +228,71 @@ def workload_name(gpus: int) -> str:
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
+ROLLOUT_STEPS = 16           # bench steps per "rollout": the episode/score statistics are all-reduced once per rollout
+
+
+class StatsReducer:
+    """The path's only exchange: once per rollout (every ROLLOUT_STEPS steps, and once more at the
+    end of a timed region) the int64[16] statistics vector the step kernel accumulated on the device is copied out and
+    cleared (`ah_stats`, one tiny launch) and, at N > 1, summed over the ranks with one asynchronous NCCL all-reduce
+    (128 B over NVLink; NCCL's stream waits for the step kernel, the next step's kernel does not wait for NCCL).  The
+    reduced vectors are accumulated so that the payload can be checked: frames == world x envs x K x steps."""
+
+    def __init__(self, env, world, dev, every=ROLLOUT_STEPS):
+        import torch
+        self.env, self.world, self.every = env, world, every
+        self.bufs = [torch.zeros(16, dtype=torch.int64, device=dev) for _ in range(2)]
+        self.acc = torch.zeros(16, dtype=torch.int64, device=dev)
+        self.pending, self.j, self.count, self.reductions = None, 0, 0, 0
+
+    def _collect(self):
+        if self.pending is not None:
+            work, buf = self.pending
+            if work is not None:
+                work.wait()                    # stream-level wait, no host sync
+            self.acc += buf
+            self.pending = None
+
+    def reduce(self):
+        import torch.distributed as dist
+        self._collect()
+        buf = self.bufs[self.j]
+        self.j ^= 1
+        self.env.stats_tensor(clear=True, out=buf)
+        work = dist.all_reduce(buf, async_op=True) if self.world > 1 else None
+        self.pending = (work, buf)
+        self.reductions += 1
+
+    def after_step(self):
+        self.count += 1
+        if self.count % self.every == 0:
+            self.reduce()
+
+    def flush(self):
+        self._collect()
+
+    def restart(self):
+        """Start a measured window: drain what earlier steps accumulated and zero the totals."""
+        self.reduce()
+        self._collect()
+        self.acc.zero_()
+        self.count, self.reductions = 0, 0
+
+    def finish(self):
+        if self.count % self.every != 0:
+            self.reduce()
+        self._collect()
+
+    def check(self, expected_frames: int):
+        v = self.acc.tolist()
+        ok = v[0] == expected_frames
+        if not ok:
+            raise SystemExit(f"all-reduced statistics are wrong: frames {v[0]} != {expected_frames}")
+        return {"frames": v[0], "expected_frames": expected_frames, "ok": ok, "reductions": self.reductions,
+                "robot_goals": v[1], "opponent_goals": v[2], "robot_wins": v[3], "opponent_wins": v[4], "dones": v[5],
+                "goals_per_1000_frames": 1000.0 * (v[1] + v[2]) / max(1, v[0])}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -159,7 +300,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=260)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
-    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--cpu-seconds", type=float, default=4.0)
+    ap.add_argument("--ref-frames", type=int, default=1000, help="frames per worker per step of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
@@ -190,26 +332,15 @@ def main():
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     n_act = 4                                                    # rotate several action tensors
     acts = [torch.randint(0, 4, (K, n), dtype=torch.int8, device=dev, generator=gen) for _ in range(n_act)]
-    stats = [torch.zeros(16, dtype=torch.int64, device=dev) for _ in range(4)]
-    pending = [None] * 4
     stream = torch.cuda.current_stream(dev)
+    red = StatsReducer(env, world, dev)
 
     def one_step(i: int):
         env.step(acts[i % n_act], K=K, out=out)
-        if world > 1:
-            # per-rollout episode/score statistics: 128 B summed over NVLink.  Issued asynchronously (NCCL's stream
-            # waits for the step kernel; the next step's kernel does not wait for the all-reduce), 4 rotating buffers.
-            j = i % 4
-            if pending[j] is not None:
-                pending[j].wait()
-            env.stats_tensor(clear=True, out=stats[j])
-            pending[j] = dist.all_reduce(stats[j], async_op=True)
+        red.after_step()
 
     def barrier():
-        for j in range(4):
-            if pending[j] is not None:
-                pending[j].wait()
-                pending[j] = None
+        red.flush()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
@@ -228,9 +359,11 @@ def main():
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.time()
+    red.restart()
     ev0.record(stream)
     for i in range(args.steps):
         one_step(i)
+    red.finish()                              # the last (partial) rollout's all-reduce is inside the timed region too
     ev1.record(stream)
     barrier()
     t_wall1 = time.time()
@@ -240,6 +373,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
     value = world * n * K * args.steps / (total_ms * 1e-3)
+    stats_check = red.check(world * n * K * args.steps)          # the collective's payload, verified on every rank
 
     clocks = None
     if rank == 0:
@@ -280,12 +414,14 @@ def main():
         e2e = run_e2e(env, dev, n, K, 5, max(10, min(args.steps, 40)), world)
 
     extras = {}
+    if not args.no_extras:
+        # BASELINE configs 4 and 5 at THIS world size (collective inside the timed region, payload checked)
+        extras["ring_append_k8_cfg4"] = run_ring_append(env, dev, n, K, world)
+        extras["ppo_rollout_cfg5"] = run_ppo_rollout(dev, world, rank)
     if world == 1 and not args.no_extras:
         extras["rollout_k1"] = run_rollout_k1(env, dev, n)
         extras["rollout_k1_4m"] = run_rollout_k1(None, dev, 1 << 22)
         extras["philox_sim_k8"] = run_philox_sim(env, dev, n, K)
-        extras["ring_append_k8_cfg4"] = run_ring_append(env, dev, n, K)
-        extras["ppo_rollout_cfg5"] = run_ppo_rollout(dev)
         extras["fp64_validation_cfg2"] = run_fp64(dev)
 
     if rank != 0:
@@ -303,7 +439,11 @@ def main():
                    "sub_updates_per_sec": 3 * value,
                    "l2": "no flush: each step touches %.0f MB of distinct HBM lines (> 126 MB L2)" % (bytes_per_launch / 1e6),
                    "launch": env.launch_info()},
-        "gpu_launches": args.steps * (1 if world == 1 else 2),   # step kernel (+ stats copy kernel when N > 1), per rank
+        # per rank: one step kernel per step + one ah_stats copy kernel per rollout (every 16 steps and at the end)
+        "gpu_launches": args.steps + stats_check["reductions"],
+        "stats_allreduce": dict(stats_check, every_steps=ROLLOUT_STEPS,
+                                what="int64[16] episode/score statistics, summed over ranks (NCCL) once per rollout, "
+                                     "inside the timed region; frames verified against world x envs x K x steps"),
         "clocks": clocks,
     }
     if e2e is not None:
@@ -330,15 +470,7 @@ def main():
             "bytes_per_env_step": bytes_per_launch / (n * K),
         }
     if not args.no_cpu_baseline and world == 1:
-        v, cores, dt, calls, envs = cpu_port_run(0, 1, seconds=args.cpu_seconds)
-        v1, _, dt1, calls1, envs1 = cpu_port_run(0, 1, envs=1 << 15, threads=1, seconds=min(3.0, args.cpu_seconds))
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"{envs} envs x {FRAMES_PER_STEP} frames x {calls} calls ({dt:.1f} s), OpenMP over {cores} threads",
-                                "one_thread_value": v1,
-                                "one_thread_sample": f"{envs1} envs x {FRAMES_PER_STEP} frames x {calls1} calls ({dt1:.1f} s), 1 thread",
-                                "python_reference_note": "the Python reference itself cannot travel to this box; in the development "
-                                                         "container it ran at 1.0-1.8e4 env-steps/s per process and 1.4e5 with an "
-                                                         "8-process pool (BASELINE.md section 2)"}
+        line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
     if extras:
         line["extras"] = extras
     print(json.dumps(line))
@@ -346,19 +478,44 @@ def main():
         dist.destroy_process_group()
 
 
-def _time_loop(dev, fn, warm, reps):
+def _time_loop(dev, fn, warm, reps, world=1, red=None):
+    """Average ms per call of fn(i): CUDA events on the current stream around `reps` calls; at world > 1 bracketed by
+    barriers and reduced with MAX over the ranks.  `red` (a StatsReducer) is stepped after every call and its final
+    all-reduce is inside the timed region."""
     import torch
+    import torch.distributed as dist
+
+    def sync():
+        if red is not None:
+            red.flush()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
     for i in range(warm):
         fn(i)
-    torch.cuda.synchronize(dev)
+        if red is not None:
+            red.after_step()
+    sync()
+    if red is not None:
+        red.restart()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s = torch.cuda.current_stream(dev)
     a.record(s)
     for i in range(reps):
         fn(i)
+        if red is not None:
+            red.after_step()
+    if red is not None:
+        red.finish()
     b.record(s)
-    torch.cuda.synchronize(dev)
-    return a.elapsed_time(b) / reps
+    sync()
+    ms = a.elapsed_time(b)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms / reps
 
 
 def run_rollout_k1(env, dev, n):
@@ -384,21 +541,29 @@ def run_rollout_k1(env, dev, n):
                          if n == (1 << 20) else "state 285 MB > 126 MB L2: algorithmic bytes are DRAM bytes"}}
 
 
-def run_ring_append(env, dev, n, K):
-    """BASELINE config 4's per-GPU work: the headline step PLUS the fused replay-ring append of the Observation tuple
-    (state 8 reals, action, reward, done, new_state 8 reals = 70 B per env-frame; replaces MemoryBuffer.append)."""
+def run_ring_append(env, dev, n, K, world=1):
+    """BASELINE config 4: per GPU 2^20 envs, the headline step PLUS the fused replay-ring append of the Observation tuple
+    (state 8 reals, action, reward, done, new_state 8 reals = 70 B per env-frame; replaces MemoryBuffer.append,
+    lib/buffer.py:24-32), sharded over `world` GPUs with the per-rollout NCCL all-reduce of the statistics inside the
+    timed region and its payload checked.  HBM-bound (write-heavy): the roofline is per GPU."""
     import torch
     from air_hockey_training_environment_b200 import ReplayRing
     ring = ReplayRing(2 * K, n, env.dtype, dev)
     out = env.make_outputs(K, ("reward", "done", "score", "game_over", "obs_next"))
     acts = [torch.randint(0, 4, (K, n), dtype=torch.int8, device=dev) for _ in range(4)]
-    ms = _time_loop(dev, lambda i: env.step(acts[i % 4], K=K, out=out, ring=ring), 10, 100)
+    red = StatsReducer(env, world, dev)
+    reps = 96
+    ms = _time_loop(dev, lambda i: env.step(acts[i % 4], K=K, out=out, ring=ring), 16, reps, world, red)
+    chk = red.check(world * n * K * reps)
     hbm_peak, src, _ = peaks()
     b = n * (2 * STATE_BYTES + 32 + K * (1 + 4 + 1 + 1 + 1) + K * 70)
     ach = b / (ms * 1e-3) / 1e9
-    return {"value": n * K / (ms * 1e-3), "unit": UNIT, "kernel_ms": ms, "ring_capacity_frames": 2 * K,
+    del ring
+    torch.cuda.empty_cache()
+    return {"value": world * n * K / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "n_gpus": world, "envs_total": world * n,
+            "ring_capacity_frames": 2 * K, "stats_allreduce": chk,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                         "traffic": None, "algorithmic_bytes_per_launch": b, "bytes_per_env_step": b / (n * K)}}
+                         "per": "GPU", "traffic": None, "algorithmic_bytes_per_launch": b, "bytes_per_env_step": b / (n * K)}}
 
 
 def run_philox_sim(env, dev, n, K):
@@ -408,35 +573,34 @@ def run_philox_sim(env, dev, n, K):
     return {"value": n * K / (ms * 1e-3), "unit": UNIT, "kernel_ms": ms}
 
 
-def run_ppo_rollout(dev):
-    """BASELINE config 5: 65,536 envs x 128 frames under the reference-shaped actor MLP, three ways:
-    (a) torch module + torch.multinomial + env.step per frame in one CUDA graph, (b) the fused actor+sampling kernel
-    + env.step per frame in one CUDA graph, (c) the whole closed loop in ONE launch (in-kernel actor)."""
+def run_ppo_rollout(dev, world=1, rank=0):
+    """BASELINE config 5: per GPU 65,536 envs x 128 frames under a torch policy (the reference-shaped actor MLP), the
+    rollout tensors written zero-copy on the device; one all-reduce of the statistics per rollout, inside the timed
+    region.  Variants: (a) ANY torch module evaluated by torch + the library's fused categorical sampler + env.step per
+    frame, captured in one CUDA graph; (b) the fused actor+sampling kernel + env.step per frame in one CUDA graph;
+    (c) the whole closed loop in ONE launch (in-kernel actor).  At world > 1 only (a) and (c) are timed."""
     import torch
     from air_hockey_training_environment_b200 import BatchedAirHockey
     from air_hockey_training_environment_b200.rollout import RolloutCollector
     n, T = 65536, 128
-    res = {"envs": n, "frames": T, "unit": UNIT}
-    for name, kw in (("torch_policy_graph", dict(fused_actor=False)), ("fused_actor_graph", dict(single_launch=False)),
-                     ("single_launch", dict(single_launch=True))):
-        env = BatchedAirHockey(n, dtype=torch.float32, device=dev, seed=7)
+    res = {"envs_per_gpu": n, "frames": T, "unit": UNIT, "n_gpus": world}
+    variants = [("torch_policy_graph", dict(fused_actor=False)), ("fused_actor_graph", dict(single_launch=False)),
+                ("single_launch", dict(single_launch=True))]
+    if world > 1:
+        variants = [variants[0], variants[2]]
+    for name, kw in variants:
+        env = BatchedAirHockey(n, dtype=torch.float32, device=dev, seed=7, env_id0=rank * n)
         env.step(None, K=2000, out=env.make_outputs(2000, ()))        # decorrelate the games
         col = RolloutCollector(env, T, seed=7, **kw)
-        for _ in range(3):
-            col.collect()
-        torch.cuda.synchronize(dev)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
+        red = StatsReducer(env, world, dev, every=1)
         reps = 10
-        for _ in range(reps):
-            col.collect()
-        b.record()
-        torch.cuda.synchronize(dev)
-        ms = a.elapsed_time(b) / reps
-        res[name] = {"value": n * T / (ms * 1e-3), "ms_per_rollout": ms}
+        ms = _time_loop(dev, lambda i: col.collect(), 3, reps, world, red)
+        chk = red.check(world * n * T * reps)
+        res[name] = {"value": world * n * T / (ms * 1e-3), "ms_per_rollout": ms, "stats_frames_ok": chk["ok"]}
+        del col, env
     res["value"] = res["single_launch"]["value"]
     res["note"] = ("obs[T+1,n,8], actions, probs[T,n,4], rewards, dones, scores, game_over written zero-copy into the "
-                   "rollout tensors in all three variants")
+                   "rollout tensors in all variants; one stats all-reduce per rollout in the timed region")
     return res
 
 

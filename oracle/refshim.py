@@ -1,11 +1,13 @@
 """TEST INFRASTRUCTURE ONLY -- never imported by the product package.
 
-Import shim for the *live* Python reference (``/root/reference``), which exists only in the
-development container (it is absent on the GPU box).  It is used by
+Import shim for the *live* Python reference: ``/root/reference`` in the development container, and on the
+GPU box (where that path is absent) the byte-compiled, sourceless copy ``oracle/_ref`` that the committed recipe
+``oracle/fetch_ref.py`` builds from those sources.  It is used by
 
   * ``oracle/gen_golden.py``   -- to generate the committed fixtures under ``tests/golden/``;
   * ``tests/test_oracle_vs_reference.py`` -- differential test of the C restatement
-    (``oracle/ah_oracle.c``) against the reference, skipped when the reference is absent.
+    (``oracle/ah_oracle.c``) against the reference, skipped when the reference is absent;
+  * ``oracle/time_reference.py`` / ``bench.py`` -- to time the reference's own CPU loop on the host cores.
 
 The reference cannot be imported as shipped in this image: it pulls in ``redis``
 (environment/airhockey.py:7, lib/utils/connect.py:8), ``keras`` (lib/utils/noisy_dense.py:4-7 via
@@ -25,11 +27,57 @@ from unittest.mock import MagicMock
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("AH_REFERENCE_ROOT", "/root/reference")
+_COMPILED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+_COMPILED_EXT = ".refc"      # a sourceless .pyc by content (oracle/fetch_ref.py)
+
+
+def _has_reference(root: str) -> bool:
+    return any(os.path.isfile(os.path.join(root, "environment", "airhockey" + ext)) for ext in (".py", _COMPILED_EXT))
+
+
+class _CompiledFinder:
+    """Import finder for the byte-compiled reference: ``pkg/mod.refc`` / ``pkg/__init__.refc`` under ``root``."""
+
+    def __init__(self, root: str):
+        self.root = root
+
+    def find_spec(self, fullname, path=None, target=None):
+        import importlib.machinery
+        import importlib.util
+        base = os.path.join(self.root, *fullname.split("."))
+        if os.path.isfile(os.path.join(base, "__init__" + _COMPILED_EXT)):
+            file = os.path.join(base, "__init__" + _COMPILED_EXT)
+            loader = importlib.machinery.SourcelessFileLoader(fullname, file)
+            return importlib.util.spec_from_file_location(fullname, file, loader=loader, submodule_search_locations=[base])
+        if os.path.isfile(base + _COMPILED_EXT):
+            loader = importlib.machinery.SourcelessFileLoader(fullname, base + _COMPILED_EXT)
+            return importlib.util.spec_from_file_location(fullname, base + _COMPILED_EXT, loader=loader)
+        return None
+
+
+def _resolve_root() -> str:
+    """The live sources in the development container; on the GPU box the byte-compiled copy that
+    ``oracle/fetch_ref.py`` built into ``oracle/_ref`` (code objects only; git-ignored, shipped by gpurun)."""
+    env = os.environ.get("AH_REFERENCE_ROOT")
+    if env:
+        return env
+    if _has_reference("/root/reference"):
+        return "/root/reference"
+    return _COMPILED_ROOT
+
+
+REFERENCE_ROOT = _resolve_root()
 
 
 def reference_available() -> bool:
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, "environment", "airhockey.py"))
+    return _has_reference(REFERENCE_ROOT)
+
+
+def reference_kind() -> str:
+    """"source" (live .py tree) or "compiled" (sourceless modules built by oracle/fetch_ref.py)."""
+    return "source" if os.path.isfile(os.path.join(REFERENCE_ROOT, "environment", "airhockey.py")) else "compiled"
 
 
 _installed = False
@@ -78,7 +126,9 @@ def install() -> None:
     if not hasattr(np, "Infinity"):
         np.Infinity = np.inf
 
-    if REFERENCE_ROOT not in sys.path:
+    if reference_kind() == "compiled":
+        sys.meta_path.insert(0, _CompiledFinder(REFERENCE_ROOT))
+    elif REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
     os.environ.setdefault("PROJECT", tempfile.mkdtemp(prefix="ah_ref_project_"))
     logging.disable(logging.CRITICAL)
