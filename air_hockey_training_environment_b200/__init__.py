@@ -5,7 +5,7 @@ Importing this package does not load the CUDA library; constructing an environme
 (ImportError / AhError) when the library or a CUDA device is missing.  There is no CPU fallback.
 """
 from ._capi import AhError, LIB_PATH, STAT_NAMES
-from .env import BatchedAirHockey, ReplayRing, StepOutputs
+from .env import BatchedAirHockey, InterleavedStepper, ReplayRing, StepOutputs
 from .exceptions import InvalidAgentError
 
-__all__ = ["BatchedAirHockey", "ReplayRing", "StepOutputs", "InvalidAgentError", "AhError", "LIB_PATH", "STAT_NAMES"]
+__all__ = ["BatchedAirHockey", "InterleavedStepper", "ReplayRing", "StepOutputs", "InvalidAgentError", "AhError", "LIB_PATH", "STAT_NAMES"]

@@ -14,17 +14,17 @@ AH_OK, AH_EINVAL, AH_ECUDA, AH_ENOMEM, AH_EAGENT, AH_ESTATE = 0, -1, -2, -3, -4,
 AH_F32, AH_F64 = 0, 1
 AH_AGENT_ROBOT, AH_AGENT_HUMAN, AH_AGENT_COMPUTER = 0, 1, 2
 (AH_ACT_NONE, AH_ACT_DISCRETE, AH_ACT_CONTINUOUS, AH_ACT_PHILOX, AH_ACT_DISCRETE_REPEAT, AH_ACT_CONTINUOUS_REPEAT,
- AH_ACT_POLICY) = range(7)
-AH_NSTATS = 16
+ AH_ACT_POLICY, AH_ACT_DISCRETE_PACKED4) = range(8)
+AH_NSTATS = 20
 AH_ACTOR_NWEIGHTS = 114
 STAT_NAMES = ("frames", "robot_goals", "opponent_goals", "robot_wins", "opponent_wins", "dones", "reward_sum",
               "reward_sq_sum", "games", "game_len_sum", "game_len_sq_sum", "game_return_sum", "nonfinite",
-              "reset_table_overflow", "contacts_robot", "contacts_opponent")
+              "reset_table_overflow", "contacts_robot", "contacts_opponent", "done_ambiguous", "_17", "_18", "_19")
 
 # every symbol include/ah_b200.h declares (tests/test_capi_symbols.py checks header <-> library <-> this list)
 SYMBOLS = ("ah_strerror", "ah_abi_version", "ah_last_cuda_error", "ah_create", "ah_destroy", "ah_bind_state",
            "ah_init_state", "ah_reset", "ah_update_state", "ah_get_state", "ah_update_score", "ah_rewards", "ah_step", "ah_pack_host", "ah_actor_sample", "ah_stats",
-           "ah_set_counters", "ah_get_counters", "ah_launch_info", "ah_selftest_nofma")
+           "ah_set_counters", "ah_get_counters", "ah_ring_sample", "ah_launch_info", "ah_selftest_nofma")
 
 
 class AhConfig(C.Structure):
@@ -33,7 +33,7 @@ class AhConfig(C.Structure):
 
 class AhRing(C.Structure):
     _fields_ = [("state", C.c_void_p), ("new_state", C.c_void_p), ("action", C.c_void_p), ("reward", C.c_void_p),
-                ("done", C.c_void_p), ("capacity", C.c_int64)]
+                ("done", C.c_void_p), ("capacity", C.c_int64), ("appended", C.c_void_p)]
 
 
 class AhStepIO(C.Structure):
@@ -42,7 +42,8 @@ class AhStepIO(C.Structure):
                 ("obs_state", C.c_void_p), ("obs_new_state", C.c_void_p), ("reward", C.c_void_p),
                 ("done", C.c_void_p), ("score", C.c_void_p), ("game_over", C.c_void_p),
                 ("obs_next", C.c_void_p), ("obs_next_per_frame", C.c_int32), ("collect_stats", C.c_int32),
-                ("ring", C.POINTER(AhRing)), ("actions_out", C.c_void_p), ("probs_out", C.c_void_p)]
+                ("ring", C.POINTER(AhRing)), ("actions_out", C.c_void_p), ("probs_out", C.c_void_p),
+                ("events", C.c_void_p), ("env_first", C.c_int64), ("env_count", C.c_int64)]
 
 
 class AhError(RuntimeError):
@@ -101,9 +102,11 @@ def lib() -> C.CDLL:
     L.ah_stats.restype = i32
     L.ah_stats.argtypes = [vp, vp, i32, vp]
     L.ah_set_counters.restype = i32
-    L.ah_set_counters.argtypes = [vp, u64, u64, vp]
+    L.ah_set_counters.argtypes = [vp, u64, vp]
     L.ah_get_counters.restype = i32
     L.ah_get_counters.argtypes = [vp, vp, vp]
+    L.ah_ring_sample.restype = i32
+    L.ah_ring_sample.argtypes = [vp, C.POINTER(AhRing), i32, i64, u64, vp, vp, vp, vp, vp, vp, vp]
     L.ah_launch_info.restype = i32
     L.ah_launch_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     L.ah_selftest_nofma.restype = i32

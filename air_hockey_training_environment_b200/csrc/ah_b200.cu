@@ -25,9 +25,9 @@ namespace ah {
 struct DevBlock {
     unsigned long long stats[AH_NSTATS];   // AH_STAT_*
     unsigned long long frame;              // global frame counter (Philox action index)
-    unsigned long long ring_appended;      // Observation tuples appended to the ring so far
+    unsigned long long reserved;
     unsigned int ticket;                   // last-block-done detection
-    unsigned int pad[27];
+    unsigned int pad[19];
 };
 static_assert(sizeof(DevBlock) == 256, "DevBlock is 256 bytes");
 
@@ -112,7 +112,11 @@ __device__ __forceinline__ void env_reset(Env<R>& e, bool total, const ResetSrc&
             dx = (R)v.x; dy = (R)v.y;
         } else { dx = R(0); dy = R(0); overflow += 1; }
     } else {
-        reset_velocity(rs.seed, rs.env_id0 + (uint64_t)i, e.resets, dx, dy);
+        // (opaque copy of the env index: keeps ptxas from hoisting the first Philox round, which only depends on the
+        // env id, out of the frame loop -- four registers and a dozen instructions per env for a rare path)
+        unsigned int iu = (unsigned int)i;
+        asm volatile("" : "+r"(iu));
+        reset_velocity(rs.seed, rs.env_id0 + (uint64_t)iu, e.resets, dx, dy);
     }
     e.resets += 1;
     e.px = K<R>::mid_x; e.py = K<R>::mid_y; e.pdx = dx; e.pdy = dy;   // puck to the centre, fresh velocity
@@ -133,6 +137,7 @@ struct StepArgs {
     int collect_stats;
     // ring
     R* ring_state; R* ring_new_state; void* ring_action; R* ring_reward; uint8_t* ring_done; int64_t ring_capacity;
+    unsigned long long* ring_appended;     // the ring's own device counter (ah_ring.appended)
     int dot_fma, friction;
     DevBlock* blk;
     int8_t* actions_out; R* probs_out;     // GENERIC mode: the actions applied / the in-kernel actor's distribution
@@ -153,6 +158,67 @@ struct BlockStats {
 __device__ __forceinline__ void stat_add(BlockStats& bs, int which, int x) {
     const unsigned addr = (unsigned)__cvta_generic_to_shared(&bs.v[which]);
     asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(addr), "r"(x) : "memory");
+}
+
+// ---- epilogue WITHOUT block barriers: warps finish at different times (contact / goal branches), so each warp
+// folds its per-frame sums into the block's shared counters (REDUX + one shared red per value) and leaves; the
+// LAST warp of the block to arrive flushes the block's statistics (<= 16 global atomics) and takes the launch
+// ticket; the last block of the launch advances the device-side frame / ring counters (graph-capturable: no host
+// value is baked into the launch).
+// ORDERED = the launch's own blocks read the frame / ring counters at their start (Philox actions, in-kernel policy,
+// ring append): those may only advance once EVERY block is done (fence + ticket).  Kernels that never read them
+// (the packed mode) let block 0 advance the frame counter: launches on a stream are serialised, so nobody races it.
+template <bool ORDERED = true>
+__device__ __forceinline__ void finish_stats(BlockStats& bs, DevBlock* blk, int collect_stats, int frames, int reward_sum,
+                                             int reward_sq, int dones, int contacts_r, int contacts_o, int overflow, int bad,
+                                             int ambiguous, int K, unsigned long long* ring_appended) {
+    const int fs = __reduce_add_sync(0xffffffffu, frames);
+    const int rs = __reduce_add_sync(0xffffffffu, reward_sum);
+    const int rq = __reduce_add_sync(0xffffffffu, reward_sq);
+    const int dd = __reduce_add_sync(0xffffffffu, dones);
+    const int cr = __reduce_add_sync(0xffffffffu, contacts_r);
+    const int co = __reduce_add_sync(0xffffffffu, contacts_o);
+    const int rare = __reduce_or_sync(0xffffffffu, overflow | bad | ambiguous);
+    int ov = 0, nf = 0, am = 0;
+    if (rare) {
+        ov = __reduce_add_sync(0xffffffffu, overflow); nf = __reduce_add_sync(0xffffffffu, bad);
+        am = __reduce_add_sync(0xffffffffu, ambiguous);
+    }
+    const int lane = threadIdx.x & 31;
+    int arrived = 0;
+    if (lane == 0) {
+        stat_add(bs, AH_STAT_DONES, dd);
+        stat_add(bs, AH_STAT_FRAMES, fs);
+        stat_add(bs, AH_STAT_REWARD_SUM, rs);
+        stat_add(bs, AH_STAT_REWARD_SQ_SUM, rq);
+        if (cr) stat_add(bs, AH_STAT_CONTACTS_ROBOT, cr);
+        if (co) stat_add(bs, AH_STAT_CONTACTS_OPPONENT, co);
+        if (ov) stat_add(bs, AH_STAT_RESET_TABLE_OVERFLOW, ov);
+        if (nf) stat_add(bs, AH_STAT_NONFINITE, nf);
+        if (am) stat_add(bs, AH_STAT_DONE_AMBIGUOUS, am);
+        __threadfence_block();
+        arrived = atomicAdd(&bs.warps_done, 1);
+    }
+    arrived = __shfl_sync(0xffffffffu, arrived, 0);
+    if (arrived != (int)(blockDim.x >> 5) - 1) return;
+    __threadfence_block();
+    if (collect_stats && lane < AH_NSTATS) {                    // lane q flushes statistic q
+        const long long sv = lane == AH_STAT_GAME_LEN_SQ_SUM ? (long long)*(volatile unsigned long long*)&bs.len_sq
+                                                             : (long long)*(volatile int*)&bs.v[lane];
+        if (sv != 0) atomicAdd(&blk->stats[lane], (unsigned long long)sv);
+    }
+    if (lane != 0) return;
+    if (!ORDERED) {
+        if (blockIdx.x == 0) blk->frame = *(volatile unsigned long long*)&blk->frame + (unsigned long long)K;
+        return;
+    }
+    __threadfence();
+    if (atomicAdd(&blk->ticket, 1u) == gridDim.x - 1) {
+        blk->frame = *(volatile unsigned long long*)&blk->frame + (unsigned long long)K;
+        if (ring_appended) *ring_appended = *(volatile unsigned long long*)ring_appended + (unsigned long long)K;
+        blk->ticket = 0;
+        __threadfence();
+    }
 }
 
 // ---- the reference's discrete PPO actor (lib/agents/ppo/model.py:56-74; BatchNorm folded into layer 2) and
@@ -249,14 +315,14 @@ step_kernel(const StepArgs<R> a) {
     // actions, ring append): a dependent L2 round-trip at the head of every thread is what the others avoid
     unsigned long long frame0 = 0ull, ring0 = 0ull;
     if (ACT == 3 || ACT == 4) frame0 = a.blk->frame;
-    if (MODE == MODE_GENERIC) ring0 = a.blk->ring_appended;
+    if (MODE == MODE_GENERIC && a.ring_capacity > 0) ring0 = *a.ring_appended;
     const bool repeat = (a.action_kind == AH_ACT_DISCRETE_REPEAT) || (a.action_kind == AH_ACT_CONTINUOUS_REPEAT);
     const bool dot_fma = a.dot_fma != 0;
     const bool friction = (MODE == MODE_GENERIC) && (a.friction != 0);
     const bool want_obs = (MODE == MODE_GENERIC) && (a.obs_state || a.obs_new_state || a.ring_capacity > 0);
     const int K = a.K;
     const size_t act_step = repeat ? 0 : (size_t)n;           // elements between frame k and k+1 of the action tensor
-    int reward_sum = 0, reward_sq = 0, frames = 0, dones = 0, contacts_r = 0, contacts_o = 0, bad = 0;
+    int reward_sum = 0, reward_sq = 0, frames = 0, dones = 0, contacts_r = 0, contacts_o = 0, bad = 0, amb = 0;
     unsigned overflow = 0;
     const int64_t ring_slot0 = (MODE == MODE_GENERIC && a.ring_capacity > 0) ? (int64_t)(ring0 % (unsigned long long)a.ring_capacity) : 0;
 
@@ -355,7 +421,7 @@ step_kernel(const StepArgs<R> a) {
             }
             // ---- Rewards                                           agent.py:70-71
             int rw, sc; bool dn;
-            rewards_call<R>(e, dot_fma, rw, sc, dn);
+            rewards_call<R>(e, dot_fma, rw, sc, dn, amb);
             e.game_return += rw;
             reward_sq += rw * rw;
             // ---- env.update_score(score)                           game.py:142 -> airhockey.py:149-169
@@ -416,50 +482,13 @@ step_kernel(const StepArgs<R> a) {
         if (PF) { raw = raw_next; ia_pf = ia_pf_next; }
     }
 
-    // ---- epilogue WITHOUT block barriers: warps finish at different times (contact / goal branches), so each warp
-    // folds its per-frame sums into the block's shared counters (REDUX + one shared red per value) and leaves; the
-    // LAST warp of the block to arrive flushes the block's statistics (<= 16 global atomics) and takes the launch
-    // ticket; the last block of the launch advances the device-side frame / ring counters (graph-capturable: no host
-    // value is baked into the launch).
-    const int fs = __reduce_add_sync(0xffffffffu, frames);
-    const int rs = __reduce_add_sync(0xffffffffu, reward_sum);
-    const int rq = __reduce_add_sync(0xffffffffu, reward_sq);
-    const int dd = __reduce_add_sync(0xffffffffu, dones);
-    const int cr = __reduce_add_sync(0xffffffffu, contacts_r);
-    const int co = __reduce_add_sync(0xffffffffu, contacts_o);
-    const int ov = __reduce_add_sync(0xffffffffu, (int)overflow);
-    const int nf = __reduce_add_sync(0xffffffffu, bad);
-    const int lane = threadIdx.x & 31;
-    int arrived = 0;
-    if (lane == 0) {
-        stat_add(bs, AH_STAT_DONES, dd);
-        stat_add(bs, AH_STAT_FRAMES, fs);
-        stat_add(bs, AH_STAT_REWARD_SUM, rs);
-        stat_add(bs, AH_STAT_REWARD_SQ_SUM, rq);
-        if (cr) stat_add(bs, AH_STAT_CONTACTS_ROBOT, cr);
-        if (co) stat_add(bs, AH_STAT_CONTACTS_OPPONENT, co);
-        if (ov) stat_add(bs, AH_STAT_RESET_TABLE_OVERFLOW, ov);
-        if (nf) stat_add(bs, AH_STAT_NONFINITE, nf);
-        __threadfence_block();
-        arrived = atomicAdd(&bs.warps_done, 1);
-    }
-    arrived = __shfl_sync(0xffffffffu, arrived, 0);
-    if (arrived != (int)(blockDim.x >> 5) - 1) return;
-    __threadfence_block();
-    if (a.collect_stats && lane < AH_NSTATS) {                  // lane q flushes statistic q
-        const long long sv = lane == AH_STAT_GAME_LEN_SQ_SUM ? (long long)*(volatile unsigned long long*)&bs.len_sq
-                                                             : (long long)*(volatile int*)&bs.v[lane];
-        if (sv != 0) atomicAdd(&a.blk->stats[lane], (unsigned long long)sv);
-    }
-    if (lane != 0) return;
-    __threadfence();
-    if (atomicAdd(&a.blk->ticket, 1u) == gridDim.x - 1) {
-        a.blk->frame = *(volatile unsigned long long*)&a.blk->frame + (unsigned long long)K;
-        if (a.ring_capacity > 0) a.blk->ring_appended = *(volatile unsigned long long*)&a.blk->ring_appended + (unsigned long long)K;
-        a.blk->ticket = 0;
-        __threadfence();
-    }
+    finish_stats(bs, a.blk, a.collect_stats, frames, reward_sum, reward_sq, dones, contacts_r, contacts_o, (int)overflow, bad, amb, K,
+                 a.ring_capacity > 0 ? a.ring_appended : nullptr);
 }
+
+}  // namespace ah
+#include "ah_step_packed.cuh"
+namespace ah {
 
 // ------------------------------------------------------------------------------------------------ small kernels
 template <typename R>
@@ -548,8 +577,8 @@ __global__ void rewards_kernel(StatePtrs<R> st, int64_t n, int dot_fma, R* rewar
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Env<R> e = load_env<R>(st, i);
-    int rw, sc; bool dn;
-    rewards_call<R>(e, dot_fma != 0, rw, sc, dn);
+    int rw, sc, amb = 0; bool dn;
+    rewards_call<R>(e, dot_fma != 0, rw, sc, dn, amb);
     st.prev_dist[i] = e.prev_dist;
     if (reward) reward[i] = (R)rw;
     if (score) score[i] = (int8_t)sc;
@@ -589,10 +618,12 @@ __global__ void pack_host_kernel(int64_t n, int K, const R* __restrict__ reward,
                                  float4* __restrict__ vel) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    for (int k = 0; k < K; ++k) {
-        const int64_t row = (int64_t)k * n + i;
-        const int rw = (int)reward[row] + 4;
-        events[row] = (uint8_t)((rw & 15) | ((done[row] ? 1 : 0) << 4));
+    if (events) {
+        for (int k = 0; k < K; ++k) {
+            const int64_t row = (int64_t)k * n + i;
+            const int rw = (int)reward[row] + 4;
+            events[row] = (uint8_t)((rw & 15) | ((done[row] ? 1 : 0) << 4));
+        }
     }
     const R* o = obs + 8 * i;
     pos[i] = make_short4((short)o[0], (short)o[1], (short)o[2], (short)o[3]);
@@ -607,11 +638,70 @@ __global__ void stats_copy_kernel(DevBlock* blk, int64_t* out, int clear) {
     }
 }
 
-__global__ void counters_set_kernel(DevBlock* blk, unsigned long long frame, unsigned long long ring) {
-    blk->frame = frame; blk->ring_appended = ring;
+__global__ void counters_set_kernel(DevBlock* blk, unsigned long long frame) { blk->frame = frame; }
+__global__ void counters_get_kernel(const DevBlock* blk, unsigned long long* out1) { out1[0] = blk->frame; }
+
+// ---- MemoryBuffer.sample (lib/buffer.py:47-50) on the device: a keyed bijection of [0, population) instead of a
+// materialised permutation.  6-round balanced Feistel network over 2^bits >= population (bits even), cycle-walked.
+struct RingKeys { uint32_t k[8]; };
+
+__host__ __device__ __forceinline__ uint32_t ring_round(uint32_t v, uint32_t key) {
+    v = (v + key) * 0x9E3779B1u;
+    v ^= v >> 15;
+    v *= 0x85EBCA77u;
+    v ^= v >> 13;
+    v *= 0xC2B2AE3Du;
+    v ^= v >> 16;
+    return v;
 }
-__global__ void counters_get_kernel(const DevBlock* blk, unsigned long long* out2) {
-    out2[0] = blk->frame; out2[1] = blk->ring_appended;
+
+__device__ __forceinline__ uint64_t ring_permute(uint64_t x, int half, const RingKeys& rk) {
+    const uint32_t mask = (half >= 32) ? 0xffffffffu : ((1u << half) - 1u);
+    uint32_t L = (uint32_t)(x >> half) & mask, Rr = (uint32_t)x & mask;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+        const uint32_t t = L ^ (ring_round(Rr, rk.k[r]) & mask);
+        L = Rr; Rr = t;
+    }
+    return ((uint64_t)L << half) | Rr;
+}
+
+template <typename R>
+__global__ void ring_sample_kernel(int64_t n, int64_t capacity, const unsigned long long* appended_p, int continuous,
+                                   int64_t batch, uint64_t seed, uint64_t draw,
+                                   const R* __restrict__ r_state, const R* __restrict__ r_new_state, const void* __restrict__ r_action,
+                                   const R* __restrict__ r_reward, const uint8_t* __restrict__ r_done,
+                                   R* state, void* action, R* reward, uint8_t* done, R* new_state, int64_t* index) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= batch) return;
+    using V = typename Vec4T<R>::type;
+    using V2 = typename std::conditional<sizeof(R) == 4, float2, double2>::type;
+    const unsigned long long appended = *appended_p;
+    const uint64_t held = appended < (unsigned long long)capacity ? appended : (unsigned long long)capacity;
+    const uint64_t population = held * (uint64_t)n;
+    if (population == 0) return;
+    int bits = 2;
+    while (bits < 64 && (1ull << bits) < population) bits += 2;
+    RingKeys rk;
+    const Philox4 a = philox4x32_10((uint32_t)draw, (uint32_t)(draw >> 32), 0x52494E47u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const Philox4 b = philox4x32_10((uint32_t)draw, (uint32_t)(draw >> 32), 0x52494E47u, 1u, (uint32_t)seed, (uint32_t)(seed >> 32));
+    rk.k[0] = a.x; rk.k[1] = a.y; rk.k[2] = a.z; rk.k[3] = a.w; rk.k[4] = b.x; rk.k[5] = b.y; rk.k[6] = b.z; rk.k[7] = b.w;
+    uint64_t f = (uint64_t)s % population;                // batch <= population is the caller's contract
+    do { f = ring_permute(f, bits >> 1, rk); } while (f >= population);
+    const uint64_t age = f / (uint64_t)n, env = f % (uint64_t)n;
+    const uint64_t slot = (appended - 1ull - age) % (unsigned long long)capacity;     // age 0 = the newest tuple
+    const int64_t row = (int64_t)(slot * (uint64_t)n + env);
+    const V* src0 = reinterpret_cast<const V*>(r_state) + 2 * row;
+    const V* src1 = reinterpret_cast<const V*>(r_new_state) + 2 * row;
+    V* dst0 = reinterpret_cast<V*>(state) + 2 * s;
+    V* dst1 = reinterpret_cast<V*>(new_state) + 2 * s;
+    dst0[0] = src0[0]; dst0[1] = src0[1];
+    dst1[0] = src1[0]; dst1[1] = src1[1];
+    if (continuous) reinterpret_cast<V2*>(action)[s] = reinterpret_cast<const V2*>(r_action)[row];
+    else reinterpret_cast<int8_t*>(action)[s] = reinterpret_cast<const int8_t*>(r_action)[row];
+    reward[s] = r_reward[row];
+    done[s] = r_done[row];
+    if (index) index[s] = (int64_t)f;
 }
 
 // a*b+c must NOT be contracted in this translation unit (FP64 validation build): discriminating probe
@@ -676,6 +766,7 @@ int launch_step(ah_env* env, const ah_step_io* io, int K, cudaStream_t s) {
     if (io->ring) {
         a.ring_state = (R*)io->ring->state; a.ring_new_state = (R*)io->ring->new_state; a.ring_action = io->ring->action;
         a.ring_reward = (R*)io->ring->reward; a.ring_done = io->ring->done; a.ring_capacity = io->ring->capacity;
+        a.ring_appended = reinterpret_cast<unsigned long long*>(io->ring->appended);
     }
     a.dot_fma = env->cfg.dot_fma; a.friction = env->cfg.friction; a.blk = env->blk;
     a.actions_out = io->actions_out; a.probs_out = (R*)io->probs_out;
@@ -686,6 +777,22 @@ int launch_step(ah_env* env, const ah_step_io* io, int K, cudaStream_t s) {
     while (threads > 64 && (env->n + threads - 1) / threads < 4 * (int64_t)env->sms) threads >>= 1;
     int64_t want = (env->n + threads - 1) / threads;
     const unsigned grid = (unsigned)(want < max_blocks ? want : max_blocks);
+    if (io->events) {                                        // PACKED rollout mode (ah_step_packed.cuh)
+        ah::PackedArgs<R> p;
+        memset(&p, 0, sizeof p);
+        p.st = a.st; p.n = env->n; p.K = K;
+        p.actions = reinterpret_cast<const uint32_t*>(io->actions); p.events = reinterpret_cast<uint32_t*>(io->events);
+        p.obs_next = (R*)io->obs_next; p.rs = a.rs; p.collect_stats = io->collect_stats; p.dot_fma = env->cfg.dot_fma; p.blk = env->blk;
+        const int64_t count = io->env_count > 0 ? io->env_count : env->n;
+        p.i0 = (uint32_t)io->env_first; p.i_end = (uint32_t)(io->env_first + count);
+        int pth = ah::kPackedThreads;
+        while (pth > 64 && (count + pth - 1) / pth < 4 * (int64_t)env->sms) pth >>= 1;
+        const int64_t pwant = (count + pth - 1) / pth;
+        const unsigned pgrid = (unsigned)(pwant < max_blocks ? pwant : max_blocks);
+        ah::step_packed_kernel<R><<<pgrid, pth, 0, s>>>(p);
+        const cudaError_t pe = cudaGetLastError();
+        return pe == cudaSuccess ? AH_OK : cuda_fail(env, pe);
+    }
     // pick the specialised variant the given pointers allow
     const bool per_frame_any = io->reward || io->done || io->score || io->game_over;
     const bool per_frame_all = io->reward && io->done && io->score && io->game_over;
@@ -700,7 +807,7 @@ int launch_step(ah_env* env, const ah_step_io* io, int K, cudaStream_t s) {
         case AH_ACT_CONTINUOUS: case AH_ACT_CONTINUOUS_REPEAT: act = 2; break;
         case AH_ACT_PHILOX: act = 3; break;
         case AH_ACT_POLICY: act = 4; break;
-        default: return AH_EINVAL;
+        default: return AH_EINVAL;                            // AH_ACT_DISCRETE_PACKED4 is only valid with io->events
     }
 #define AH_LAUNCH(ACT_, MODE_) ah::step_kernel<R, ACT_, MODE_><<<grid, threads, 0, s>>>(a)
 #define AH_LAUNCH_MODE(ACT_) do { if (mode == ah::MODE_LEAN) AH_LAUNCH(ACT_, ah::MODE_LEAN); \
@@ -873,8 +980,16 @@ int ah_step(ah_env* env, const ah_step_io* io, int K, void* stream) {
     AH_CHECK_BOUND(env);
     if (!io || K < 1 || K > 4096) return AH_EINVAL;
     const int kind = io->action_kind;
-    if (kind != AH_ACT_DISCRETE && kind != AH_ACT_CONTINUOUS && kind != AH_ACT_PHILOX &&
-        kind != AH_ACT_DISCRETE_REPEAT && kind != AH_ACT_CONTINUOUS_REPEAT && kind != AH_ACT_POLICY) return AH_EINVAL;
+    if (kind != AH_ACT_DISCRETE && kind != AH_ACT_CONTINUOUS && kind != AH_ACT_PHILOX && kind != AH_ACT_DISCRETE_REPEAT &&
+        kind != AH_ACT_CONTINUOUS_REPEAT && kind != AH_ACT_POLICY && kind != AH_ACT_DISCRETE_PACKED4) return AH_EINVAL;
+    if ((kind == AH_ACT_DISCRETE_PACKED4) != (io->events != nullptr)) return AH_EINVAL;   // the packed mode is all-or-nothing
+    if (io->env_first < 0 || io->env_count < 0 || io->env_first + io->env_count > env->n) return AH_EINVAL;
+    if ((io->env_first != 0 || io->env_count != 0) && !io->events) return AH_EINVAL;     // sub-ranges: packed mode only
+    if (io->events) {
+        if ((reinterpret_cast<uintptr_t>(io->events) & 3u) || (reinterpret_cast<uintptr_t>(io->actions) & 3u)) return AH_EINVAL;
+        if (io->reward || io->done || io->score || io->game_over || io->obs_state || io->obs_new_state || io->ring ||
+            io->actions_out || io->probs_out || (io->obs_next && io->obs_next_per_frame) || env->cfg.friction) return AH_EINVAL;
+    }
     if (!aligned16(io->probs_out) || (io->probs_out && kind != AH_ACT_POLICY)) return AH_EINVAL;
     if (kind != AH_ACT_PHILOX && !io->actions) return AH_EINVAL;
     if ((kind == AH_ACT_CONTINUOUS || kind == AH_ACT_CONTINUOUS_REPEAT) &&
@@ -883,7 +998,8 @@ int ah_step(ah_env* env, const ah_step_io* io, int K, void* stream) {
     if (!aligned16(io->obs_state) || !aligned16(io->obs_new_state) || !aligned16(io->obs_next)) return AH_EINVAL;
     if (io->ring) {
         const ah_ring* r = io->ring;
-        if (r->capacity <= 0 || !r->state || !r->new_state || !r->action || !r->reward || !r->done) return AH_EINVAL;
+        if (r->capacity <= 0 || !r->state || !r->new_state || !r->action || !r->reward || !r->done || !r->appended) return AH_EINVAL;
+        if (reinterpret_cast<uintptr_t>(r->appended) & 7u) return AH_EINVAL;
         if (!aligned16(r->state) || !aligned16(r->new_state)) return AH_EINVAL;
     }
     DeviceGuard g(env->device);
@@ -904,7 +1020,8 @@ int ah_actor_sample(ah_env* env, const float* d_weights, const void* d_obs, void
 
 int ah_pack_host(ah_env* env, int K, const void* d_reward, const uint8_t* d_done, const void* d_obs_next,
                  uint8_t* d_events, int16_t* d_obs_pos, float* d_obs_vel, void* stream) {
-    if (!env || K < 1 || !d_reward || !d_done || !d_obs_next || !d_events || !d_obs_pos || !d_obs_vel) return AH_EINVAL;
+    if (!env || K < 1 || !d_obs_next || !d_obs_pos || !d_obs_vel) return AH_EINVAL;
+    if ((d_events != nullptr) != (d_reward != nullptr) || (d_events != nullptr) != (d_done != nullptr)) return AH_EINVAL;
     if (!aligned16(d_obs_vel) || (reinterpret_cast<uintptr_t>(d_obs_pos) & 7u)) return AH_EINVAL;
     DeviceGuard g(env->device);
     cudaStream_t s = (cudaStream_t)stream;
@@ -920,17 +1037,35 @@ int ah_stats(ah_env* env, int64_t* d_out, int clear, void* stream) {
     AH_LAUNCH_RC(env);
 }
 
-int ah_set_counters(ah_env* env, uint64_t frame, uint64_t ring_appended, void* stream) {
+int ah_set_counters(ah_env* env, uint64_t frame, void* stream) {
     if (!env) return AH_EINVAL;
     DeviceGuard g(env->device);
-    ah::counters_set_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(env->blk, frame, ring_appended);
+    ah::counters_set_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(env->blk, frame);
     AH_LAUNCH_RC(env);
 }
 
-int ah_get_counters(ah_env* env, uint64_t* d_out2, void* stream) {
-    if (!env || !d_out2) return AH_EINVAL;
+int ah_get_counters(ah_env* env, uint64_t* d_out1, void* stream) {
+    if (!env || !d_out1) return AH_EINVAL;
     DeviceGuard g(env->device);
-    ah::counters_get_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(env->blk, reinterpret_cast<unsigned long long*>(d_out2));
+    ah::counters_get_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(env->blk, reinterpret_cast<unsigned long long*>(d_out1));
+    AH_LAUNCH_RC(env);
+}
+
+int ah_ring_sample(ah_env* env, const ah_ring* ring, int continuous, int64_t batch, uint64_t draw, void* d_state,
+                   void* d_action, void* d_reward, uint8_t* d_done, void* d_new_state, int64_t* d_index, void* stream) {
+    if (!env || !ring || batch <= 0 || !d_state || !d_action || !d_reward || !d_done || !d_new_state) return AH_EINVAL;
+    if (ring->capacity <= 0 || !ring->state || !ring->new_state || !ring->action || !ring->reward || !ring->done || !ring->appended) return AH_EINVAL;
+    if (!aligned16(d_state) || !aligned16(d_new_state) || !aligned16(ring->state) || !aligned16(ring->new_state)) return AH_EINVAL;
+    DeviceGuard g(env->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)((batch + 255) / 256);
+    const unsigned long long* ap = reinterpret_cast<const unsigned long long*>(ring->appended);
+    AH_DISPATCH(env, (ah::ring_sample_kernel<float><<<grid, 256, 0, s>>>(env->n, ring->capacity, ap, continuous, batch, env->seed, draw,
+                          (const float*)ring->state, (const float*)ring->new_state, ring->action, (const float*)ring->reward, ring->done,
+                          (float*)d_state, d_action, (float*)d_reward, d_done, (float*)d_new_state, d_index)),
+                (ah::ring_sample_kernel<double><<<grid, 256, 0, s>>>(env->n, ring->capacity, ap, continuous, batch, env->seed, draw,
+                          (const double*)ring->state, (const double*)ring->new_state, ring->action, (const double*)ring->reward, ring->done,
+                          (double*)d_state, d_action, (double*)d_reward, d_done, (double*)d_new_state, d_index)));
     AH_LAUNCH_RC(env);
 }
 

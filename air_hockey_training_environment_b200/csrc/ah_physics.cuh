@@ -335,9 +335,16 @@ __device__ __forceinline__ Obs<R> get_state(const Env<R>& e, bool robot) {
     return o;
 }
 
+// pow(x, 2) vs x*x (see rewards_call): inside the band AND at least one square inexact (its rounding error != 0)
+__device__ __forceinline__ bool done_is_ambiguous(double ex, double ey, double ssq) {
+    if (!(fabs(ssq - 1225.0) < 1e-9)) return false;
+    return __fma_rn(ex, ex, -(ex * ex)) != 0.0 || __fma_rn(ey, ey, -(ey * ey)) != 0.0;
+}
+__device__ __forceinline__ bool done_is_ambiguous(float, float, float) { return false; }
+
 // ---- Rewards.__call__ for agent "robot"  lib/rewards.py:118-142 ----
 template <typename R>
-__device__ __forceinline__ void rewards_call(Env<R>& e, bool dot_fma, int& reward, int& score, bool& done) {
+__device__ __forceinline__ void rewards_call(Env<R>& e, bool dot_fma, int& reward, int& score, bool& done, int& ambiguous) {
     using M = Math<R>;
     // compute_score_reward  rewards.py:64-81 with Goal.__contains__  goal.py:13-18; its reward and its own
     // `done` are discarded by the caller (rewards.py:122).  The left-goal test comes second and wins ties.
@@ -351,8 +358,13 @@ __device__ __forceinline__ void rewards_call(Env<R>& e, bool dot_fma, int& rewar
     const R dsq = M::dot2(ex, ey, ex, ey, dot_fma);
     if (M::exact) {
         // sqrt((px-mx)**2 + (py-my)**2) < 35 : plain (non-fused) sum of squares; `** 2` is libm pow() in the
-        // reference, evaluated here as x*x (they differ only within an ulp of the threshold)
-        done = M::sqrt_(ex * ex + ey * ey) < K<R>::radius;
+        // reference, evaluated here as x*x.  pow(x, 2) is within an ulp of x*x (and equal to it when the square is exactly
+        // representable, e.g. for the integer-valued states before the first contact), so the two can only decide
+        // differently when the sum is within a few ulps (5e-13) of 1225 and a square is inexact: such frames are COUNTED
+        // (AH_STAT_DONE_AMBIGUOUS, band 1e-9); a run whose count is 0 has `done` provably equal to the reference's.
+        const R ssq = ex * ex + ey * ey;
+        done = M::sqrt_(ssq) < K<R>::radius;
+        ambiguous += done_is_ambiguous(ex, ey, ssq) ? 1 : 0;
     } else {
         done = dsq < K<R>::radius_sq;
     }

@@ -1,0 +1,266 @@
+// The PACKED step kernel: the headline rollout mode (BASELINE config 3) with byte-packed per-frame I/O.
+//
+// Same frame as ah::step_kernel (game.py:133-177 + lib/agents/agent.py:57-78), same device functions, same
+// results -- what changes is how a frame's inputs and outputs cross the register file:
+//
+//   actions  u8 [ceil(K/4)][n][4]   "quad-major": byte j of word (q, i) is env i's action of frame 4q + j.  One
+//                                   coalesced LDG.32 per env per 4 frames (a warp reads 128 contiguous bytes)
+//                                   instead of a byte load + 64-bit pointer bump + prefetch logic per frame.
+//   events   u8 [ceil(K/4)][n][4]   one byte per env-frame carrying EVERYTHING the reference's frame returns:
+//                                       bits 0-2  (reward + 4) / 2     reward in {-4,-2,0,2,4,6}  lib/rewards.py:118-142
+//                                       bit  3    done                 "mallet overlaps puck"     rewards.py:86-89,124
+//                                       bits 4-5  score + 1            -1 / 0 / +1                rewards.py:64-81
+//                                       bits 6-7  game_over            0 / 1 robot / 2 opponent   game.py:101-109,169-177
+//                                   assembled in a register (one PRMT per frame) and written as one STG.32 per 4
+//                                   frames, instead of four stores + four pointer bumps + conversions per frame.
+//   The launch's statistics (reward sum, reward^2 sum, dones) are recovered from the packed words with two IDP.4A
+//   and a POPC per 4 frames instead of three accumulations per frame.
+//
+// Other common-path savings over step_kernel (all result-preserving; FP64 stays bit-exact):
+//   * the action -> nudge map is a 256-entry shared table indexed by the raw action byte (no clamp), its shared
+//     address hoisted out of the loop;
+//   * "the puck's velocity may be out of limits" is carried as the contact-test threshold (1225, or +inf when
+//     dirty) instead of a flag tested beside it;
+//   * FP32 only: the goal / wall predicates of Rewards are single compares (valid because the puck has just been
+//     advanced by Puck.update, so 5 <= x <= 895), and the computer sub-update's speed clamp is min(v, 10) unless
+//     the rare branch ran (the velocity was within limits before computerAI's +2 nudge).
+#pragma once
+
+namespace ah {
+
+template <typename R>
+struct PackedArgs {
+    StatePtrs<R> st;
+    int64_t n;
+    int K;
+    const uint32_t* actions;      // u8 [ceil(K/4)][n][4]
+    uint32_t* events;             // u8 [ceil(K/4)][n][4]
+    R* obs_next;                  // [n][8], nullable
+    ResetSrc rs;
+    int collect_stats, dot_fma;
+    DevBlock* blk;
+    uint32_t i0, i_end;           // envs [i0, i_end) are stepped by this launch (row strides stay n)
+};
+
+// ---- Rewards.__call__ as predicates (lib/rewards.py:118-142); see rewards_call for the line-by-line citations.
+// IN_FRAME: the puck was just advanced by Puck.update (5 <= px <= 895), which lets the FP32 build test the goal and
+// wall zones with one compare each: |900 - px| < 30 <=> px > 870, |0 - px| < 30 <=> px < 30, |px - 13| < 15 <=> px < 28,
+// |px - 882| < 15 <=> px > 867 (the subtractions are exact next to their thresholds, so the equivalences are exact).
+template <typename R>
+__device__ __forceinline__ void rewards_bits(Env<R>& e, bool dot_fma, int& score, bool& done, bool& wl, bool& wr, bool& closer,
+                                             int& ambiguous) {
+    using M = Math<R>;
+    const bool in_y = M::abs_(K<R>::mid_y - e.py) < R(95);
+    bool right, left;
+    if (M::exact) {
+        right = (M::abs_(K<R>::table_w - e.px) < R(30)) && in_y;
+        left = (M::abs_(R(0) - e.px) < R(30)) && in_y;
+        wl = M::abs_(e.px - K<R>::left_wall) < K<R>::puck_r;
+        wr = M::abs_(e.px - K<R>::right_wall) < K<R>::puck_r;
+    } else {
+        right = (e.px > R(870)) && in_y;
+        left = (e.px < R(30)) && in_y;
+        wl = e.px < R(28);
+        wr = e.px > R(867);
+    }
+    score = left ? -1 : (right ? 1 : 0);
+    R ex, ey;
+    M::sub2(ex, ey, e.px, e.py, e.rx, e.ry);
+    const R dsq = M::dot2(ex, ey, ex, ey, dot_fma);
+    if (M::exact) {                               // see rewards_call: pow(x, 2) vs x*x
+        const R ssq = ex * ex + ey * ey;
+        done = M::sqrt_(ssq) < K<R>::radius;
+        ambiguous += done_is_ambiguous(ex, ey, ssq) ? 1 : 0;
+    } else {
+        done = dsq < K<R>::radius_sq;
+    }
+    const R nd = M::sqrt_(dsq);
+    closer = nd < e.prev_dist;
+    e.prev_dist = nd;
+}
+
+// the common tail of a sub-update with the speed-limit bookkeeping carried in `thr` (see file header)
+template <typename R, bool COMPUTER>
+__device__ __forceinline__ void physics_tail_thr(Env<R>& e, bool dot_fma, R& thr, int& contacts) {
+    R rdx_, rdy_, odx_, ody_;
+    const R dr = contact_dist_sq<R>(e.px, e.py, e.rx, e.ry, dot_fma, rdx_, rdy_);
+    R dq = contact_dist_sq<R>(e.px, e.py, e.ox, e.oy, dot_fma, odx_, ody_);
+    if (!(dr > thr) || !(dq > thr)) {                                            // :210, or velocity possibly out of limits
+        R dr_in = dr;
+        opaque(dr_in); opaque(dq);
+        if (!(dr_in > K<R>::radius_sq)) {
+            contacts += 1;
+            contact_response<R>(e.px, e.py, e.pdx, e.pdy, e.rx, e.ry, e.rdx, e.rdy, rdx_, rdy_, dr_in, dot_fma);
+            dq = contact_dist_sq<R>(e.px, e.py, e.ox, e.oy, dot_fma, odx_, ody_);
+        }
+        if (!(dq > K<R>::radius_sq)) {
+            contacts += 0x10000;
+            contact_response<R>(e.px, e.py, e.pdx, e.pdy, e.ox, e.oy, e.odx, e.ody, odx_, ody_, dq, dot_fma);
+        }
+        limit_puck_speed<R>(e.pdx, e.pdy);                                       // :117
+        thr = K<R>::radius_sq;
+    } else if (COMPUTER) {
+        if (Math<R>::exact) limit_puck_speed<R>(e.pdx, e.pdy);
+    }
+    if (COMPUTER && !Math<R>::exact) {
+        // within limits before computerAI's nudge (+2 or +0 on both axes) => only the upper limit can bind; after the
+        // rare branch the velocity is already limited and this is the identity
+        e.pdx = fminf((float)e.pdx, 10.0f);
+        e.pdy = fminf((float)e.pdy, 10.0f);
+    }
+    puck_update<R>(e.px, e.py, e.pdx, e.pdy);                                    // :118
+    mallet_update<R>(e.rx, e.ry, e.rdx, e.rdy, K<R>::robot_lo, K<R>::robot_hi);  // :121-122
+    mallet_update<R>(e.ox, e.oy, e.odx, e.ody, K<R>::opp_lo, K<R>::opp_hi);
+}
+
+// raw action byte -> position nudge (airhockey.py:74-84): 0: y += 10, 1: y -= 10, 2: x -= 10, 3: x += 10, any other
+// value: no nudge.  A 256-entry table in GLOBAL memory read through L1 (ld.global.nc): no per-block table to fill and no
+// index clamp; 2 KB / 4 KB that stay L1-resident.
+__device__ const float2 g_nudge_f32[256] = {{0.f, 10.f}, {0.f, -10.f}, {-10.f, 0.f}, {10.f, 0.f}};
+__device__ const double2 g_nudge_f64[256] = {{0., 10.}, {0., -10.}, {-10., 0.}, {10., 0.}};
+__device__ __forceinline__ float2 nudge_of(const float2* t, uint32_t byte) { return __ldg(t + byte); }
+__device__ __forceinline__ double2 nudge_of(const double2* t, uint32_t byte) { return __ldg(t + byte); }
+
+template <typename V2> __device__ __forceinline__ V2 lds_v2(uint32_t addr);
+template <> __device__ __forceinline__ float2 lds_v2<float2>(uint32_t addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+template <> __device__ __forceinline__ double2 lds_v2<double2>(uint32_t addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+
+// Launch geometry (measured on B200, n = 2^20, K = 8, FP32; gpurun_out r2c-r2e): blocks of 128
+// threads, 9 per SM (56 registers; the kernel needs 51) beat 256 x 4 by 1.5-2 us per launch -- a block's registers are
+// held until its slowest warp is done, and the warps of a block finish at different times (contact / goal branches);
+// 10 or 12 blocks per SM (48 / 40 registers, spills outside the loop) are slower: the loop is pipe-bound, not
+// latency-bound.
+#ifndef AH_PACKED_THREADS
+#define AH_PACKED_THREADS 128
+#endif
+#ifndef AH_PACKED_OCC_F32
+#define AH_PACKED_OCC_F32 9
+#endif
+constexpr int kPackedThreads = AH_PACKED_THREADS;
+template <typename R> struct PackedOcc { static constexpr int blocks = AH_PACKED_OCC_F32; };
+template <> struct PackedOcc<double> { static constexpr int blocks = 512 / AH_PACKED_THREADS; };
+
+template <typename R>
+__global__ void __launch_bounds__(kPackedThreads, PackedOcc<R>::blocks)
+step_packed_kernel(const PackedArgs<R> a) {
+    using V2 = typename std::conditional<sizeof(R) == 4, float2, double2>::type;
+    __shared__ BlockStats bs;
+    if (threadIdx.x < AH_NSTATS) bs.v[threadIdx.x] = 0;
+    if (threadIdx.x == 0) { bs.len_sq = 0ull; bs.warps_done = 0; }
+    __syncthreads();
+    const V2* nudge_tab = sizeof(R) == 4 ? reinterpret_cast<const V2*>(g_nudge_f32) : reinterpret_cast<const V2*>(g_nudge_f64);
+
+    const uint32_t n = (uint32_t)a.n;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const bool dot_fma = a.dot_fma != 0;
+    const int nK = a.K;
+    const int quads = (nK + 3) >> 2;
+    int r3sum = 0, r3sq = 0, dones = 0, contacts = 0, frames = 0, bad = 0, amb = 0;
+    unsigned overflow = 0;
+
+    for (uint32_t i = a.i0 + blockIdx.x * blockDim.x + threadIdx.x; i < a.i_end; i += stride) {
+        Env<R> e = load_env<R>(a.st, i);
+        uint32_t aw = a.actions[i];
+        int go = (e.robot_score == 10) ? 1 : ((e.opp_score == 10) ? 2 : 0);   // only reachable through injected state
+        // contact-test threshold: radius^2, or +inf while the velocity may be outside the speed limits (injected
+        // state, table resets): the rare branch then runs once and clamps (limit_puck_speed is idempotent)
+        R thr = speed_out_of_limits<R>(e.pdx, e.pdy) ? (R)INFINITY : K<R>::radius_sq;
+        int gf_base = e.game_frames;        // frames-in-game = gf_base + frames done in this launch
+        // The current game's return is kept as "sum of r3 since r3_mark": reward = 2 r3 - 4, so
+        // return = 2 (r3sum - r3_mark) - 4 frames_in_game.  One accumulator (r3sum) serves the launch statistics too.
+        int r3_mark = r3sum - ((e.game_return + 4 * e.game_frames) >> 1);
+        uint32_t off = i;                   // word (q, i) of the quad-major action / event arrays: q * n + i
+        int left = nK;                      // frames left at the start of the quad
+#pragma unroll 1
+        do {
+            const int kc = left < 4 ? left : 4;
+            uint32_t aw_next = 0;
+            if (left > 4) aw_next = a.actions[off + n];
+            uint32_t ev = 0;
+            int jr = kc;                    // frames left in the quad, counting the current one
+#pragma unroll 1
+            do {
+                const V2 nd = nudge_of(nudge_tab, aw & 0xffu);
+                aw >>= 8;
+                // ---- robot.move(a): sub-update #1                      game.py:136 -> agent.py:32-36
+                move_robot<R>(e, false, nd.x, nd.y);
+                physics_tail_thr<R, false>(e, dot_fma, thr, contacts);
+                // ---- robot.step(a) -> self.move(a): sub-update #2      agent.py:64
+                move_robot<R>(e, false, nd.x, nd.y);
+                physics_tail_thr<R, false>(e, dot_fma, thr, contacts);
+                // ---- Rewards                                           agent.py:70-71
+                int sc; bool dn, wl, wr, closer;
+                rewards_bits<R>(e, dot_fma, sc, dn, wl, wr, closer, amb);
+                // event byte: (reward + 4) / 2 = 1 + closer + wall + 2 done, done << 3, (score + 1) << 4, game_over << 6
+                uint32_t byte = (closer ? 0x12u : 0x11u) + (wr ? 1u : (wl ? 0xffffffffu : 0u)) + (dn ? 10u : 0u);
+                // ---- env.update_score(score)                           game.py:142 -> airhockey.py:149-169
+                if (sc != 0) {
+                    byte += (uint32_t)(sc * 16);
+                    if (sc > 0) { e.robot_score += 1; stat_add(bs, AH_STAT_ROBOT_GOALS, 1); }
+                    else { e.opp_score += 1; stat_add(bs, AH_STAT_OPPONENT_GOALS, 1); }
+                    env_reset<R>(e, false, a.rs, i, overflow);
+                    if (a.rs.table != nullptr) thr = (R)INFINITY;         // table values may exceed the limits
+                    go = (e.robot_score == 10) ? 1 : go;                  // stats(): game.py:101-109
+                    go = (e.opp_score == 10) ? 2 : go;
+                }
+                byte += (uint32_t)go << 6;
+                ev = __byte_perm(ev, byte, 0x4321);                       // frames land in byte order
+                // ---- env.update_state(agent_name="computer"): sub-update #3   game.py:166
+                computer_ai<R>(e);
+                physics_tail_thr<R, true>(e, dot_fma, thr, contacts);
+                // ---- 10-goal game over                                 game.py:169-177
+                if (go != 0) {
+                    int jr_o = jr, left_o = left;                          // (opaque: no induction variables for the rare path)
+                    asm volatile("" : "+r"(jr_o), "+r"(left_o));
+                    const int jdone = (left_o < 4 ? left_o : 4) - jr_o + 1;   // frames of this quad done, with this one
+                    const int kk = nK - left_o + jdone;                    // frames done in this launch
+                    stat_add(bs, AH_STAT_GAMES, 1);
+                    stat_add(bs, go == 1 ? AH_STAT_ROBOT_WINS : AH_STAT_OPPONENT_WINS, 1);
+                    const int len = gf_base + kk;
+                    stat_add(bs, AH_STAT_GAME_LEN_SUM, len);
+                    atomicAdd(&bs.len_sq, (unsigned long long)len * (unsigned long long)len);
+                    // r3 of the finished game = whole quads so far + this quad's frames so far (unfilled bytes are 0)
+                    const int part = (int)__dp4a(ev & 0x07070707u, 0x01010101u, 0u);
+                    stat_add(bs, AH_STAT_GAME_RETURN_SUM, 2 * (r3sum + part - r3_mark) - 4 * len);
+                    r3_mark = r3sum + part;
+                    gf_base = -kk;
+                    env_reset<R>(e, true, a.rs, i, overflow);
+                    if (a.rs.table != nullptr) thr = (R)INFINITY;
+                    go = 0;
+                }
+            } while (--jr > 0);
+            if (left < 4) ev >>= 8 * (4 - left);                           // partial last quad: frame 0 in byte 0
+            a.events[off] = ev;
+            // statistics of the quad from the packed word
+            const uint32_t r3 = ev & 0x07070707u;
+            r3sum = (int)__dp4a(r3, 0x01010101u, (uint32_t)r3sum);
+            r3sq = (int)__dp4a(r3, r3, (uint32_t)r3sq);
+            dones += __popc(ev & 0x08080808u);
+            off += n;
+            left -= 4;
+            aw = aw_next;
+        } while (left > 0);
+        if (a.obs_next) store_obs<R>(a.obs_next, i, get_state<R>(e, true));   // the next frame's policy input (agent.py:46)
+        frames += nK;
+        e.game_frames = gf_base + nK;
+        e.game_return = 2 * (r3sum - r3_mark) - 4 * e.game_frames;
+        bad += isfinite((e.px + e.py) + (e.pdx + e.pdy)) ? 0 : 1;           // any NaN / inf component poisons the sum
+        store_env<R>(a.st, i, e);
+    }
+
+    // reward = 2 r3 - 4  =>  sum = 2 S1 - 4 F,  sum of squares = 4 S2 - 16 S1 + 16 F
+    const int reward_sum = 2 * r3sum - 4 * frames;
+    const int reward_sq = 4 * r3sq - 16 * r3sum + 16 * frames;
+    finish_stats<false>(bs, a.blk, a.collect_stats, frames, reward_sum, reward_sq, dones, contacts & 0xffff, contacts >> 16,
+                 (int)overflow, bad, amb, a.i0 == 0 ? nK : 0, nullptr);
+}
+
+}  // namespace ah

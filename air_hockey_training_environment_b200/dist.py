@@ -34,6 +34,52 @@ def rank_info() -> Tuple[int, int, int]:
             int(os.environ.get("LOCAL_RANK", "0")))
 
 
+def _parse_cpulist(text: str):
+    cpus = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.extend(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def _gpu_numa_node(index: int) -> Tuple[str, int]:
+    p = torch.cuda.get_device_properties(index)
+    bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+    path = f"/sys/bus/pci/devices/{bdf}/numa_node"
+    return bdf, (int(open(path).read().strip()) if os.path.exists(path) else -1)
+
+
+def bind_host_to_gpu(local_rank: int, local_world: int = 1) -> Dict[str, object]:
+    """Pin this process to host cores next to its GPU, BEFORE it allocates pinned staging buffers (first touch puts
+    them on that NUMA node): the host-buffer path (``host.HostStepper``) is bound by PCIe and host memory, and at 8
+    ranks per box unpinned processes all land on one node.  The cores of the GPU's NUMA node (sysfs) that this
+    process may use are split evenly among the local ranks whose GPUs share that node.  Best effort: returns what it
+    did (``bound: False`` with the reason when sysfs / affinity calls are not available)."""
+    info: Dict[str, object] = {"bound": False}
+    try:
+        bdf, node = _gpu_numa_node(local_rank)
+        peers = [r for r in range(local_world) if _gpu_numa_node(r)[1] == node] or [local_rank]
+        allowed = sorted(os.sched_getaffinity(0))
+        info.update(pci=bdf, numa_node=node, allowed_cpus=len(allowed), ranks_on_node=len(peers))
+        cpus = allowed
+        cpulist = f"/sys/devices/system/node/node{node}/cpulist"
+        if node >= 0 and os.path.exists(cpulist):
+            local = [c for c in _parse_cpulist(open(cpulist).read()) if c in allowed]
+            info["node_local_cpus"] = len(local)
+            if local:
+                cpus = local
+        share = max(1, len(cpus) // len(peers))
+        k = peers.index(local_rank) if local_rank in peers else 0
+        mine = cpus[k * share:(k + 1) * share] or cpus
+        os.sched_setaffinity(0, mine)
+        info.update(bound=True, cpus=len(mine), first_cpu=mine[0])
+    except Exception as e:                                   # no sysfs / no permission: run unbound
+        info["error"] = repr(e)
+    return info
+
+
 def init_process_group(backend: Optional[str] = None) -> Tuple[int, int, int]:
     """Initialise torch.distributed from the torchrun environment (nccl on GPUs, gloo on CPU)."""
     rank, world, local = rank_info()
@@ -49,10 +95,10 @@ def init_process_group(backend: Optional[str] = None) -> Tuple[int, int, int]:
 
 
 def all_reduce_stats(stats: torch.Tensor, group=None) -> torch.Tensor:
-    """Sum the int64[16] statistics vector over all ranks, in place (one 128-byte all-reduce per rollout; NCCL
+    """Sum the int64[AH_NSTATS] statistics vector over all ranks, in place (one 160-byte all-reduce per rollout; NCCL
     over NVLink on GPUs).  A no-op for a single process."""
     if stats.dtype != torch.int64 or stats.numel() != _capi.AH_NSTATS:
-        raise ValueError("stats must be the int64[16] vector returned by BatchedAirHockey.stats_tensor()")
+        raise ValueError("stats must be the int64[AH_NSTATS] vector returned by BatchedAirHockey.stats_tensor()")
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
     return stats

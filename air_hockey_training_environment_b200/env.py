@@ -26,7 +26,27 @@ from .exceptions import InvalidAgentError
 
 _AGENTS = {"robot": _capi.AH_AGENT_ROBOT, "human": _capi.AH_AGENT_HUMAN, "computer": _capi.AH_AGENT_COMPUTER}
 
-STEP_FIELDS = ("obs_state", "obs_new_state", "reward", "done", "score", "game_over", "obs_next", "actions", "probs")
+STEP_FIELDS = ("obs_state", "obs_new_state", "reward", "done", "score", "game_over", "obs_next", "actions", "probs", "events")
+
+
+def pack_actions(actions: torch.Tensor) -> torch.Tensor:
+    """int8/uint8 [K, N] per-frame discrete actions -> uint8 [ceil(K/4), N, 4] "quad-major" (AH_ACT_DISCRETE_PACKED4):
+    byte j of word (q, i) is env i's action of frame 4q + j.  The input format of the packed rollout mode."""
+    K, n = actions.shape
+    q = (K + 3) // 4
+    a = actions.to(torch.uint8)
+    if q * 4 != K:
+        a = torch.cat([a, torch.zeros(q * 4 - K, n, dtype=torch.uint8, device=a.device)], 0)
+    return a.view(q, 4, n).permute(0, 2, 1).contiguous()
+
+
+def unpack_events(events: torch.Tensor, K: int) -> Dict[str, torch.Tensor]:
+    """uint8 [ceil(K/4), N, 4] event bytes (AH_EVENT_* in include/ah_b200.h) -> the reference's per-frame outputs,
+    time-major [K, N]: reward (int8, lib/rewards.py:118-142), done (bool), score (int8), game_over (uint8)."""
+    q, n, _ = events.shape
+    b = events.permute(0, 2, 1).reshape(q * 4, n)[:K]
+    return {"reward": ((b & 7).to(torch.int8) << 1) - 4, "done": ((b >> 3) & 1).to(torch.bool),
+            "score": ((b >> 4) & 3).to(torch.int8) - 1, "game_over": (b >> 6) & 3}
 
 
 @dataclass
@@ -41,14 +61,23 @@ class StepOutputs:
     obs_next: Optional[torch.Tensor] = None        # real [N,8] or [K,N,8]: the next frame's policy input
     actions: Optional[torch.Tensor] = None         # i8   [K,N]    the discrete actions applied (Philox / in-kernel policy)
     probs: Optional[torch.Tensor] = None           # real [K,N,4]  the in-kernel actor's distribution (policy mode only)
+    events: Optional[torch.Tensor] = None          # u8   [ceil(K/4),N,4]  packed rollout mode: reward, done, score and
+                                                   #               game_over of a frame in ONE byte (see unpack_events)
 
 
 class ReplayRing:
     """Device-resident replacement of ``MemoryBuffer`` (lib/buffer.py:11-66) for ``Observation`` tuples
     (lib/types.py:7), filled from inside the step kernel.  Layout ``[capacity, N, ...]``; like the reference's
-    ``appendleft`` + ``retreive`` the newest entry comes first when read back."""
+    ``appendleft`` + ``retreive`` the newest entry comes first when read back.
 
-    def __init__(self, capacity: int, n_envs: int, dtype: torch.dtype, device, continuous: bool = False):
+    The ring owns its append counter as a device tensor (``counter``, uint64 as int64[1]): the step kernel reads the
+    write slot from it and advances it, so it is correct under CUDA-graph replay, and ``purge()`` is a stream-ordered
+    ``counter.zero_()``.  ``len(ring)`` / ``order()`` / ``retreive()`` read it back (one host sync); ``sample`` does not."""
+
+    FIELDS = ("state", "action", "reward", "done", "new_state")
+
+    def __init__(self, capacity: int, n_envs: int, dtype: torch.dtype, device, continuous: bool = False,
+                 default: Optional[Dict[str, float]] = None):
         self.capacity, self.n = int(capacity), int(n_envs)
         self.continuous = continuous
         self.state = torch.zeros(capacity, n_envs, 8, dtype=dtype, device=device)
@@ -57,36 +86,91 @@ class ReplayRing:
                        else torch.zeros(capacity, n_envs, dtype=torch.int8, device=device))
         self.reward = torch.zeros(capacity, n_envs, dtype=dtype, device=device)
         self.done = torch.zeros(capacity, n_envs, dtype=torch.uint8, device=device)
+        self.counter = torch.zeros(1, dtype=torch.int64, device=device)
         self._c = _capi.AhRing(self.state.data_ptr(), self.new_state.data_ptr(), self.action.data_ptr(),
-                               self.reward.data_ptr(), self.done.data_ptr(), self.capacity)
-        self.appended = 0          # host mirror of the device counter (valid when steps are not graph-replayed)
+                               self.reward.data_ptr(), self.done.data_ptr(), self.capacity, self.counter.data_ptr())
+        self._draw = 0
+        if default:                                    # lib/buffer.py:19-22: a buffer full of default entries
+            self.fill(default)
+
+    def fill(self, default: Dict[str, float]) -> None:
+        """Fill every slot with a default tuple (``MemoryBuffer(capacity, default)``, lib/buffer.py:19-22)."""
+        for k in self.FIELDS:
+            getattr(self, k).fill_(default.get(k, 0))
+        self.counter.fill_(self.capacity)
+
+    def append(self, state: torch.Tensor, action: torch.Tensor, reward: torch.Tensor, done: torch.Tensor,
+               new_state: torch.Tensor) -> None:
+        """``MemoryBuffer.append(Observation(...))`` (lib/buffer.py:24-32) from device tensors ([N, ...], one tuple per
+        env) -- the host-side verb; rollouts append from inside the step kernel instead (``step(ring=...)``).
+        Stream-ordered, no host sync: the slot is computed on the device from the ring's counter."""
+        slot = self.counter % self.capacity
+        for k, v in zip(self.FIELDS, (state, action, reward, done, new_state)):
+            dst = getattr(self, k)
+            dst.index_copy_(0, slot, v.to(dst.dtype).reshape((1,) + tuple(dst.shape[1:])))
+        self.counter += 1
+
+    @property
+    def appended(self) -> int:
+        """Observation tuples appended since the last purge (reads the device counter)."""
+        return int(self.counter.item())
 
     def __len__(self) -> int:      # lib/buffer.py:63-66
         return min(self.appended, self.capacity)
 
     def order(self) -> torch.Tensor:
         """Slot indices newest-first, the order of ``MemoryBuffer.retreive`` (lib/buffer.py:34-45)."""
-        n = len(self)
-        newest = (self.appended - 1) % self.capacity
+        appended = self.appended
+        n = min(appended, self.capacity)
+        newest = (appended - 1) % self.capacity
         return (newest - torch.arange(n, device=self.state.device)) % self.capacity
 
-    def retreive(self) -> Dict[str, torch.Tensor]:
+    def retreive(self, average: bool = False) -> Dict[str, torch.Tensor]:
+        """``MemoryBuffer.retreive`` (lib/buffer.py:34-45): the held tuples, newest first, as ``[len, N, ...]`` tensors;
+        ``average=True`` returns the one-entry column average ``int(sum(col) / len)`` (truncated, :37-38)."""
         idx = self.order()
-        return {"state": self.state[idx], "action": self.action[idx], "reward": self.reward[idx],
-                "done": self.done[idx], "new_state": self.new_state[idx]}
+        got = {k: getattr(self, k)[idx] for k in self.FIELDS}
+        if average:
+            got = {k: torch.trunc(v.to(torch.float64).sum(0, keepdim=True) / max(1, idx.numel())).to(v.dtype)
+                   for k, v in got.items()}
+        return got
 
-    def sample(self, batch_size: int, generator: Optional[torch.Generator] = None) -> Dict[str, torch.Tensor]:
-        """Uniform sample without replacement over (slot, env) pairs (lib/buffer.py:47-50), on device."""
-        total = len(self) * self.n
-        if batch_size > total:
-            raise ValueError("Sample larger than population")        # what random.sample raises
-        flat = torch.randperm(total, device=self.state.device, generator=generator)[:batch_size]
-        slot, env = self.order()[flat // self.n], flat % self.n
-        return {"state": self.state[slot, env], "action": self.action[slot, env], "reward": self.reward[slot, env],
-                "done": self.done[slot, env], "new_state": self.new_state[slot, env]}
+    def sample(self, batch_size: int, env: "BatchedAirHockey", draw: Optional[int] = None, check: bool = True,
+               out: Optional[Dict[str, torch.Tensor]] = None, with_index: bool = False) -> Dict[str, torch.Tensor]:
+        """``MemoryBuffer.sample(batch_size)`` (lib/buffer.py:47-50): uniform WITHOUT replacement over the held
+        (tuple, env) pairs, in one kernel (``ah_ring_sample``: a keyed bijection of the population, no permutation is
+        materialised).  ``draw`` numbers the sample (default: a counter that advances per call); ``check`` reads the
+        device counter to raise what ``random.sample`` raises for an over-sized batch (skip it inside CUDA graphs)."""
+        if check and batch_size > len(self) * self.n:
+            raise ValueError("Sample larger than population or is negative")
+        if draw is None:
+            draw, self._draw = self._draw, self._draw + 1
+        dev, dt, B = self.state.device, self.state.dtype, int(batch_size)
+        if out is None:
+            out = {"state": torch.empty(B, 8, dtype=dt, device=dev), "new_state": torch.empty(B, 8, dtype=dt, device=dev),
+                   "action": (torch.empty(B, 2, dtype=dt, device=dev) if self.continuous
+                              else torch.empty(B, dtype=torch.int8, device=dev)),
+                   "reward": torch.empty(B, dtype=dt, device=dev), "done": torch.empty(B, dtype=torch.uint8, device=dev)}
+            if with_index:
+                out["index"] = torch.empty(B, dtype=torch.int64, device=dev)
+        idx = out.get("index")
+        _capi.check(env._lib.ah_ring_sample(env._h, C.byref(self._c), int(self.continuous), B, int(draw),
+                                            out["state"].data_ptr(), out["action"].data_ptr(), out["reward"].data_ptr(),
+                                            out["done"].data_ptr(), out["new_state"].data_ptr(),
+                                            None if idx is None else idx.data_ptr(), env._stream()), "ah_ring_sample", env._h)
+        return out
 
-    def purge(self) -> None:       # lib/buffer.py:52-61
-        self.appended = 0
+    def purge(self, default: Optional[Dict[str, float]] = None) -> None:       # lib/buffer.py:52-61
+        self.counter.zero_()
+        if default:
+            self.fill(default)
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        return {k: getattr(self, k).clone() for k in ("state", "new_state", "action", "reward", "done", "counter")}
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
+        for k in ("state", "new_state", "action", "reward", "done", "counter"):
+            getattr(self, k).copy_(sd[k])
 
 
 class BatchedAirHockey:
@@ -273,12 +357,14 @@ class BatchedAirHockey:
             o.actions = torch.empty(K, self.n, dtype=torch.int8, device=self.device)
         if "probs" in fields:
             o.probs = torch.empty(K, self.n, 4, **r)
+        if "events" in fields:
+            o.events = torch.empty((K + 3) // 4, self.n, 4, dtype=torch.uint8, device=self.device)
         return o
 
     def step(self, actions: Optional[torch.Tensor] = None, K: int = 1, *, repeat: bool = False,
              out: Optional[StepOutputs] = None, reset_table: Optional[torch.Tensor] = None,
              ring: Optional[ReplayRing] = None, collect_stats: bool = True,
-             policy_weights: Optional[torch.Tensor] = None) -> StepOutputs:
+             policy_weights: Optional[torch.Tensor] = None, env_range: Optional[Sequence[int]] = None) -> StepOutputs:
         """K fused frames of ``Game.play`` for every env, in ONE kernel launch (state stays in registers).
 
         actions: None                -> uniform random {0,1,2,3} drawn in-kernel (Philox)
@@ -286,6 +372,8 @@ class BatchedAirHockey:
                  real [K,N,2]        -> one continuous action per frame ([N,2] when K == 1 or ``repeat``)
         repeat:  apply the single given action to all K frames (frame-skip)
         out:     preallocated ``StepOutputs`` (see ``make_outputs``); default: reward/done/score/game_over/obs_next
+        env_range: (first, count) -- packed mode only: step just that slice of the envs (tensor shapes stay those of the
+                 full N), so one step can be issued as disjoint slices on different streams (host.InterleavedStepper)
         policy_weights: float32 [114] device tensor (``rollout.FusedActor.weights``): closed loop -- every frame the
                  reference-shaped actor is evaluated IN the kernel on the env's current observation and the action
                  is sampled from its softmax (``actions`` must be None); ``out.actions`` / ``out.probs`` receive them
@@ -299,6 +387,13 @@ class BatchedAirHockey:
             self._check_tensor(policy_weights, (_capi.AH_ACTOR_NWEIGHTS,), torch.float32, "policy_weights")
             io.action_kind = _capi.AH_ACT_POLICY
             io.actions = policy_weights.data_ptr()
+        elif out.events is not None:
+            # PACKED rollout mode: quad-major uint8 actions in, one event byte per env-frame out (+ obs_next [N,8])
+            if actions is None or actions.dtype not in (torch.uint8, torch.int8):
+                raise ValueError("the packed mode takes uint8 [ceil(K/4), N, 4] actions (see pack_actions)")
+            self._check_tensor(actions, ((K + 3) // 4, self.n, 4), actions.dtype, "actions")
+            io.action_kind = _capi.AH_ACT_DISCRETE_PACKED4
+            io.actions = actions.data_ptr()
         elif actions is None:
             io.action_kind = _capi.AH_ACT_PHILOX
         else:
@@ -339,14 +434,17 @@ class BatchedAirHockey:
             if policy_weights is None:
                 raise ValueError("out.probs is only produced in policy mode")
             io.probs_out = self._check_tensor(out.probs, (K, self.n, 4), r, "probs").data_ptr()
+        if out.events is not None:
+            io.events = self._check_tensor(out.events, ((K + 3) // 4, self.n, 4), torch.uint8, "events").data_ptr()
         io.collect_stats = int(collect_stats)
+        if env_range is not None:
+            io.env_first, io.env_count = int(env_range[0]), int(env_range[1])
         if ring is not None:
             if ring.n != self.n or ring.state.dtype != self.dtype or ring.state.device != self.device:
                 raise ValueError("ring does not match this environment")
             if ring.continuous != (io.action_kind in (_capi.AH_ACT_CONTINUOUS, _capi.AH_ACT_CONTINUOUS_REPEAT)):
                 raise ValueError("ring action layout (discrete/continuous) does not match the actions given")
             io.ring = C.pointer(ring._c)
-            ring.appended += K
         self._io_keepalive = (io, actions)
         _capi.check(self._lib.ah_step(self._h, C.byref(io), int(K), self._stream()), "ah_step", self._h)
         return out
@@ -362,14 +460,13 @@ class BatchedAirHockey:
         v = self.stats_tensor(clear).tolist()
         return dict(zip(_capi.STAT_NAMES, v))
 
-    def set_counters(self, frame: int = 0, ring_appended: int = 0) -> None:
-        _capi.check(self._lib.ah_set_counters(self._h, frame, ring_appended, self._stream()), "ah_set_counters", self._h)
+    def set_counters(self, frame: int = 0) -> None:
+        _capi.check(self._lib.ah_set_counters(self._h, frame, self._stream()), "ah_set_counters", self._h)
 
     def counters(self) -> Dict[str, int]:
-        buf = torch.zeros(2, dtype=torch.int64, device=self.device)
+        buf = torch.zeros(1, dtype=torch.int64, device=self.device)
         _capi.check(self._lib.ah_get_counters(self._h, buf.data_ptr(), self._stream()), "ah_get_counters", self._h)
-        f, r = buf.tolist()
-        return {"frame": f, "ring_appended": r}
+        return {"frame": int(buf.item())}
 
     def launch_info(self) -> Dict[str, int]:
         b, t, s = C.c_int(), C.c_int(), C.c_int()
@@ -386,11 +483,51 @@ class BatchedAirHockey:
         c = self.counters()
         return {"puck": self.puck.clone(), "robot": self.robot.clone(), "opponent": self.opponent.clone(),
                 "prev_dist": self.prev_dist.clone(), "meta": self.meta.clone(),
-                "counters": torch.tensor([c["frame"], c["ring_appended"]], dtype=torch.int64),
+                "counters": torch.tensor([c["frame"]], dtype=torch.int64),
                 "seed": torch.tensor([self.seed, self.env_id0], dtype=torch.int64)}
 
     def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
         for k in ("puck", "robot", "opponent", "prev_dist", "meta"):
             getattr(self, k).copy_(sd[k])
-        f, r = sd["counters"].tolist()
-        self.set_counters(int(f), int(r))
+        self.set_counters(int(sd["counters"][0]))
+
+
+class InterleavedStepper:
+    """Issues every packed step as ``parts`` disjoint env slices on ``parts`` private streams (``env_range`` launches).
+
+    One launch over all N envs pays a ramp (every resident block loads its state at once) and a tail (the last blocks
+    finish on a mostly idle GPU) per step.  Slices on different streams are independent (an env only ever depends on
+    its own previous step, which is earlier on the SAME stream), so the GPU never drains between steps: the tail of
+    one slice's launch overlaps the head of the next slice's.  Results are identical to ``env.step`` (same kernel, same
+    per-env arithmetic; tests/test_gpu_packed.py).
+
+    ``step`` returns immediately; call ``join()`` before reading outputs / state / statistics on the caller's stream.
+    """
+
+    def __init__(self, env: BatchedAirHockey, parts: int = 2, align: int = 1024):
+        self.env, self.parts = env, int(parts)
+        per = -(-env.n // self.parts)
+        per = -(-per // align) * align                       # whole blocks per slice
+        self.ranges = [(lo, min(per, env.n - lo)) for lo in range(0, env.n, per)]
+        self.streams = [torch.cuda.Stream(env.device) for _ in self.ranges]
+        self._forked = False
+
+    def step(self, actions: torch.Tensor, K: int, out: StepOutputs, **kw) -> StepOutputs:
+        if out.events is None:
+            raise ValueError("InterleavedStepper drives the packed mode (out.events)")
+        cur = torch.cuda.current_stream(self.env.device)
+        if not self._forked:                                 # order the slices after whatever the caller queued
+            for s in self.streams:
+                s.wait_stream(cur)
+            self._forked = True
+        for s, rng in zip(self.streams, self.ranges):
+            with torch.cuda.stream(s):
+                self.env.step(actions, K=K, out=out, env_range=rng, **kw)
+        return out
+
+    def join(self) -> None:
+        """Make the caller's current stream wait for every slice issued so far (no host sync)."""
+        cur = torch.cuda.current_stream(self.env.device)
+        for s in self.streams:
+            cur.wait_stream(s)
+        self._forked = False

@@ -21,9 +21,10 @@ from .env import BatchedAirHockey
 @dataclass
 class HostResult:
     """Results of one step in pinned host memory (valid after ``wait()``)."""
-    events: torch.Tensor        # uint8 [K, n]: low nibble = reward + 4, bit 4 = done
+    events: torch.Tensor        # uint8 [ceil(K/4), n, 4]: one AH_EVENT byte per env-frame (include/ah_b200.h), quad-major
     obs_pos: torch.Tensor       # int16 [n, 4]: int(agent.x), int(agent.y), int(puck.x), int(puck.y)
     obs_vel: torch.Tensor       # float32 [n, 4]: agent.dx, agent.dy, puck.dx, puck.dy
+    K: int = 8
     _event: Optional[torch.cuda.Event] = None
 
     def wait(self) -> "HostResult":
@@ -31,13 +32,25 @@ class HostResult:
             self._event.synchronize()
         return self
 
+    def _frames(self) -> torch.Tensor:          # uint8 [K, n], time-major
+        q, n, _ = self.events.shape
+        return self.events.permute(0, 2, 1).reshape(q * 4, n)[:self.K]
+
     @property
     def reward(self) -> torch.Tensor:           # int8 [K, n]  (lib/rewards.py:118-142 returns integers)
-        return (self.events & 15).to(torch.int8) - 4
+        return ((self._frames() & 7).to(torch.int8) << 1) - 4
 
     @property
     def done(self) -> torch.Tensor:             # bool [K, n]
-        return (self.events >> 4).to(torch.bool)
+        return ((self._frames() >> 3) & 1).to(torch.bool)
+
+    @property
+    def score(self) -> torch.Tensor:            # int8 [K, n]: +1 robot scored, -1 opponent scored
+        return ((self._frames() >> 4) & 3).to(torch.int8) - 1
+
+    @property
+    def game_over(self) -> torch.Tensor:        # uint8 [K, n]: 0 / 1 robot won / 2 opponent won
+        return (self._frames() >> 6) & 3
 
     @property
     def obs(self) -> torch.Tensor:              # float32 [n, 8] in the reference's layout
@@ -45,36 +58,54 @@ class HostResult:
 
 
 class HostStepper:
-    """``submit(actions_host)`` enqueues H2D -> fused step -> pack -> D2H for one step and returns immediately;
-    the returned ``HostResult`` is complete after ``wait()``.  ``slots`` steps can be in flight."""
+    """``submit(actions_host)`` enqueues H2D -> fused step -> D2H for one step and returns immediately; the returned
+    ``HostResult`` is complete after ``wait()``.  ``slots`` steps can be in flight.
+
+    The step runs in the packed rollout mode: the actions cross the bus as the quad-major uint8 words the kernel reads
+    (``pack_actions_host``), the per-frame results as the event bytes it writes -- nothing is re-encoded on the device
+    except the observation (4 x int16 + 4 x float32 per env).
+
+    Streams: the copies and the kernels run on three private streams.  ``submit`` first makes them wait for the
+    caller's current stream (so work the caller queued on the env -- ``init_state``, an earlier ``env.step`` -- is
+    ordered before this step), and ``join()`` makes the caller's current stream wait for everything submitted (call it
+    before reading ``env`` state or statistics on the caller's stream)."""
 
     def __init__(self, env: BatchedAirHockey, K: int = 8, slots: int = 3):
         self.env, self.K, self.slots = env, int(K), int(slots)
-        n, dev = env.n, env.device
+        n, dev, q = env.n, env.device, (int(K) + 3) // 4
         self._lib = _capi.lib()
-        self.d_act = [torch.empty(K, n, dtype=torch.int8, device=dev) for _ in range(slots)]
-        self.outs = [env.make_outputs(K, ("reward", "done", "score", "game_over", "obs_next")) for _ in range(slots)]
-        self.d_events = [torch.empty(K, n, dtype=torch.uint8, device=dev) for _ in range(slots)]
+        self.d_act = [torch.empty(q, n, 4, dtype=torch.uint8, device=dev) for _ in range(slots)]
+        self.outs = [env.make_outputs(K, ("events", "obs_next")) for _ in range(slots)]
         self.d_pos = [torch.empty(n, 4, dtype=torch.int16, device=dev) for _ in range(slots)]
         self.d_vel = [torch.empty(n, 4, dtype=torch.float32, device=dev) for _ in range(slots)]
-        self.h = [HostResult(torch.empty(K, n, dtype=torch.uint8).pin_memory(),
+        self.h = [HostResult(torch.empty(q, n, 4, dtype=torch.uint8).pin_memory(),
                              torch.empty(n, 4, dtype=torch.int16).pin_memory(),
-                             torch.empty(n, 4, dtype=torch.float32).pin_memory()) for _ in range(slots)]
+                             torch.empty(n, 4, dtype=torch.float32).pin_memory(), K=int(K)) for _ in range(slots)]
         self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
         self.e_in = [torch.cuda.Event() for _ in range(slots)]
         self.e_run = [torch.cuda.Event() for _ in range(slots)]
         self.e_out: List[Optional[torch.cuda.Event]] = [None] * slots
         self._i = 0
-        self.h2d_bytes_per_step = K * n
-        self.d2h_bytes_per_step = K * n + n * 4 * 2 + n * 4 * 4
+        self.h2d_bytes_per_step = q * 4 * n
+        self.d2h_bytes_per_step = q * 4 * n + n * 4 * 2 + n * 4 * 4
+        self.s_run.wait_stream(torch.cuda.current_stream(dev))
+
+    @staticmethod
+    def pack_actions_host(actions: torch.Tensor) -> torch.Tensor:
+        """int8 [K, n] CPU actions -> pinned uint8 [ceil(K/4), n, 4] in the kernel's quad-major layout."""
+        from .env import pack_actions
+        return pack_actions(actions).pin_memory()
 
     def submit(self, actions_host: torch.Tensor) -> HostResult:
-        """actions_host: int8 [K, n] CPU tensor (pinned for an asynchronous copy)."""
+        """actions_host: uint8 [ceil(K/4), n, 4] CPU tensor (``pack_actions_host``; pinned for an asynchronous copy)."""
         K, n, s = self.K, self.env.n, self._i % self.slots
         self._i += 1
-        if actions_host.dtype != torch.int8 or tuple(actions_host.shape) != (K, n) or actions_host.device.type != "cpu":
-            raise ValueError(f"actions_host must be an int8 [{K}, {n}] CPU tensor")
+        if (actions_host.dtype != torch.uint8 or tuple(actions_host.shape) != ((K + 3) // 4, n, 4)
+                or actions_host.device.type != "cpu"):
+            raise ValueError(f"actions_host must be a uint8 [{(K + 3) // 4}, {n}, 4] CPU tensor (see pack_actions_host)")
         env = self.env
+        cur = torch.cuda.current_stream(env.device)
+        self.s_run.wait_stream(cur)                           # whatever the caller queued on the env comes first
         with torch.cuda.stream(self.s_in):
             self.s_in.wait_event(self.e_run[s])               # the slot's previous kernel has consumed its actions
             self.d_act[s].copy_(actions_host, non_blocking=True)
@@ -85,14 +116,13 @@ class HostStepper:
                 self.s_run.wait_event(self.e_out[s])          # the slot's previous results have left the device
             o = self.outs[s]
             env.step(self.d_act[s], K=K, out=o)
-            _capi.check(self._lib.ah_pack_host(env._h, K, o.reward.data_ptr(), o.done.data_ptr(), o.obs_next.data_ptr(),
-                                               self.d_events[s].data_ptr(), self.d_pos[s].data_ptr(),
+            _capi.check(self._lib.ah_pack_host(env._h, K, None, None, o.obs_next.data_ptr(), None, self.d_pos[s].data_ptr(),
                                                self.d_vel[s].data_ptr(), self.s_run.cuda_stream), "ah_pack_host", env._h)
             self.e_run[s].record(self.s_run)
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(self.e_run[s])
             h = self.h[s]
-            h.events.copy_(self.d_events[s], non_blocking=True)
+            h.events.copy_(o.events, non_blocking=True)
             h.obs_pos.copy_(self.d_pos[s], non_blocking=True)
             h.obs_vel.copy_(self.d_vel[s], non_blocking=True)
             ev = torch.cuda.Event()
@@ -100,6 +130,12 @@ class HostStepper:
             self.e_out[s] = ev
             h._event = ev
         return h
+
+    def join(self) -> None:
+        """Order the caller's current stream after everything submitted so far (no host sync)."""
+        cur = torch.cuda.current_stream(self.env.device)
+        cur.wait_stream(self.s_run)
+        cur.wait_stream(self.s_out)
 
     def drain(self) -> None:
         for ev in self.e_out:

@@ -222,9 +222,10 @@ def run_reference_arm(args):
 
 
 def workload_name(gpus: int) -> str:
-    return (f"{ENVS_PER_GPU} envs/GPU x {gpus} GPU, FP32, K={FRAMES_PER_STEP} fused frames/launch, per-frame int8 actions, "
-            "computerAI opponent + Rewards reward, reward/done/score/game_over[K,n] + obs_next[n,8] written, "
-            "in-kernel stats" + (" + NCCL all-reduce of stats per step" if gpus > 1 else ""))
+    return (f"{ENVS_PER_GPU} envs/GPU x {gpus} GPU, FP32, K={FRAMES_PER_STEP} fused frames/launch, per-frame uint8 actions "
+            "(quad-major), computerAI opponent + Rewards reward; written per env-frame: one event byte = reward, done, score, "
+            "game_over; per env: obs_next[n,8]; in-kernel stats, copied out"
+            + (" and all-reduced over NCCL" if gpus > 1 else "") + f" once per rollout ({ROLLOUT_STEPS} steps)")
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
@@ -233,16 +234,17 @@ ROLLOUT_STEPS = 16           # bench steps per "rollout": the episode/score stat
 
 class StatsReducer:
     """The path's only exchange: once per rollout (every ROLLOUT_STEPS steps, and once more at the
-    end of a timed region) the int64[16] statistics vector the step kernel accumulated on the device is copied out and
+    end of a timed region) the int64[AH_NSTATS] statistics vector the step kernel accumulated on the device is copied out and
     cleared (`ah_stats`, one tiny launch) and, at N > 1, summed over the ranks with one asynchronous NCCL all-reduce
-    (128 B over NVLink; NCCL's stream waits for the step kernel, the next step's kernel does not wait for NCCL).  The
+    (160 B over NVLink; NCCL's stream waits for the step kernel, the next step's kernel does not wait for NCCL).  The
     reduced vectors are accumulated so that the payload can be checked: frames == world x envs x K x steps."""
 
     def __init__(self, env, world, dev, every=ROLLOUT_STEPS):
         import torch
         self.env, self.world, self.every = env, world, every
-        self.bufs = [torch.zeros(16, dtype=torch.int64, device=dev) for _ in range(2)]
-        self.acc = torch.zeros(16, dtype=torch.int64, device=dev)
+        from air_hockey_training_environment_b200 import STAT_NAMES
+        self.bufs = [torch.zeros(len(STAT_NAMES), dtype=torch.int64, device=dev) for _ in range(2)]
+        self.acc = torch.zeros(len(STAT_NAMES), dtype=torch.int64, device=dev)
         self.pending, self.j, self.count, self.reductions = None, 0, 0, 0
 
     def _collect(self):
@@ -320,6 +322,10 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # host placement for the host-buffer (e2e) leg: cores and pinned staging memory next to this rank's GPU
+    from air_hockey_training_environment_b200.dist import bind_host_to_gpu
+    affinity0 = os.sched_getaffinity(0)
+    host_binding = bind_host_to_gpu(local, world)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n, K = args.envs_per_gpu, FRAMES_PER_STEP
@@ -328,10 +334,12 @@ def main():
     W = max(260, args.warmup)
 
     env = BatchedAirHockey(n, dtype=torch.float32, device=dev, seed=1234, env_id0=rank * n)
-    out = env.make_outputs(K, ("reward", "done", "score", "game_over", "obs_next"))
+    # the packed rollout mode: quad-major uint8 actions in, one event byte (reward, done, score, game_over) per
+    # env-frame + the next observation out (csrc/ah_step_packed.cuh)
+    out = env.make_outputs(K, ("events", "obs_next"))
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     n_act = 4                                                    # rotate several action tensors
-    acts = [torch.randint(0, 4, (K, n), dtype=torch.int8, device=dev, generator=gen) for _ in range(n_act)]
+    acts = [torch.randint(0, 4, ((K + 3) // 4, n, 4), dtype=torch.uint8, device=dev, generator=gen) for _ in range(n_act)]
     stream = torch.cuda.current_stream(dev)
     red = StatsReducer(env, world, dev)
 
@@ -419,6 +427,7 @@ def main():
         extras["ring_append_k8_cfg4"] = run_ring_append(env, dev, n, K, world)
         extras["ppo_rollout_cfg5"] = run_ppo_rollout(dev, world, rank)
     if world == 1 and not args.no_extras:
+        extras["unpacked_outputs_k8"] = run_unpacked(env, dev, n, K)
         extras["rollout_k1"] = run_rollout_k1(env, dev, n)
         extras["rollout_k1_4m"] = run_rollout_k1(None, dev, 1 << 22)
         extras["philox_sim_k8"] = run_philox_sim(env, dev, n, K)
@@ -430,7 +439,7 @@ def main():
         return
 
     hbm_peak, peak_src, sm_max = peaks()
-    bytes_per_launch = n * (2 * STATE_BYTES + 32 + K * (1 + 4 + 1 + 1 + 1))
+    bytes_per_launch = n * (2 * STATE_BYTES + 32 + K * (1 + 1))     # state in + out, obs_next, 1 action + 1 event byte per frame
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -442,7 +451,7 @@ def main():
         # per rank: one step kernel per step + one ah_stats copy kernel per rollout (every 16 steps and at the end)
         "gpu_launches": args.steps + stats_check["reductions"],
         "stats_allreduce": dict(stats_check, every_steps=ROLLOUT_STEPS,
-                                what="int64[16] episode/score statistics, summed over ranks (NCCL) once per rollout, "
+                                what="int64[20] episode/score statistics, summed over ranks (NCCL) once per rollout, "
                                      "inside the timed region; frames verified against world x envs x K x steps"),
         "clocks": clocks,
     }
@@ -456,7 +465,7 @@ def main():
         line["roofline"] = {
             "bound": "fp32", "achieved": lane_ach, "peak": lane_peak, "unit": "Glane-op/s", "frac": lane_ach / lane_peak,
             "traffic": profile_fact("dram_bytes_per_launch"),
-            "kernel": "ah::step_kernel<float, discrete, LEAN>", "kernel_ms": kernel_ms,
+            "kernel": "ah::step_packed_kernel<float>", "kernel_ms": kernel_ms,
             "kernel_ms_isolated": kernel_ms_isolated,
             "note": "K=8 fused frames: bound by FP32/ALU-pipe issue, not HBM (north_star: the slower of FP32 peak and "
                     "state bytes over HBM bandwidth). achieved = 254 algorithmic lane-ops/env-step x env-steps/s; "
@@ -469,7 +478,9 @@ def main():
             "hbm_peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
             "bytes_per_env_step": bytes_per_launch / (n * K),
         }
+    line["host_binding"] = host_binding
     if not args.no_cpu_baseline and world == 1:
+        os.sched_setaffinity(0, affinity0)                       # the CPU baseline gets every host core
         line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
     if extras:
         line["extras"] = extras
@@ -566,6 +577,18 @@ def run_ring_append(env, dev, n, K, world=1):
                          "per": "GPU", "traffic": None, "algorithmic_bytes_per_launch": b, "bytes_per_env_step": b / (n * K)}}
 
 
+def run_unpacked(env, dev, n, K):
+    """The same K = 8 launch with the per-frame outputs as four separate tensors (reward f32, done u8, score i8, game_over
+    u8, [K, n] each) and time-major int8 actions -- round 1's headline kernel (ah::step_kernel<float, 1, LEAN>), kept as
+    the reference point for the packed mode."""
+    import torch
+    out = env.make_outputs(K, ("reward", "done", "score", "game_over", "obs_next"))
+    acts = [torch.randint(0, 4, (K, n), dtype=torch.int8, device=dev) for _ in range(4)]
+    ms = _time_loop(dev, lambda i: env.step(acts[i % 4], K=K, out=out), 10, 100)
+    return {"value": n * K / (ms * 1e-3), "unit": UNIT, "kernel_ms": ms,
+            "lane_op_roofline_frac": LANE_OPS_PER_ENV_STEP * n * K / (ms * 1e-3) / (148 * 128 * peaks()[2] * 1e6)}
+
+
 def run_philox_sim(env, dev, n, K):
     """Pure simulation: actions drawn in-kernel (Philox), only the final observation written."""
     out = env.make_outputs(K, ("obs_next",))
@@ -619,16 +642,18 @@ def run_fp64(dev):
 
 
 def run_e2e(env, dev, n, K, warm, steps, world):
-    """The public HOST-buffer API (air_hockey_training_environment_b200.host.HostStepper): per step, H2D of the int8
-    [K,n] actions from pinned host memory, the fused step, the lossless compact packing of (reward, done, next
-    observation) and its D2H into pinned host memory -- all inside the timed region; 3 slots / 3 streams so the
-    copies overlap the kernels.  Every result is waited for on the host before its slot is reused."""
+    """The public HOST-buffer API (air_hockey_training_environment_b200.host.HostStepper): per step, H2D of the uint8
+    quad-major actions from pinned host memory, the fused packed step, and D2H of the step's results (one event byte per
+    env-frame = reward, done, score, game_over; the next observation as 4 x int16 + 4 x f32) into pinned host memory --
+    all inside the timed region; 3 slots / 3 streams so the copies overlap the kernels.  Every result is waited for on
+    the host before its slot is reused.  Its roofline is the host link: the same copies WITHOUT the kernels, on the same
+    streams and buffers, concurrently on every rank (`roofline.peak`)."""
     import torch
     import torch.distributed as dist
     from air_hockey_training_environment_b200.host import HostStepper
     slots = 3
     st = HostStepper(env, K=K, slots=slots)
-    h_act = [torch.randint(0, 4, (K, n), dtype=torch.int8).pin_memory() for _ in range(slots)]
+    h_act = [torch.randint(0, 4, ((K + 3) // 4, n, 4), dtype=torch.uint8).pin_memory() for _ in range(slots)]
 
     def run(count):
         inflight = []
@@ -639,27 +664,48 @@ def run_e2e(env, dev, n, K, warm, steps, world):
         for r in inflight:
             r.wait()
 
+    def copies_only(count):
+        for i in range(count):
+            s = i % slots
+            with torch.cuda.stream(st.s_in):
+                st.d_act[s].copy_(h_act[s], non_blocking=True)
+            with torch.cuda.stream(st.s_out):
+                st.h[s].events.copy_(st.outs[s].events, non_blocking=True)
+                st.h[s].obs_pos.copy_(st.d_pos[s], non_blocking=True)
+                st.h[s].obs_vel.copy_(st.d_vel[s], non_blocking=True)
+
     def sync():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    def timed(fn, count):
+        sync()
+        t0 = time.perf_counter()
+        fn(count)
+        sync()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return dt
+
     run(warm)
-    sync()
-    t0 = time.perf_counter()
-    run(steps)
-    sync()
-    dt = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([dt], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
+    dt = timed(run, steps)
+    copies_only(warm)
+    dt_copy = timed(copies_only, steps)
     last = st.h[(steps - 1) % slots]
-    checksum = int(last.reward.sum()) + int(last.done.sum())     # the host really holds decodable results
+    checksum = int(last.reward.sum(dtype=torch.int64)) + int(last.done.sum())     # the host really holds decodable results
+    per_step = st.h2d_bytes_per_step + st.d2h_bytes_per_step
     return {"value": world * n * K * steps / dt, "unit": UNIT, "h2d_bytes_per_step": st.h2d_bytes_per_step,
             "d2h_bytes_per_step": st.d2h_bytes_per_step, "steps": steps, "host_checksum_last_step": checksum,
-            "note": "HostStepper: pinned host actions in; reward+done (1 B/frame/env) and the next observation (4 x int16 + "
-                    "4 x f32 per env) out, lossless; 3 slots / 3 streams; host clock around barrier + synchronize; PCIe-bound"}
+            "roofline": {"bound": "pcie", "unit": "GB/s (H2D + D2H, whole job)", "achieved": world * per_step * steps / dt / 1e9,
+                         "peak": world * per_step * steps / dt_copy / 1e9, "frac": dt_copy / dt,
+                         "peak_source": "measured in this run: the same pinned copies on the same streams without the kernels, "
+                                        "all ranks concurrently"},
+            "note": "HostStepper: pinned host actions in (1 B/frame/env); event byte (1 B/frame/env) and the next observation "
+                    "(4 x int16 + 4 x f32 per env) out, lossless; 3 slots / 3 streams; host clock around barrier + synchronize"}
 
 
 if __name__ == "__main__":

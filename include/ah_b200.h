@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define AH_ABI_VERSION 1
+#define AH_ABI_VERSION 2
 #define AH_ACTOR_NWEIGHTS 114   /* W1[4][8] b1[4] W2[6][4] b2[6] W3[4][6] b3[4] W4[4][4] b4[4], see ah_actor_sample */
 
 typedef struct ah_env ah_env;
@@ -69,10 +69,23 @@ enum {
     AH_ACT_PHILOX = 3,       /* uniform {0,1,2,3} drawn in-kernel (synthetic random-action workload)     */
     AH_ACT_DISCRETE_REPEAT = 4,   /* int8 [n]: one action applied to all K frames (frame-skip)            */
     AH_ACT_CONTINUOUS_REPEAT = 5, /* real [n][2]: one action applied to all K frames                      */
-    AH_ACT_POLICY = 6        /* closed loop: every frame the reference's discrete PPO actor is evaluated IN the  */
+    AH_ACT_POLICY = 6,       /* closed loop: every frame the reference's discrete PPO actor is evaluated IN the  */
                              /* kernel on the env's current observation and an action is sampled from its       */
                              /* softmax (see ah_actor_sample); `actions` = device float[AH_ACTOR_NWEIGHTS]       */
+    AH_ACT_DISCRETE_PACKED4 = 7 /* uint8 [ceil(K/4)][n][4], "quad-major": byte j of word (q, i) is env i's action of */
+                             /* frame 4q + j (same action codes as AH_ACT_DISCRETE; 32-bit aligned).  The input     */
+                             /* format of the packed rollout mode (ah_step_io.events)                               */
 };
+
+/* One byte per env-frame carrying everything a frame of Game.play returns (ah_step_io.events):
+ *   bits 0-2  (reward + 4) / 2    reward in {-4,-2,0,2,4,6}      lib/rewards.py:118-142
+ *   bit  3    done                "mallet overlaps puck"          rewards.py:86-89,124
+ *   bits 4-5  score + 1           -1 / 0 / +1                     rewards.py:64-81
+ *   bits 6-7  game_over           0 / 1 robot won / 2 opponent    game.py:101-109,169-177 */
+#define AH_EVENT_REWARD(b)    ((int)(((b) & 7u) << 1) - 4)
+#define AH_EVENT_DONE(b)      ((int)(((b) >> 3) & 1u))
+#define AH_EVENT_SCORE(b)     ((int)(((b) >> 4) & 3u) - 1)
+#define AH_EVENT_GAME_OVER(b) ((int)(((b) >> 6) & 3u))
 
 /* indices into the statistics vector (int64[AH_NSTATS]); the device-side equivalent of the per-frame
  * scores.csv row (game.py:82-112) and of the rewards CSV (lib/rewards.py:129-140) */
@@ -93,7 +106,11 @@ enum {
     AH_STAT_RESET_TABLE_OVERFLOW = 13, /* resets that found their reset table exhausted (velocity set to 0) */
     AH_STAT_CONTACTS_ROBOT = 14,  /* AirHockey.collision() returned True, robot mallet (airhockey.py:189-268) */
     AH_STAT_CONTACTS_OPPONENT = 15,
-    AH_NSTATS = 16
+    AH_STAT_DONE_AMBIGUOUS = 16,  /* AH_F64 only: frames whose `done` test sqrt(dx**2 + dy**2) < 35 (puck.py:138) had its   */
+                                  /* sum of squares within 1e-9 of 1225 with an inexact square -- the only frames where libm */
+                                  /* pow(x, 2) (the reference) and x*x (the device) could decide differently; 0 proves `done` */
+                                  /* exact for the run                                                                     */
+    AH_NSTATS = 20                /* 17-19 reserved */
 };
 
 /* ---- configuration (flags only; the physical constants of environment/config.py are compile-time) ---- */
@@ -115,6 +132,9 @@ typedef struct ah_ring {
     void* reward;       /* real   [capacity][n] */
     uint8_t* done;      /* uint8  [capacity][n] */
     int64_t capacity;
+    uint64_t* appended; /* device uint64[1], owned by the ring: Observation tuples appended so far.  The step kernel   */
+                        /* reads the write slot from it and advances it (so captured graphs advance it too);          */
+                        /* MemoryBuffer.purge (lib/buffer.py:52-61) = set it to 0                                     */
 } ah_ring;
 
 /* ---- inputs / outputs of the fused step ---- */
@@ -140,6 +160,17 @@ typedef struct ah_step_io {
     /* the actions actually applied and, for AH_ACT_POLICY, the actor's distribution (PPO's old_prediction) */
     int8_t* actions_out;          /* i8   [K][n], nullable (discrete / Philox / policy actions) */
     void* probs_out;              /* real [K][n][4], nullable (AH_ACT_POLICY only) */
+    /* PACKED rollout mode: all four per-frame outputs in one byte per env-frame (AH_EVENT_*), quad-major like the
+     * actions: u8 [ceil(K/4)][n][4], 32-bit aligned.  Requires action_kind == AH_ACT_DISCRETE_PACKED4 and excludes the
+     * other per-frame outputs (reward, done, score, game_over, obs_state, obs_new_state, per-frame obs_next, ring,
+     * actions_out, probs_out) and the friction flag; obs_next [n][8] stays available. */
+    uint8_t* events;
+    /* Sub-range launch (packed mode only): step only the envs [env_first, env_first + env_count) of the bound arrays;
+     * env_count == 0 means all n.  Array shapes and strides stay those of the full n, so a caller can split one step
+     * into disjoint ranges on DIFFERENT streams: the tail of one range's launch then overlaps the head of the next
+     * range's (host.InterleavedStepper).  The frame counter advances with the range that contains env 0. */
+    int64_t env_first;
+    int64_t env_count;
 } ah_step_io;
 
 const char* ah_strerror(int code);
@@ -198,17 +229,30 @@ int ah_actor_sample(ah_env* env, const float* d_weights, const void* d_obs, void
  *   events   u8    [K][n]   low nibble = reward + 4, bit 4 = done
  *   obs_pos  int16 [n][4]   the int()-truncated agent / puck locations of the observation (airhockey.py:136-147)
  *   obs_vel  f32   [n][4]   agent / puck velocities, rounded to binary32
- * 33 bytes instead of 72 per env for K = 8. */
+ * 33 bytes instead of 72 per env for K = 8.  d_reward, d_done and d_events may all be NULL: only the observation is
+ * packed then (the packed rollout mode already produces its per-frame results as one byte, ah_step_io.events). */
 int ah_pack_host(ah_env* env, int K, const void* d_reward, const uint8_t* d_done, const void* d_obs_next,
                  uint8_t* d_events, int16_t* d_obs_pos, float* d_obs_vel, void* stream);
 
 /* Copy the int64[AH_NSTATS] statistics block to a caller device buffer, optionally clearing it. */
 int ah_stats(ah_env* env, int64_t* d_out, int clear, void* stream);
 
-/* Global frame counter (Philox action index) and ring append counter, kept on the device so that captured
- * graphs advance them; get copies {frame, ring_appended} (uint64[2]) to a caller device buffer. */
-int ah_set_counters(ah_env* env, uint64_t frame, uint64_t ring_appended, void* stream);
-int ah_get_counters(ah_env* env, uint64_t* d_out2, void* stream);
+/* Global frame counter (Philox action / sampling index), kept on the device so that captured graphs advance it;
+ * get copies it (uint64[1]) to a caller device buffer.  (The ring's append counter lives in the ring: ah_ring.appended.) */
+int ah_set_counters(ah_env* env, uint64_t frame, void* stream);
+int ah_get_counters(ah_env* env, uint64_t* d_out1, void* stream);
+
+/* MemoryBuffer.sample(batch) (lib/buffer.py:47-50: random.sample, i.e. WITHOUT replacement) on the device, in one
+ * kernel and without materialising a permutation: sample s is entry pi(s) of the population of
+ * min(*ring->appended, capacity) x n Observation tuples, where pi is a keyed bijection of [0, population) (a 6-round
+ * Feistel network over the next even power of two, cycle-walked; round keys from Philox4x32-10 keyed on the env's seed
+ * with counter `draw`) -- so the `batch` samples are distinct, and a different `draw` gives a different sample.
+ * Entry f = age * n + env, age 0 = the newest tuple (the order of appendleft + retreive, lib/buffer.py:27,45).
+ * Outputs (device, caller-owned): state / new_state real [batch][8], action int8 [batch] (or real [batch][2] for a
+ * continuous ring), reward real [batch], done u8 [batch], index int64 [batch] = f (nullable).  batch must not exceed
+ * the population (the reference raises ValueError); entries beyond it wrap around. */
+int ah_ring_sample(ah_env* env, const ah_ring* ring, int continuous, int64_t batch, uint64_t draw, void* d_state,
+                   void* d_action, void* d_reward, uint8_t* d_done, void* d_new_state, int64_t* d_index, void* stream);
 
 /* Launch geometry actually used by ah_step (for reports): blocks, threads per block, SM count. */
 int ah_launch_info(const ah_env* env, int* blocks, int* threads, int* sms);

@@ -273,7 +273,7 @@ static void get_state(const env_t* e, int agent_is_robot, double* obs8) {
 }
 
 /* ------------------------------------------------------------------ lib/rewards.py:118-142 (agent "robot") */
-static void rewards_call(env_t* e, int dot_fma, int* reward, int* score, int* done) {
+static void rewards_call(env_t* e, int dot_fma, int* reward, int* score, int* done, int* ambiguous) {
     const body_t* p = &e->puck;
     const body_t* m = &e->robot;
     int sc = 0;
@@ -283,6 +283,16 @@ static void rewards_call(env_t* e, int dot_fma, int* reward, int* score, int* do
     /* compute_mallet_hit_puck, rewards.py:83-89 with Puck.__and__, puck.py:135-146 (`** 2` is libm pow) */
     double ex = p->x - m->x, ey = p->y - m->y;
     double distance = sqrt(pow(ex, 2.0) + pow(ey, 2.0));
+    /* The device evaluates `** 2` as x*x.  pow(x, 2) is within an ulp of x*x, so the two can only decide `done`
+     * differently when the sum of squares is within a few ulps (5e-13) of 1225.  ambiguous[0]: frames inside the
+     * (far wider) band 1e-9 the device counts as AH_STAT_DONE_AMBIGUOUS; ambiguous[1]: frames where the two
+     * evaluations actually disagree. */
+    if (ambiguous) {
+        const double ssq = ex * ex + ey * ey;
+        /* (exactly representable squares are exact under pow too: only inexact ones can differ) */
+        ambiguous[0] += fabs(ssq - 1225.0) < 1e-9 && (fma(ex, ex, -(ex * ex)) != 0.0 || fma(ey, ey, -(ey * ey)) != 0.0);
+        ambiguous[1] += (sqrt(ssq) < PUCK_R + MALLET_R) != (distance < PUCK_R + MALLET_R);
+    }
     int rw, dn;
     if (distance < PUCK_R + MALLET_R) { rw = 3; dn = 1; } else { rw = -1; dn = 0; }
     /* compute_wall_reward, rewards.py:45-62 with puck.py:148-164 */
@@ -404,11 +414,11 @@ int orc_frames(int64_t n, int T, double* state13, int32_t* scores2,
                int dot_fma, int friction, int record_every, int nthreads,
                const orc_outputs_t* out) {
     int overflow = 0;
-    int64_t stats_acc[16];
+    int64_t stats_acc[20];
     memset(stats_acc, 0, sizeof stats_acc);
 #ifdef _OPENMP
     if (nthreads > 0) omp_set_num_threads(nthreads);
-#pragma omp parallel for schedule(static) reduction(| : overflow) reduction(+ : stats_acc[:16])
+#pragma omp parallel for schedule(static) reduction(| : overflow) reduction(+ : stats_acc[:20])
 #endif
     for (int64_t i = 0; i < n; ++i) {
         env_t e;
@@ -427,8 +437,8 @@ int orc_frames(int64_t n, int T, double* state13, int32_t* scores2,
             if (out->obs_state) get_state(&e, 1, out->obs_state + 8 * o); /* state                agent.py:61 */
             update_state_c(&e, 0, kind, ia, ax, ay, dot_fma, friction, cts, &dmin);   /* self.move(a)   agent.py:64 */
             if (out->obs_new_state) get_state(&e, 1, out->obs_new_state + 8 * o);   /*            agent.py:67 */
-            int rw, sc, dn;
-            rewards_call(&e, dot_fma, &rw, &sc, &dn);                     /*                      agent.py:71 */
+            int rw, sc, dn, amb[2] = {0, 0};
+            rewards_call(&e, dot_fma, &rw, &sc, &dn, amb);                /*                      agent.py:71 */
             if (sc > 0) { e.robot_score += 1; env_reset(&e, 0, &rs); }    /* update_score     airhockey.py:152-158 */
             if (sc < 0) { e.opp_score += 1; env_reset(&e, 0, &rs); }      /*                  airhockey.py:161-168 */
             int go = 0;                                                   /* stats()             game.py:101-109 */
@@ -454,6 +464,8 @@ int orc_frames(int64_t n, int T, double* state13, int32_t* scores2,
             stats_acc[5] += dn;                /* dones */
             stats_acc[6] += rw;                /* sum reward */
             stats_acc[7] += (int64_t)rw * rw;  /* sum reward^2 */
+            stats_acc[16] += amb[0];           /* `done` within the pow-vs-multiply ambiguity band */
+            stats_acc[17] += amb[1];           /* `done` by libm pow != `done` by x*x */
             if (record_every > 0 && (t + 1) % record_every == 0) {
                 size_t r = (size_t)((t + 1) / record_every - 1) * n + i;
                 if (out->states_rec) { int32_t tmp[2]; store_env(&e, out->states_rec + 13 * r, out->scores_rec ? out->scores_rec + 2 * r : tmp); }
@@ -463,7 +475,7 @@ int orc_frames(int64_t n, int T, double* state13, int32_t* scores2,
         reset_cursor[i] = rs.cursor;
         overflow |= rs.overflow;
     }
-    if (out->stats) for (int k = 0; k < 16; ++k) out->stats[k] += stats_acc[k];
+    if (out->stats) for (int k = 0; k < 20; ++k) out->stats[k] += stats_acc[k];
     return overflow;
 }
 

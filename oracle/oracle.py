@@ -19,7 +19,8 @@ _lib = None
 DOT_FMA_DEFAULT = 1
 
 STAT_NAMES = ("frames", "robot_goals", "opponent_goals", "robot_wins", "opponent_wins", "dones",
-              "reward_sum", "reward_sq_sum", "_8", "_9", "_10", "_11", "_12", "_13", "contacts_robot", "contacts_opponent")
+              "reward_sum", "reward_sq_sum", "_8", "_9", "_10", "_11", "_12", "_13", "contacts_robot", "contacts_opponent",
+              "done_ambiguous", "done_pow_vs_mul_disagree", "_18", "_19")
 
 
 class _Outputs(C.Structure):
@@ -117,7 +118,7 @@ def run_frames(state: np.ndarray, scores: np.ndarray, T: int, *,
     if record_every:
         out["states_rec"] = np.zeros((T // record_every, n, 13), np.float64)
         out["scores_rec"] = np.zeros((T // record_every, n, 2), np.int32)
-    out["stats"] = np.zeros(16, np.int64)
+    out["stats"] = np.zeros(20, np.int64)
     o = _Outputs(**{k: _p(out.get(k)) for k, _ in _Outputs._fields_})
     rc = lib().orc_frames(n, T, _p(state), _p(scores), _p(a_i8), _p(a_f64), _p(reset_table), R,
                           _p(reset_cursor), seed, env_id0, frame0, int(dot_fma), int(friction),

@@ -37,17 +37,17 @@ def test_every_declared_symbol_is_exported_and_bound():
 
 def test_abi_version_and_strerror():
     lib = _capi.lib()
-    assert lib.ah_abi_version() == 1
+    assert lib.ah_abi_version() == 2
     assert _capi.strerror(_capi.AH_OK) == "ok"
     assert "agent" in _capi.strerror(_capi.AH_EAGENT)
     assert "CUDA" in _capi.strerror(_capi.AH_ECUDA)
 
 
 def test_struct_layouts_match_header():
-    # sizes the C side assumes (LP64): ah_config 32 B, ah_ring 48 B, ah_step_io 112 B
+    # sizes the C side assumes (LP64): ah_config 32 B, ah_ring 56 B, ah_step_io 136 B
     assert C.sizeof(_capi.AhConfig) == 32
-    assert C.sizeof(_capi.AhRing) == 48
-    assert C.sizeof(_capi.AhStepIO) == 112
+    assert C.sizeof(_capi.AhRing) == 56
+    assert C.sizeof(_capi.AhStepIO) == 136
 
 
 def test_argument_validation_needs_no_gpu():

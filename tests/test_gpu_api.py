@@ -180,32 +180,7 @@ def test_friction_flag_changes_trajectories_only_when_enabled():
     assert same(snapshot(a), snapshot(b)) and not same(snapshot(a), snapshot(c))
 
 
-# ---------------------------------------------------------------- fused ring buffer (lib/buffer.py)
-def test_ring_append_matches_step_outputs_and_wraps():
-    from air_hockey_training_environment_b200 import ReplayRing
-    n, cap = 256, 6
-    env = make_env(n, seed=4)
-    ring = ReplayRing(cap, n, env.dtype, env.device)
-    assert len(ring) == 0
-    hist = []
-    for _ in range(4):                                   # 4 launches x 2 frames = 8 appends into 6 slots
-        acts = torch.randint(0, 4, (2, n), dtype=torch.int8, device=env.device)
-        out = env.step(acts, K=2, out=env.make_outputs(2, ("obs_state", "obs_new_state", "reward", "done")), ring=ring)
-        for k in range(2):
-            hist.append((out.obs_state[k].clone(), acts[k].clone(), out.reward[k].clone(), out.done[k].clone(),
-                         out.obs_new_state[k].clone()))
-    assert len(ring) == cap and ring.appended == 8 and env.counters()["ring_appended"] == 8
-    got = ring.retreive()                                # newest first, like MemoryBuffer.retreive()
-    for j in range(cap):
-        s, a, r, d, s2 = hist[-1 - j]
-        assert torch.equal(got["state"][j], s) and torch.equal(got["new_state"][j], s2)
-        assert torch.equal(got["action"][j], a) and torch.equal(got["reward"][j], r) and torch.equal(got["done"][j], d)
-    batch = ring.sample(100)
-    assert batch["state"].shape == (100, 8) and batch["action"].shape == (100,)
-    with pytest.raises(ValueError):
-        ring.sample(cap * n + 1)                         # random.sample raises ValueError too
-    ring.purge()
-    assert len(ring) == 0
+# (the fused ring buffer, lib/buffer.py, has its own file: tests/test_gpu_ring.py)
 
 
 # ---------------------------------------------------------------- CUDA graph capture
@@ -264,27 +239,33 @@ def test_full_size_properties_1m_envs_fp32_k8():
 
 
 # ---------------------------------------------------------------- host-buffer front end
-def test_host_stepper_round_trip_is_lossless():
+@pytest.mark.parametrize("K", [8, 6])
+def test_host_stepper_round_trip_is_lossless(K):
     from air_hockey_training_environment_b200.host import HostStepper
-    n, K = 8192, 8
+    n = 8192
     env, twin = make_env(n, seed=31), make_env(n, seed=31)
     for e in (env, twin):
-        e.step(None, K=300, out=e.make_outputs(300, ()))              # decorrelate, get some dones / goals
-    st = HostStepper(env, K=K, slots=3)
-    acts = [torch.randint(0, 4, (K, n), dtype=torch.int8).pin_memory() for _ in range(5)]
+        e.step(None, K=300, out=e.make_outputs(300, ()))              # decorrelate, get some dones / goals (caller's stream:
+    st = HostStepper(env, K=K, slots=3)                               #  submit() orders itself after it)
+    acts = [torch.randint(0, 4, (K, n), dtype=torch.int8) for _ in range(5)]
     results = []
     for a in acts:
-        r = st.submit(a).wait()
-        results.append((r.reward.clone(), r.done.clone(), r.obs.clone()))
-    st.drain()
+        r = st.submit(HostStepper.pack_actions_host(a)).wait()
+        results.append((r.reward.clone(), r.done.clone(), r.score.clone(), r.game_over.clone(), r.obs.clone()))
+    st.join()                                                         # env state / stats are read on the caller's stream
     dones = 0
-    for a, (rw, dn, ob) in zip(acts, results):
+    for a, (rw, dn, sc, go, ob) in zip(acts, results):
         out = twin.step(a.cuda(), K=K)
         assert torch.equal(rw.float(), out.reward.cpu()) and torch.equal(dn, out.done.cpu().bool())
+        assert torch.equal(sc, out.score.cpu()) and torch.equal(go, out.game_over.cpu())
         assert torch.equal(ob, out.obs_next.cpu())
         dones += int(dn.sum())
-    assert st.d2h_bytes_per_step == n * (K + 8 + 16) and st.h2d_bytes_per_step == n * K
+    assert same(snapshot(env), snapshot(twin)) and env.stats() == twin.stats()
+    q = (K + 3) // 4
+    assert st.d2h_bytes_per_step == n * (4 * q + 8 + 16) and st.h2d_bytes_per_step == n * 4 * q
     assert dones > 0
+    with pytest.raises(ValueError):
+        st.submit(acts[0])                                            # time-major int8 is not the wire format
 
 
 # ---------------------------------------------------------------- the HBM-bound small-K variant (persistent grid + prefetch)
@@ -390,8 +371,9 @@ def test_guard_bands_survive_every_kernel(dtype):
     ring.state, ring.new_state = carve((3, n, 8), dtype), carve((3, n, 8), dtype)
     ring.action, ring.reward, ring.done = carve((3, n), torch.int8), carve((3, n), dtype), carve((3, n), torch.uint8)
     from air_hockey_training_environment_b200 import _capi
+    ring.counter = carve((1,), torch.int64, ring.counter)
     ring._c = _capi.AhRing(ring.state.data_ptr(), ring.new_state.data_ptr(), ring.action.data_ptr(), ring.reward.data_ptr(),
-                           ring.done.data_ptr(), 3)
+                           ring.done.data_ptr(), 3, ring.counter.data_ptr())
     acts = torch.randint(0, 4, (K, n), dtype=torch.int8, device=dev)
     for _ in range(40):
         env.step(acts, K=K, out=out, ring=ring)                                   # GENERIC
@@ -404,11 +386,17 @@ def test_guard_bands_survive_every_kernel(dtype):
     pw = torch.randn(114, device=dev) * 0.1
     pol = StepOutputs(reward=out.reward, done=out.done, obs_next=out.obs_next, actions=out.actions, probs=carve((K, n, 4), dtype))
     env.step(None, K=K, out=pol, policy_weights=pw)                               # in-kernel policy
+    from air_hockey_training_environment_b200.env import pack_actions
+    packed = StepOutputs(events=carve(((K + 3) // 4, n, 4), torch.uint8), obs_next=lean.obs_next)
+    env.step(carve(((K + 3) // 4, n, 4), torch.uint8, pack_actions(acts)), K=K, out=packed)   # PACKED (partial last quad)
+    smp = {"state": carve((500, 8), dtype), "new_state": carve((500, 8), dtype), "action": carve((500,), torch.int8),
+           "reward": carve((500,), dtype), "done": carve((500,), torch.uint8), "index": carve((500,), torch.int64)}
+    ring.sample(500, env, out=smp)                                                # ring sampler
     torch.cuda.synchronize()
     for raw, pad, numel in guards:
         assert bool((raw[:pad] == 77).all()) and bool((raw[pad + numel:] == 77).all()), "guard band overwritten"
     assert not bool((out.reward == 77).any()) and not bool((pol.probs == 77).any())    # interiors were written
-    assert env.stats()["frames"] == n * K * 43 and env.stats()["nonfinite"] == 0
+    assert env.stats()["frames"] == n * K * 44 and env.stats()["nonfinite"] == 0
 
 
 def test_8m_envs_on_one_gpu():
