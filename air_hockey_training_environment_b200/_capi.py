@@ -23,7 +23,7 @@ STAT_NAMES = ("frames", "robot_goals", "opponent_goals", "robot_wins", "opponent
 
 # every symbol include/ah_b200.h declares (tests/test_capi_symbols.py checks header <-> library <-> this list)
 SYMBOLS = ("ah_strerror", "ah_abi_version", "ah_last_cuda_error", "ah_create", "ah_destroy", "ah_bind_state",
-           "ah_init_state", "ah_reset", "ah_update_state", "ah_get_state", "ah_update_score", "ah_rewards", "ah_step", "ah_pack_host", "ah_actor_sample", "ah_stats",
+           "ah_init_state", "ah_reset", "ah_update_state", "ah_get_state", "ah_update_score", "ah_rewards", "ah_step", "ah_pack_host", "ah_actor_sample", "ah_stats", "ah_stats_bank",
            "ah_set_counters", "ah_get_counters", "ah_ring_sample", "ah_launch_info", "ah_selftest_nofma")
 
 
@@ -43,7 +43,8 @@ class AhStepIO(C.Structure):
                 ("done", C.c_void_p), ("score", C.c_void_p), ("game_over", C.c_void_p),
                 ("obs_next", C.c_void_p), ("obs_next_per_frame", C.c_int32), ("collect_stats", C.c_int32),
                 ("ring", C.POINTER(AhRing)), ("actions_out", C.c_void_p), ("probs_out", C.c_void_p),
-                ("events", C.c_void_p), ("env_first", C.c_int64), ("env_count", C.c_int64)]
+                ("events", C.c_void_p), ("env_first", C.c_int64), ("env_count", C.c_int64),
+                ("stats_bank", C.c_int32), ("reserved0", C.c_int32)]
 
 
 class AhError(RuntimeError):
@@ -101,6 +102,8 @@ def lib() -> C.CDLL:
     L.ah_actor_sample.argtypes = [vp, vp, vp, vp, vp, i32, vp]
     L.ah_stats.restype = i32
     L.ah_stats.argtypes = [vp, vp, i32, vp]
+    L.ah_stats_bank.restype = i32
+    L.ah_stats_bank.argtypes = [vp, i32, vp, i32, vp]
     L.ah_set_counters.restype = i32
     L.ah_set_counters.argtypes = [vp, u64, vp]
     L.ah_get_counters.restype = i32

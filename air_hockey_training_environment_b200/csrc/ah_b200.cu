@@ -23,13 +23,13 @@ namespace ah {
 
 // ------------------------------------------------------------------------------------------------ device block
 struct DevBlock {
-    unsigned long long stats[AH_NSTATS];   // AH_STAT_*
+    unsigned long long stats[2][AH_NSTATS];   // AH_STAT_*, two banks (ah_step_io.stats_bank)
     unsigned long long frame;              // global frame counter (Philox action index)
     unsigned long long reserved;
     unsigned int ticket;                   // last-block-done detection
-    unsigned int pad[19];
+    unsigned int pad[43];
 };
-static_assert(sizeof(DevBlock) == 256, "DevBlock is 256 bytes");
+static_assert(sizeof(DevBlock) == 512, "DevBlock is 512 bytes");
 
 template <typename R> struct Vec4T;
 template <> struct Vec4T<float> { using type = float4; };
@@ -140,6 +140,7 @@ struct StepArgs {
     unsigned long long* ring_appended;     // the ring's own device counter (ah_ring.appended)
     int dot_fma, friction;
     DevBlock* blk;
+    int stats_bank;
     int8_t* actions_out; R* probs_out;     // GENERIC mode: the actions applied / the in-kernel actor's distribution
 };
 
@@ -169,7 +170,7 @@ __device__ __forceinline__ void stat_add(BlockStats& bs, int which, int x) {
 // ring append): those may only advance once EVERY block is done (fence + ticket).  Kernels that never read them
 // (the packed mode) let block 0 advance the frame counter: launches on a stream are serialised, so nobody races it.
 template <bool ORDERED = true>
-__device__ __forceinline__ void finish_stats(BlockStats& bs, DevBlock* blk, int collect_stats, int frames, int reward_sum,
+__device__ __forceinline__ void finish_stats(BlockStats& bs, DevBlock* blk, int bank, int collect_stats, int frames, int reward_sum,
                                              int reward_sq, int dones, int contacts_r, int contacts_o, int overflow, int bad,
                                              int ambiguous, int K, unsigned long long* ring_appended) {
     const int fs = __reduce_add_sync(0xffffffffu, frames);
@@ -205,7 +206,7 @@ __device__ __forceinline__ void finish_stats(BlockStats& bs, DevBlock* blk, int 
     if (collect_stats && lane < AH_NSTATS) {                    // lane q flushes statistic q
         const long long sv = lane == AH_STAT_GAME_LEN_SQ_SUM ? (long long)*(volatile unsigned long long*)&bs.len_sq
                                                              : (long long)*(volatile int*)&bs.v[lane];
-        if (sv != 0) atomicAdd(&blk->stats[lane], (unsigned long long)sv);
+        if (sv != 0) atomicAdd(&blk->stats[bank][lane], (unsigned long long)sv);
     }
     if (lane != 0) return;
     if (!ORDERED) {
@@ -482,7 +483,7 @@ step_kernel(const StepArgs<R> a) {
         if (PF) { raw = raw_next; ia_pf = ia_pf_next; }
     }
 
-    finish_stats(bs, a.blk, a.collect_stats, frames, reward_sum, reward_sq, dones, contacts_r, contacts_o, (int)overflow, bad, amb, K,
+    finish_stats(bs, a.blk, a.stats_bank, a.collect_stats, frames, reward_sum, reward_sq, dones, contacts_r, contacts_o, (int)overflow, bad, amb, K,
                  a.ring_capacity > 0 ? a.ring_appended : nullptr);
 }
 
@@ -514,7 +515,7 @@ __global__ void reset_kernel(StatePtrs<R> st, int64_t n, int total, const uint8_
     env_reset<R>(e, total != 0, rs, i, overflow);
     if (total) { e.game_frames = 0; e.game_return = 0; }
     store_env<R>(st, i, e);
-    if (overflow) atomicAdd(&blk->stats[AH_STAT_RESET_TABLE_OVERFLOW], 1ull);
+    if (overflow) atomicAdd(&blk->stats[0][AH_STAT_RESET_TABLE_OVERFLOW], 1ull);
 }
 
 // AirHockey.update_state  airhockey.py:96-134 : one sub-update
@@ -568,7 +569,7 @@ __global__ void update_score_kernel(StatePtrs<R> st, int64_t n, const int8_t* sc
     if (sc > 0) e.robot_score += 1; else e.opp_score += 1;
     env_reset<R>(e, false, rs, i, overflow);
     store_env<R>(st, i, e);
-    if (overflow) atomicAdd(&blk->stats[AH_STAT_RESET_TABLE_OVERFLOW], 1ull);
+    if (overflow) atomicAdd(&blk->stats[0][AH_STAT_RESET_TABLE_OVERFLOW], 1ull);
 }
 
 // Rewards.__call__  lib/rewards.py:118-142
@@ -630,11 +631,11 @@ __global__ void pack_host_kernel(int64_t n, int K, const R* __restrict__ reward,
     vel[i] = make_float4((float)o[4], (float)o[5], (float)o[6], (float)o[7]);
 }
 
-__global__ void stats_copy_kernel(DevBlock* blk, int64_t* out, int clear) {
+__global__ void stats_copy_kernel(DevBlock* blk, int bank, int64_t* out, int clear) {
     const int q = threadIdx.x;
     if (q < AH_NSTATS) {
-        out[q] = (int64_t)blk->stats[q];
-        if (clear) blk->stats[q] = 0ull;
+        out[q] = (int64_t)blk->stats[bank][q];
+        if (clear) blk->stats[bank][q] = 0ull;
     }
 }
 
@@ -768,7 +769,7 @@ int launch_step(ah_env* env, const ah_step_io* io, int K, cudaStream_t s) {
         a.ring_reward = (R*)io->ring->reward; a.ring_done = io->ring->done; a.ring_capacity = io->ring->capacity;
         a.ring_appended = reinterpret_cast<unsigned long long*>(io->ring->appended);
     }
-    a.dot_fma = env->cfg.dot_fma; a.friction = env->cfg.friction; a.blk = env->blk;
+    a.dot_fma = env->cfg.dot_fma; a.friction = env->cfg.friction; a.blk = env->blk; a.stats_bank = io->stats_bank;
     a.actions_out = io->actions_out; a.probs_out = (R*)io->probs_out;
     const int max_blocks = sizeof(R) == 4 ? env->blocks_f32 : env->blocks_f64;
     // block size: 256 threads, halved (down to 64) while the grid would leave SMs unevenly filled (< 4 blocks per SM):
@@ -782,7 +783,7 @@ int launch_step(ah_env* env, const ah_step_io* io, int K, cudaStream_t s) {
         memset(&p, 0, sizeof p);
         p.st = a.st; p.n = env->n; p.K = K;
         p.actions = reinterpret_cast<const uint32_t*>(io->actions); p.events = reinterpret_cast<uint32_t*>(io->events);
-        p.obs_next = (R*)io->obs_next; p.rs = a.rs; p.collect_stats = io->collect_stats; p.dot_fma = env->cfg.dot_fma; p.blk = env->blk;
+        p.obs_next = (R*)io->obs_next; p.rs = a.rs; p.collect_stats = io->collect_stats; p.dot_fma = env->cfg.dot_fma; p.blk = env->blk; p.stats_bank = io->stats_bank;
         const int64_t count = io->env_count > 0 ? io->env_count : env->n;
         p.i0 = (uint32_t)io->env_first; p.i_end = (uint32_t)(io->env_first + count);
         int pth = ah::kPackedThreads;
@@ -983,6 +984,7 @@ int ah_step(ah_env* env, const ah_step_io* io, int K, void* stream) {
     if (kind != AH_ACT_DISCRETE && kind != AH_ACT_CONTINUOUS && kind != AH_ACT_PHILOX && kind != AH_ACT_DISCRETE_REPEAT &&
         kind != AH_ACT_CONTINUOUS_REPEAT && kind != AH_ACT_POLICY && kind != AH_ACT_DISCRETE_PACKED4) return AH_EINVAL;
     if ((kind == AH_ACT_DISCRETE_PACKED4) != (io->events != nullptr)) return AH_EINVAL;   // the packed mode is all-or-nothing
+    if (io->stats_bank != 0 && io->stats_bank != 1) return AH_EINVAL;
     if (io->env_first < 0 || io->env_count < 0 || io->env_first + io->env_count > env->n) return AH_EINVAL;
     if ((io->env_first != 0 || io->env_count != 0) && !io->events) return AH_EINVAL;     // sub-ranges: packed mode only
     if (io->events) {
@@ -1030,12 +1032,14 @@ int ah_pack_host(ah_env* env, int K, const void* d_reward, const uint8_t* d_done
     AH_LAUNCH_RC(env);
 }
 
-int ah_stats(ah_env* env, int64_t* d_out, int clear, void* stream) {
-    if (!env || !d_out) return AH_EINVAL;
+int ah_stats_bank(ah_env* env, int bank, int64_t* d_out, int clear, void* stream) {
+    if (!env || !d_out || (bank != 0 && bank != 1)) return AH_EINVAL;
     DeviceGuard g(env->device);
-    ah::stats_copy_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(env->blk, d_out, clear);
+    ah::stats_copy_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(env->blk, bank, d_out, clear);
     AH_LAUNCH_RC(env);
 }
+
+int ah_stats(ah_env* env, int64_t* d_out, int clear, void* stream) { return ah_stats_bank(env, 0, d_out, clear, stream); }
 
 int ah_set_counters(ah_env* env, uint64_t frame, void* stream) {
     if (!env) return AH_EINVAL;

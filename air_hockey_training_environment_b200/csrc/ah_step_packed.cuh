@@ -37,7 +37,7 @@ struct PackedArgs {
     uint32_t* events;             // u8 [ceil(K/4)][n][4]
     R* obs_next;                  // [n][8], nullable
     ResetSrc rs;
-    int collect_stats, dot_fma;
+    int collect_stats, dot_fma, stats_bank;
     DevBlock* blk;
     uint32_t i0, i_end;           // envs [i0, i_end) are stepped by this launch (row strides stay n)
 };
@@ -259,7 +259,7 @@ step_packed_kernel(const PackedArgs<R> a) {
     // reward = 2 r3 - 4  =>  sum = 2 S1 - 4 F,  sum of squares = 4 S2 - 16 S1 + 16 F
     const int reward_sum = 2 * r3sum - 4 * frames;
     const int reward_sq = 4 * r3sq - 16 * r3sum + 16 * frames;
-    finish_stats<false>(bs, a.blk, a.collect_stats, frames, reward_sum, reward_sq, dones, contacts & 0xffff, contacts >> 16,
+    finish_stats<false>(bs, a.blk, a.stats_bank, a.collect_stats, frames, reward_sum, reward_sq, dones, contacts & 0xffff, contacts >> 16,
                  (int)overflow, bad, amb, a.i0 == 0 ? nK : 0, nullptr);
 }
 

@@ -364,7 +364,8 @@ class BatchedAirHockey:
     def step(self, actions: Optional[torch.Tensor] = None, K: int = 1, *, repeat: bool = False,
              out: Optional[StepOutputs] = None, reset_table: Optional[torch.Tensor] = None,
              ring: Optional[ReplayRing] = None, collect_stats: bool = True,
-             policy_weights: Optional[torch.Tensor] = None, env_range: Optional[Sequence[int]] = None) -> StepOutputs:
+             policy_weights: Optional[torch.Tensor] = None, env_range: Optional[Sequence[int]] = None,
+             stats_bank: int = 0) -> StepOutputs:
         """K fused frames of ``Game.play`` for every env, in ONE kernel launch (state stays in registers).
 
         actions: None                -> uniform random {0,1,2,3} drawn in-kernel (Philox)
@@ -437,6 +438,7 @@ class BatchedAirHockey:
         if out.events is not None:
             io.events = self._check_tensor(out.events, ((K + 3) // 4, self.n, 4), torch.uint8, "events").data_ptr()
         io.collect_stats = int(collect_stats)
+        io.stats_bank = int(stats_bank)
         if env_range is not None:
             io.env_first, io.env_count = int(env_range[0]), int(env_range[1])
         if ring is not None:
@@ -450,10 +452,11 @@ class BatchedAirHockey:
         return out
 
     # ------------------------------------------------------------------ statistics, counters, checkpoints
-    def stats_tensor(self, clear: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """int64 [16] device tensor of the AH_STAT_* counters accumulated by ``step`` (no host sync)."""
+    def stats_tensor(self, clear: bool = False, out: Optional[torch.Tensor] = None, bank: int = 0) -> torch.Tensor:
+        """int64 [AH_NSTATS] device tensor of the AH_STAT_* counters accumulated by ``step`` (no host sync).  ``bank``:
+        which of the two statistics banks (``step(stats_bank=...)``; everything defaults to bank 0)."""
         out = self._stats_buf if out is None else out
-        _capi.check(self._lib.ah_stats(self._h, out.data_ptr(), int(clear), self._stream()), "ah_stats", self._h)
+        _capi.check(self._lib.ah_stats_bank(self._h, int(bank), out.data_ptr(), int(clear), self._stream()), "ah_stats_bank", self._h)
         return out
 
     def stats(self, clear: bool = False) -> Dict[str, int]:
@@ -510,6 +513,8 @@ class InterleavedStepper:
         per = -(-per // align) * align                       # whole blocks per slice
         self.ranges = [(lo, min(per, env.n - lo)) for lo in range(0, env.n, per)]
         self.streams = [torch.cuda.Stream(env.device) for _ in self.ranges]
+        self.stats_stream = torch.cuda.Stream(env.device)
+        self.bank = 0
         self._forked = False
 
     def step(self, actions: torch.Tensor, K: int, out: StepOutputs, **kw) -> StepOutputs:
@@ -522,12 +527,32 @@ class InterleavedStepper:
             self._forked = True
         for s, rng in zip(self.streams, self.ranges):
             with torch.cuda.stream(s):
-                self.env.step(actions, K=K, out=out, env_range=rng, **kw)
+                self.env.step(actions, K=K, out=out, env_range=rng, stats_bank=self.bank, **kw)
         return out
+
+    def close_rollout(self, stats_out: torch.Tensor) -> torch.cuda.Stream:
+        """End of a rollout, WITHOUT draining the GPU: the statistics bank the steps so far accumulated into is copied
+        to ``stats_out`` and cleared on a private stream that waits for exactly those steps, and later steps switch to
+        the other bank -- they neither wait for the copy nor race with it.  Returns the stream the copy was queued on
+        (queue the all-reduce there, or make a consumer stream wait for it)."""
+        done = []
+        for s in self.streams:
+            ev = torch.cuda.Event()
+            ev.record(s)
+            done.append(ev)
+        if not self._forked:                                 # nothing issued since the last join: order after the caller
+            self.stats_stream.wait_stream(torch.cuda.current_stream(self.env.device))
+        for ev in done:
+            self.stats_stream.wait_event(ev)
+        with torch.cuda.stream(self.stats_stream):
+            self.env.stats_tensor(clear=True, out=stats_out, bank=self.bank)
+        self.bank ^= 1
+        return self.stats_stream
 
     def join(self) -> None:
         """Make the caller's current stream wait for every slice issued so far (no host sync)."""
         cur = torch.cuda.current_stream(self.env.device)
         for s in self.streams:
             cur.wait_stream(s)
+        cur.wait_stream(self.stats_stream)
         self._forked = False

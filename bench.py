@@ -234,35 +234,49 @@ ROLLOUT_STEPS = 16           # bench steps per "rollout": the episode/score stat
 
 class StatsReducer:
     """The path's only exchange: once per rollout (every ROLLOUT_STEPS steps, and once more at the
-    end of a timed region) the int64[AH_NSTATS] statistics vector the step kernel accumulated on the device is copied out and
-    cleared (`ah_stats`, one tiny launch) and, at N > 1, summed over the ranks with one asynchronous NCCL all-reduce
-    (160 B over NVLink; NCCL's stream waits for the step kernel, the next step's kernel does not wait for NCCL).  The
-    reduced vectors are accumulated so that the payload can be checked: frames == world x envs x K x steps."""
+    end of a timed region) the int64[AH_NSTATS] statistics vector the step kernel accumulated on the device is copied out
+    and cleared (`ah_stats_bank`, one tiny launch) and, at N > 1, summed over the ranks with one asynchronous NCCL
+    all-reduce (160 B over NVLink).  Nothing in the step path waits for it: with an InterleavedStepper the copy runs on a
+    private stream behind exactly the steps of the finished rollout while later steps accumulate into the other
+    statistics bank (`close_rollout`); on a single stream NCCL's stream waits for the step kernel and the next step's
+    kernel does not wait for NCCL.  The reduced vectors are accumulated so that the payload can be checked:
+    frames == world x envs x K x steps."""
 
-    def __init__(self, env, world, dev, every=ROLLOUT_STEPS):
+    def __init__(self, env, world, dev, every=ROLLOUT_STEPS, stepper=None):
         import torch
-        self.env, self.world, self.every = env, world, every
         from air_hockey_training_environment_b200 import STAT_NAMES
+        self.env, self.world, self.every, self.stepper, self.dev = env, world, every, stepper, dev
         self.bufs = [torch.zeros(len(STAT_NAMES), dtype=torch.int64, device=dev) for _ in range(2)]
         self.acc = torch.zeros(len(STAT_NAMES), dtype=torch.int64, device=dev)
         self.pending, self.j, self.count, self.reductions = None, 0, 0, 0
 
     def _collect(self):
+        import torch
         if self.pending is not None:
-            work, buf = self.pending
+            work, buf, side = self.pending
             if work is not None:
                 work.wait()                    # stream-level wait, no host sync
+            if side is not None:
+                torch.cuda.current_stream(self.dev).wait_stream(side)
             self.acc += buf
             self.pending = None
 
     def reduce(self):
+        import torch
         import torch.distributed as dist
         self._collect()
         buf = self.bufs[self.j]
         self.j ^= 1
-        self.env.stats_tensor(clear=True, out=buf)
-        work = dist.all_reduce(buf, async_op=True) if self.world > 1 else None
-        self.pending = (work, buf)
+        side = None
+        if self.stepper is not None:
+            self.stepper.stats_stream.wait_stream(torch.cuda.current_stream(self.dev))   # buf's previous reader is done
+            side = self.stepper.close_rollout(buf)
+            with torch.cuda.stream(side):
+                work = dist.all_reduce(buf, async_op=True) if self.world > 1 else None
+        else:
+            self.env.stats_tensor(clear=True, out=buf)
+            work = dist.all_reduce(buf, async_op=True) if self.world > 1 else None
+        self.pending = (work, buf, side)
         self.reductions += 1
 
     def after_step(self):
@@ -307,6 +321,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--parts", type=int, default=2, help="env slices (streams) per step; 1 = a single launch per step")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -341,13 +356,23 @@ def main():
     n_act = 4                                                    # rotate several action tensors
     acts = [torch.randint(0, 4, ((K + 3) // 4, n, 4), dtype=torch.uint8, device=dev, generator=gen) for _ in range(n_act)]
     stream = torch.cuda.current_stream(dev)
-    red = StatsReducer(env, world, dev)
+    # Every step is issued as `--parts` disjoint env slices on as many streams (InterleavedStepper): the slices are
+    # independent, so the GPU does not drain between steps -- the tail of one slice's launch overlaps the head of the
+    # next one's.  --parts 1 = one launch per step on the current stream.
+    from air_hockey_training_environment_b200 import InterleavedStepper
+    stepper = InterleavedStepper(env, parts=args.parts) if args.parts > 1 else None
+    red = StatsReducer(env, world, dev, stepper=stepper)
 
     def one_step(i: int):
-        env.step(acts[i % n_act], K=K, out=out)
+        if stepper is not None:
+            stepper.step(acts[i % n_act], K, out)
+        else:
+            env.step(acts[i % n_act], K=K, out=out)
         red.after_step()
 
     def barrier():
+        if stepper is not None:
+            stepper.join()
         red.flush()
         if world > 1:
             dist.barrier()
@@ -368,10 +393,15 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.time()
     red.restart()
+    # the GPU spins for ~0.1 ms before the start event so that the host's first launches are already queued when the
+    # timed region opens: the region then measures K steps of device work, not the host's latency to issue the first one
+    torch.cuda._sleep(200_000)
     ev0.record(stream)
     for i in range(args.steps):
         one_step(i)
     red.finish()                              # the last (partial) rollout's all-reduce is inside the timed region too
+    if stepper is not None:
+        stepper.join()
     ev1.record(stream)
     barrier()
     t_wall1 = time.time()
@@ -402,12 +432,16 @@ def main():
     if rank == 0:
         sampler.stop()
 
-    # ---- duration of the dominant kernel.  At N = 1 a bench step IS one launch of the step kernel and the timed region is
-    # a back-to-back queue of them, so the timed region's CUDA-event time / steps is that kernel's average launch
-    # duration; an isolated per-launch measurement (event pair around every launch) is reported beside it.
-    kernel_ms = kernel_ms_isolated = None
+    # ---- duration of the dominant kernel.  The timed region is a back-to-back queue of step-kernel launches and nothing
+    # else (plus one tiny stats copy per rollout), so CUDA-event time / steps is the kernel time one step costs: with
+    # --parts 1 that IS the average launch duration; with slices the launches of consecutive steps overlap tail-to-head
+    # and it is the time per step's worth of launches.  Beside it: a single whole-n launch timed back-to-back on one
+    # stream (`single_launch_ms`) and with an event pair around every launch (`kernel_ms_isolated`).
+    kernel_ms = kernel_ms_isolated = single_launch_ms = None
     if world == 1:
         kernel_ms = total_ms / args.steps
+        barrier()
+        single_launch_ms = _time_loop(dev, lambda i: env.step(acts[i % n_act], K=K, out=out), 20, max(args.steps, 100))
         reps = min(args.steps, 200)
         kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
         for i, (a, b) in enumerate(kev):
@@ -447,9 +481,12 @@ def main():
         "config": {"workload": workload_name(world), "envs_per_gpu": n, "frames_per_step": K,
                    "sub_updates_per_sec": 3 * value,
                    "l2": "no flush: each step touches %.0f MB of distinct HBM lines (> 126 MB L2)" % (bytes_per_launch / 1e6),
-                   "launch": env.launch_info()},
+                   "launch": env.launch_info(),
+                   "launches_per_step": max(1, args.parts),
+                   "interleaving": (f"each step = {args.parts} disjoint env slices on {args.parts} streams (sub-range launches of the same "
+                                    "kernel); consecutive steps overlap tail-to-head" if args.parts > 1 else "one launch per step")},
         # per rank: one step kernel per step + one ah_stats copy kernel per rollout (every 16 steps and at the end)
-        "gpu_launches": args.steps + stats_check["reductions"],
+        "gpu_launches": args.steps * max(1, args.parts) + stats_check["reductions"],
         "stats_allreduce": dict(stats_check, every_steps=ROLLOUT_STEPS,
                                 what="int64[20] episode/score statistics, summed over ranks (NCCL) once per rollout, "
                                      "inside the timed region; frames verified against world x envs x K x steps"),
@@ -466,10 +503,13 @@ def main():
             "bound": "fp32", "achieved": lane_ach, "peak": lane_peak, "unit": "Glane-op/s", "frac": lane_ach / lane_peak,
             "traffic": profile_fact("dram_bytes_per_launch"),
             "kernel": "ah::step_packed_kernel<float>", "kernel_ms": kernel_ms,
-            "kernel_ms_isolated": kernel_ms_isolated,
+            "kernel_ms_isolated": kernel_ms_isolated, "single_launch_ms": single_launch_ms,
+            "single_launch_frac": (LANE_OPS_PER_ENV_STEP * n * K / (single_launch_ms * 1e-3) / 1e9 / lane_peak) if single_launch_ms else None,
             "note": "K=8 fused frames: bound by FP32/ALU-pipe issue, not HBM (north_star: the slower of FP32 peak and "
                     "state bytes over HBM bandwidth). achieved = 254 algorithmic lane-ops/env-step x env-steps/s; "
-                    "peak = 148 SMs x 128 FP32 lanes x SM clock under load. The HBM view of the same launch follows.",
+                    "peak = 148 SMs x 128 FP32 lanes x SM clock under load. kernel_ms = timed region / steps (each step = "
+                    "`launches_per_step` sub-range launches whose tails and heads overlap across steps); single_launch_* = one "
+                    "whole-n launch per step on one stream. The HBM view of the same step follows.",
             "algorithmic_lane_ops_per_env_step": LANE_OPS_PER_ENV_STEP,
             "executed_warp_insts_per_warp_frame": profile_fact("warp_insts_per_warp_frame"),
             "alu_pipe_active_pct_ncu": profile_fact("alu_pipe_active_pct"),

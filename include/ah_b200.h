@@ -171,6 +171,11 @@ typedef struct ah_step_io {
      * range's (host.InterleavedStepper).  The frame counter advances with the range that contains env 0. */
     int64_t env_first;
     int64_t env_count;
+    /* Which of the handle's two statistics banks this launch accumulates into (0 or 1).  A caller that overlaps steps on
+     * several streams alternates the bank per rollout, so that closing a rollout (ah_stats_bank: copy + clear of the
+     * finished bank) never has to wait for -- or race with -- the launches of the next one. */
+    int32_t stats_bank;
+    int32_t reserved0;
 } ah_step_io;
 
 const char* ah_strerror(int code);
@@ -234,8 +239,10 @@ int ah_actor_sample(ah_env* env, const float* d_weights, const void* d_obs, void
 int ah_pack_host(ah_env* env, int K, const void* d_reward, const uint8_t* d_done, const void* d_obs_next,
                  uint8_t* d_events, int16_t* d_obs_pos, float* d_obs_vel, void* stream);
 
-/* Copy the int64[AH_NSTATS] statistics block to a caller device buffer, optionally clearing it. */
+/* Copy the int64[AH_NSTATS] statistics block to a caller device buffer, optionally clearing it.  ah_stats reads bank 0
+ * (the default of ah_step_io.stats_bank); ah_stats_bank reads the given bank (0 or 1). */
 int ah_stats(ah_env* env, int64_t* d_out, int clear, void* stream);
+int ah_stats_bank(ah_env* env, int bank, int64_t* d_out, int clear, void* stream);
 
 /* Global frame counter (Philox action / sampling index), kept on the device so that captured graphs advance it;
  * get copies it (uint64[1]) to a caller device buffer.  (The ring's append counter lives in the ring: ah_ring.appended.) */

@@ -224,3 +224,33 @@ def test_interleaved_slices_equal_one_launch(parts):
     from air_hockey_training_environment_b200 import AhError
     with pytest.raises(AhError):                            # sub-ranges exist in the packed mode only
         b.step(None, K=1, env_range=(0, 100))
+
+
+def test_close_rollout_banks_partition_the_statistics():
+    """close_rollout(): the statistics of the steps issued so far land in one bank, later steps in the other -- without a
+    join in between.  Per-rollout vectors must add up to the single-stream totals and each carry exactly its own frames."""
+    from air_hockey_training_environment_b200 import InterleavedStepper, STAT_NAMES
+    n, K = 1 << 16, 8
+    a, b = make_env(n, seed=4), make_env(n, seed=4)
+    for env in (a, b):
+        env.step(None, K=400, out=env.make_outputs(400, ()))
+        env.stats(clear=True)
+    st = InterleavedStepper(b, parts=2)
+    gen = torch.Generator(device="cuda").manual_seed(2)
+    oa, ob = a.make_outputs(K, ("events",)), b.make_outputs(K, ("events",))
+    bufs = [torch.zeros(len(STAT_NAMES), dtype=torch.int64, device="cuda") for _ in range(3)]
+    per_rollout = [5, 3, 4]
+    for r, steps in enumerate(per_rollout):
+        for _ in range(steps):
+            acts = torch.randint(0, 4, (2, n, 4), dtype=torch.uint8, device="cuda", generator=gen)
+            a.step(acts, K=K, out=oa)
+            st.step(acts, K, ob)
+        st.close_rollout(bufs[r])                            # no join: the next rollout's steps follow immediately
+    st.join()
+    torch.cuda.synchronize()
+    for r, steps in enumerate(per_rollout):
+        assert int(bufs[r][0]) == steps * K * n              # each rollout's vector holds exactly its own frames
+    total = dict(zip(STAT_NAMES, (bufs[0] + bufs[1] + bufs[2]).tolist()))
+    assert total == a.stats()
+    assert b.stats(clear=False)["frames"] == 0 and int(b.stats_tensor(bank=1)[0]) == 0
+    assert same(snapshot(a), snapshot(b))
