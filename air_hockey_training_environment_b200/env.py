@@ -65,6 +65,16 @@ class StepOutputs:
                                                    #               game_over of a frame in ONE byte (see unpack_events)
 
 
+@dataclass
+class StepPlan:
+    """A validated, frozen ``ah_step`` call (``BatchedAirHockey.plan_step`` / ``launch``)."""
+    io: object
+    io_ref: object
+    K: int
+    out: "StepOutputs"
+    keepalive: tuple
+
+
 class ReplayRing:
     """Device-resident replacement of ``MemoryBuffer`` (lib/buffer.py:11-66) for ``Observation`` tuples
     (lib/types.py:7), filled from inside the step kernel.  Layout ``[capacity, N, ...]``; like the reference's
@@ -361,12 +371,31 @@ class BatchedAirHockey:
             o.events = torch.empty((K + 3) // 4, self.n, 4, dtype=torch.uint8, device=self.device)
         return o
 
-    def step(self, actions: Optional[torch.Tensor] = None, K: int = 1, *, repeat: bool = False,
-             out: Optional[StepOutputs] = None, reset_table: Optional[torch.Tensor] = None,
-             ring: Optional[ReplayRing] = None, collect_stats: bool = True,
-             policy_weights: Optional[torch.Tensor] = None, env_range: Optional[Sequence[int]] = None,
-             stats_bank: int = 0) -> StepOutputs:
-        """K fused frames of ``Game.play`` for every env, in ONE kernel launch (state stays in registers).
+    def step(self, actions: Optional[torch.Tensor] = None, K: int = 1, *, out: Optional[StepOutputs] = None,
+             stream: Optional[int] = None, **kw) -> StepOutputs:
+        """``plan_step`` + ``launch``: see ``plan_step`` for the arguments.  ``stream``: raw ``cudaStream_t`` to enqueue on
+        (default: torch's current stream)."""
+        if out is None:
+            out = self.make_outputs(K)
+        plan = self.plan_step(actions, K, out=out, **kw)
+        self.launch(plan, stream)
+        return out
+
+    def launch(self, plan: "StepPlan", stream: Optional[int] = None) -> None:
+        """Enqueue a prepared step (``plan_step``) -- one C-ABI call, no argument checking, no allocation."""
+        self._io_keepalive = plan
+        _capi.check(self._lib.ah_step(self._h, plan.io_ref, plan.K, self._stream() if stream is None else stream),
+                    "ah_step", self._h)
+
+    def plan_step(self, actions: Optional[torch.Tensor] = None, K: int = 1, *, repeat: bool = False,
+                  out: Optional[StepOutputs] = None, reset_table: Optional[torch.Tensor] = None,
+                  ring: Optional[ReplayRing] = None, collect_stats: bool = True,
+                  policy_weights: Optional[torch.Tensor] = None, env_range: Optional[Sequence[int]] = None,
+                  stats_bank: int = 0) -> "StepPlan":
+        """Validate the arguments of one step and freeze them into a ``StepPlan`` that ``launch`` can enqueue any number
+        of times (the tensors are referenced, not copied: replays read / write the same memory).
+
+        K fused frames of ``Game.play`` for every env, in ONE kernel launch (state stays in registers).
 
         actions: None                -> uniform random {0,1,2,3} drawn in-kernel (Philox)
                  int8 [K,N]          -> one discrete action per frame   ([N] when K == 1 or ``repeat``)
@@ -447,9 +476,7 @@ class BatchedAirHockey:
             if ring.continuous != (io.action_kind in (_capi.AH_ACT_CONTINUOUS, _capi.AH_ACT_CONTINUOUS_REPEAT)):
                 raise ValueError("ring action layout (discrete/continuous) does not match the actions given")
             io.ring = C.pointer(ring._c)
-        self._io_keepalive = (io, actions)
-        _capi.check(self._lib.ah_step(self._h, C.byref(io), int(K), self._stream()), "ah_step", self._h)
-        return out
+        return StepPlan(io, C.byref(io), int(K), out, (actions, reset_table, ring, policy_weights))
 
     # ------------------------------------------------------------------ statistics, counters, checkpoints
     def stats_tensor(self, clear: bool = False, out: Optional[torch.Tensor] = None, bank: int = 0) -> torch.Tensor:
@@ -513,9 +540,11 @@ class InterleavedStepper:
         per = -(-per // align) * align                       # whole blocks per slice
         self.ranges = [(lo, min(per, env.n - lo)) for lo in range(0, env.n, per)]
         self.streams = [torch.cuda.Stream(env.device) for _ in self.ranges]
+        self._raw_streams = [s.cuda_stream for s in self.streams]
         self.stats_stream = torch.cuda.Stream(env.device)
         self.bank = 0
         self._forked = False
+        self._plans: Dict[tuple, list] = {}
 
     def step(self, actions: torch.Tensor, K: int, out: StepOutputs, **kw) -> StepOutputs:
         if out.events is None:
@@ -525,9 +554,15 @@ class InterleavedStepper:
             for s in self.streams:
                 s.wait_stream(cur)
             self._forked = True
-        for s, rng in zip(self.streams, self.ranges):
-            with torch.cuda.stream(s):
-                self.env.step(actions, K=K, out=out, env_range=rng, stats_bank=self.bank, **kw)
+        key = (actions.data_ptr(), id(out), K, self.bank, tuple(sorted((k, id(v)) for k, v in kw.items())))
+        plans = self._plans.get(key)
+        if plans is None:                                    # validated once per (actions, outputs, bank) combination
+            if len(self._plans) > 64:
+                self._plans.clear()
+            plans = [self.env.plan_step(actions, K, out=out, env_range=rng, stats_bank=self.bank, **kw) for rng in self.ranges]
+            self._plans[key] = plans
+        for s, plan in zip(self._raw_streams, plans):
+            self.env.launch(plan, s)
         return out
 
     def close_rollout(self, stats_out: torch.Tensor) -> torch.cuda.Stream:

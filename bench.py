@@ -393,12 +393,12 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.time()
     red.restart()
-    # the GPU spins for ~0.1 ms before the start event so that the host's first launches are already queued when the
-    # timed region opens: the region then measures K steps of device work, not the host's latency to issue the first one
-    torch.cuda._sleep(200_000)
+    align_start(dev, world)
     ev0.record(stream)
+    t_issue0 = time.perf_counter()
     for i in range(args.steps):
         one_step(i)
+    host_issue_us = 1e6 * (time.perf_counter() - t_issue0) / args.steps
     red.finish()                              # the last (partial) rollout's all-reduce is inside the timed region too
     if stepper is not None:
         stepper.join()
@@ -482,7 +482,7 @@ def main():
                    "sub_updates_per_sec": 3 * value,
                    "l2": "no flush: each step touches %.0f MB of distinct HBM lines (> 126 MB L2)" % (bytes_per_launch / 1e6),
                    "launch": env.launch_info(),
-                   "launches_per_step": max(1, args.parts),
+                   "launches_per_step": max(1, args.parts), "host_issue_us_per_step": host_issue_us,
                    "interleaving": (f"each step = {args.parts} disjoint env slices on {args.parts} streams (sub-range launches of the same "
                                     "kernel); consecutive steps overlap tail-to-head" if args.parts > 1 else "one launch per step")},
         # per rank: one step kernel per step + one ah_stats copy kernel per rollout (every 16 steps and at the end)
@@ -529,6 +529,24 @@ def main():
         dist.destroy_process_group()
 
 
+_align_buf = {}
+
+
+def align_start(dev, world):
+    """Queued right before a start event.  (1) At N > 1 a one-element NCCL all-reduce: it completes on every GPU at the
+    same moment, so the ranks' timed regions open together ON THE DEVICE (the host barrier before it only aligns the
+    hosts to a few hundred microseconds, which a collective inside a ~2 ms timed region would otherwise expose as rank
+    skew).  (2) The GPU then spins (0.1 ms; 1 ms at N > 1) so that the host's first launches are already queued when the
+    region opens: the region measures K steps of device work, not the host's latency to issue the first one."""
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        if dev not in _align_buf:
+            _align_buf[dev] = torch.zeros(1, device=dev)
+        dist.all_reduce(_align_buf[dev])
+    torch.cuda._sleep(2_000_000 if world > 1 else 200_000)
+
+
 def _time_loop(dev, fn, warm, reps, world=1, red=None):
     """Average ms per call of fn(i): CUDA events on the current stream around `reps` calls; at world > 1 bracketed by
     barriers and reduced with MAX over the ranks.  `red` (a StatsReducer) is stepped after every call and its final
@@ -552,6 +570,7 @@ def _time_loop(dev, fn, warm, reps, world=1, red=None):
         red.restart()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s = torch.cuda.current_stream(dev)
+    align_start(dev, world)
     a.record(s)
     for i in range(reps):
         fn(i)
