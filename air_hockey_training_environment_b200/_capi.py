@@ -14,7 +14,7 @@ AH_OK, AH_EINVAL, AH_ECUDA, AH_ENOMEM, AH_EAGENT, AH_ESTATE = 0, -1, -2, -3, -4,
 AH_F32, AH_F64 = 0, 1
 AH_AGENT_ROBOT, AH_AGENT_HUMAN, AH_AGENT_COMPUTER = 0, 1, 2
 (AH_ACT_NONE, AH_ACT_DISCRETE, AH_ACT_CONTINUOUS, AH_ACT_PHILOX, AH_ACT_DISCRETE_REPEAT, AH_ACT_CONTINUOUS_REPEAT,
- AH_ACT_POLICY, AH_ACT_DISCRETE_PACKED4) = range(8)
+ AH_ACT_POLICY, AH_ACT_DISCRETE_PACKED4, AH_ACT_POLICY_MLP) = range(9)
 AH_NSTATS = 20
 AH_ACTOR_NWEIGHTS = 114
 STAT_NAMES = ("frames", "robot_goals", "opponent_goals", "robot_wins", "opponent_wins", "dones", "reward_sum",
@@ -23,7 +23,7 @@ STAT_NAMES = ("frames", "robot_goals", "opponent_goals", "robot_wins", "opponent
 
 # every symbol include/ah_b200.h declares (tests/test_capi_symbols.py checks header <-> library <-> this list)
 SYMBOLS = ("ah_strerror", "ah_abi_version", "ah_last_cuda_error", "ah_create", "ah_destroy", "ah_bind_state",
-           "ah_init_state", "ah_reset", "ah_update_state", "ah_get_state", "ah_update_score", "ah_rewards", "ah_step", "ah_pack_host", "ah_actor_sample", "ah_stats", "ah_stats_bank",
+           "ah_init_state", "ah_reset", "ah_update_state", "ah_get_state", "ah_update_score", "ah_rewards", "ah_step", "ah_pack_host", "ah_actor_sample", "ah_policy_act", "ah_stats", "ah_stats_bank",
            "ah_set_counters", "ah_get_counters", "ah_ring_sample", "ah_launch_info", "ah_selftest_nofma")
 
 
@@ -36,6 +36,24 @@ class AhRing(C.Structure):
                 ("done", C.c_void_p), ("capacity", C.c_int64), ("appended", C.c_void_p)]
 
 
+AH_ACTV_LINEAR, AH_ACTV_RELU, AH_ACTV_TANH = 0, 1, 2
+AH_HEAD_SOFTMAX, AH_HEAD_VALUES, AH_HEAD_DUELING, AH_HEAD_CONTINUOUS = 0, 1, 2, 3
+(AH_SELECT_SAMPLE, AH_SELECT_GREEDY, AH_SELECT_EPS_GREEDY, AH_SELECT_BOLTZMANN, AH_SELECT_MAX_BOLTZMANN, AH_SELECT_GAUSSIAN,
+ AH_SELECT_OU) = range(7)
+AH_POLICY_MAX_LAYERS, AH_POLICY_MAX_WIDTH = 4, 32
+
+
+class AhPolicy(C.Structure):
+    _fields_ = [("n_layers", C.c_int32), ("width", C.c_int32 * 5), ("activation", C.c_int32 * 4),
+                ("head", C.c_int32), ("select", C.c_int32), ("n_actions", C.c_int32),
+                ("epsilon", C.c_float), ("initial_epsilon", C.c_float), ("final_epsilon", C.c_float),
+                ("observe", C.c_int32), ("explore", C.c_int32),
+                ("tau", C.c_float), ("clip_lo", C.c_float), ("clip_hi", C.c_float),
+                ("mu", C.c_float), ("sigma", C.c_float), ("sigma_min", C.c_float), ("n_steps_annealing", C.c_int32),
+                ("theta", C.c_float), ("dt", C.c_float),
+                ("weights", C.c_void_p), ("noise_state", C.c_void_p)]
+
+
 class AhStepIO(C.Structure):
     _fields_ = [("actions", C.c_void_p), ("action_kind", C.c_int32), ("reset_table_len", C.c_int32),
                 ("reset_table", C.c_void_p),
@@ -43,7 +61,8 @@ class AhStepIO(C.Structure):
                 ("done", C.c_void_p), ("score", C.c_void_p), ("game_over", C.c_void_p),
                 ("obs_next", C.c_void_p), ("obs_next_per_frame", C.c_int32), ("collect_stats", C.c_int32),
                 ("ring", C.POINTER(AhRing)), ("actions_out", C.c_void_p), ("probs_out", C.c_void_p),
-                ("events", C.c_void_p), ("env_first", C.c_int64), ("env_count", C.c_int64),
+                ("events", C.c_void_p), ("policy", C.POINTER(AhPolicy)), ("actions_real_out", C.c_void_p),
+                ("env_first", C.c_int64), ("env_count", C.c_int64),
                 ("stats_bank", C.c_int32), ("reserved0", C.c_int32)]
 
 
@@ -100,6 +119,8 @@ def lib() -> C.CDLL:
     L.ah_pack_host.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp]
     L.ah_actor_sample.restype = i32
     L.ah_actor_sample.argtypes = [vp, vp, vp, vp, vp, i32, vp]
+    L.ah_policy_act.restype = i32
+    L.ah_policy_act.argtypes = [vp, C.POINTER(AhPolicy), vp, vp, vp, vp, vp, vp]
     L.ah_stats.restype = i32
     L.ah_stats.argtypes = [vp, vp, i32, vp]
     L.ah_stats_bank.restype = i32

@@ -94,6 +94,10 @@ __device__ __forceinline__ void store_obs(R* base, int64_t row, const Obs<R>& o)
     dst[0] = a; dst[1] = b;
 }
 
+}  // namespace ah
+#include "ah_policy.cuh"
+namespace ah {
+
 // ------------------------------------------------------------------------------------------------ resets
 struct ResetSrc {
     const double* table;   // [n][R][2] or nullptr => Philox
@@ -142,6 +146,7 @@ struct StepArgs {
     DevBlock* blk;
     int stats_bank;
     int8_t* actions_out; R* probs_out;     // GENERIC mode: the actions applied / the in-kernel actor's distribution
+    PolicyDev pol; R* actions_real_out;    // AH_ACT_POLICY_MLP
 };
 
 // Block-level statistics: rare events (goals, wins, contacts ...) are counted with shared-memory atomics right
@@ -300,8 +305,12 @@ step_kernel(const StepArgs<R> a) {
     // instead of four compares and four selects per frame.  Entry 4 = "any other int": no nudge.
     __shared__ V2 s_nudge[8];
     __shared__ __align__(16) float s_actor[ACT == 4 ? 128 : 4];     // AH_ACT_POLICY: the actor's 114 weights
+    __shared__ __align__(16) float s_pol[ACT == 5 ? kPolMaxFloats : 4];              // AH_ACT_POLICY_MLP: weights
+    __shared__ float s_hs[ACT == 5 ? 2 * kPolMaxW * kPolThreads : 4];                //                    activations
     if (ACT == 4)
         for (int t = threadIdx.x; t < AH_ACTOR_NWEIGHTS; t += blockDim.x) s_actor[t] = reinterpret_cast<const float*>(a.actions)[t];
+    if (ACT == 5) policy_stage(a.pol, s_pol);
+    const bool cont_act = (ACT == 2) || (ACT == 5 && a.pol.head == AH_HEAD_CONTINUOUS);
     if (threadIdx.x < AH_NSTATS) bs.v[threadIdx.x] = 0;
     if (threadIdx.x == 0) { bs.len_sq = 0ull; bs.warps_done = 0; }
     if (threadIdx.x < 8) {
@@ -315,7 +324,7 @@ step_kernel(const StepArgs<R> a) {
     // the device-side counters are read up front only by the variants that need them in the frame loop (Philox
     // actions, ring append): a dependent L2 round-trip at the head of every thread is what the others avoid
     unsigned long long frame0 = 0ull, ring0 = 0ull;
-    if (ACT == 3 || ACT == 4) frame0 = a.blk->frame;
+    if (ACT == 3 || ACT == 4 || ACT == 5) frame0 = a.blk->frame;
     if (MODE == MODE_GENERIC && a.ring_capacity > 0) ring0 = *a.ring_appended;
     const bool repeat = (a.action_kind == AH_ACT_DISCRETE_REPEAT) || (a.action_kind == AH_ACT_CONTINUOUS_REPEAT);
     const bool dot_fma = a.dot_fma != 0;
@@ -393,6 +402,29 @@ step_kernel(const StepArgs<R> a) {
                     typename Vec4T<R>::type q; q.x = p[0]; q.y = p[1]; q.z = p[2]; q.w = p[3];
                     reinterpret_cast<typename Vec4T<R>::type*>(a.probs_out)[(int64_t)k * n + i] = q;
                 }
+            } else if (ACT == 5) {
+                // closed loop with a generic dense policy + exploration strategy (ah_policy.cuh)
+                const Obs<R> ob = get_state<R>(e, true);
+                const float x[8] = {(float)ob.v[0], (float)ob.v[1], (float)ob.v[2], (float)ob.v[3],
+                                    (float)ob.v[4], (float)ob.v[5], (float)ob.v[6], (float)ob.v[7]};
+                float y[8], v[8];
+                policy_forward(a.pol, s_pol, s_hs, x, y);
+                policy_head(a.pol, y, v);
+                const PolicyAction pa = policy_select(a.pol, v, a.rs.seed, a.rs.env_id0 + (uint64_t)i, frame0 + (unsigned long long)k, (int64_t)i);
+                if (cont_act) {
+                    ax = (R)pa.ax; ay = (R)pa.ay;
+                    if (a.actions_real_out) reinterpret_cast<V2*>(a.actions_real_out)[(int64_t)k * n + i] = V2{ax, ay};
+                } else {
+                    ia = pa.ia;
+                    const V2 nd = s_nudge[min((unsigned)ia, 4u)];
+                    ax = nd.x; ay = nd.y;
+                }
+                if (a.probs_out) {
+                    const int nv = cont_act ? 2 : a.pol.n_actions;
+                    R* dst = a.probs_out + ((int64_t)k * n + i) * nv;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) if (q < nv) dst[q] = (R)v[q];
+                }
             } else {
                 const unsigned long long f = frame0 + (unsigned long long)k;
                 const uint32_t bid = (uint32_t)(f >> 6);
@@ -402,7 +434,7 @@ step_kernel(const StepArgs<R> a) {
                 ax = nd.x; ay = nd.y;
             }
             // ---- robot.move(a): sub-update #1                      game.py:136 -> agent.py:32-36
-            move_robot<R>(e, ACT == 2, ax, ay);
+            move_robot<R>(e, cont_act, ax, ay);
             physics_tail<R, false>(e, dot_fma, friction, speed_dirty, contacts_r, contacts_o);
             // observations are stored the moment they exist (not held in registers until the end of the frame)
             const int64_t row = (int64_t)k * n + i;
@@ -413,7 +445,7 @@ step_kernel(const StepArgs<R> a) {
                 if (a.ring_capacity > 0) store_obs<R>(a.ring_state, rrow, s0);
             }
             // ---- robot.step(a) -> self.move(a): sub-update #2      agent.py:64
-            move_robot<R>(e, ACT == 2, ax, ay);
+            move_robot<R>(e, cont_act, ax, ay);
             physics_tail<R, false>(e, dot_fma, friction, speed_dirty, contacts_r, contacts_o);
             if (MODE == MODE_GENERIC && want_obs) {                             // Observation.new_state  agent.py:67
                 const Obs<R> s1 = get_state<R>(e, true);
@@ -447,10 +479,10 @@ step_kernel(const StepArgs<R> a) {
                 if (a.done) a.done[row] = dn ? 1 : 0;
                 if (a.score) a.score[row] = (int8_t)sc;
                 if (a.game_over) a.game_over[row] = (uint8_t)go;
-                if (ACT != 2 && a.actions_out) a.actions_out[row] = (int8_t)ia;
+                if (!cont_act && a.actions_out) a.actions_out[row] = (int8_t)ia;
                 if (a.ring_capacity > 0) {      // fused MemoryBuffer.append(Observation(...))   lib/buffer.py:24-32
                     ring_slot = (ring_slot + 1 == a.ring_capacity) ? 0 : ring_slot + 1;
-                    if (ACT == 2) reinterpret_cast<V2*>(a.ring_action)[rrow] = V2{ax, ay};
+                    if (cont_act) reinterpret_cast<V2*>(a.ring_action)[rrow] = V2{ax, ay};
                     else reinterpret_cast<int8_t*>(a.ring_action)[rrow] = (int8_t)ia;
                     a.ring_reward[rrow] = (R)rw;
                     a.ring_done[rrow] = dn ? 1 : 0;
@@ -753,6 +785,53 @@ inline ah::ResetSrc reset_src(const ah_env* env, const double* table, int R) {
 
 inline unsigned small_grid(int64_t n) { return (unsigned)((n + 255) / 256); }
 
+// ah_policy (host struct, validated) -> the by-value kernel argument
+int make_policy_dev(const ah_policy* p, ah::PolicyDev* d, bool need_weights) {
+    if (!p || !d) return AH_EINVAL;
+    memset(d, 0, sizeof *d);
+    if (p->head < AH_HEAD_SOFTMAX || p->head > AH_HEAD_CONTINUOUS || p->select < AH_SELECT_SAMPLE || p->select > AH_SELECT_OU) return AH_EINVAL;
+    const bool cont = p->head == AH_HEAD_CONTINUOUS;
+    if (cont != (p->select == AH_SELECT_GAUSSIAN || p->select == AH_SELECT_OU || (cont && p->select == AH_SELECT_GREEDY))) return AH_EINVAL;
+    if (!cont && (p->n_actions < 1 || p->n_actions > 7)) return AH_EINVAL;
+    if (p->select == AH_SELECT_OU && (!p->noise_state || (reinterpret_cast<uintptr_t>(p->noise_state) & 7u))) return AH_EINVAL;
+    d->head = p->head; d->select = p->select; d->n_actions = cont ? 2 : p->n_actions;
+    if (need_weights) {
+        if (p->n_layers < 1 || p->n_layers > AH_POLICY_MAX_LAYERS || p->width[0] != 8 || !p->weights || !aligned16(p->weights)) return AH_EINVAL;
+        const int last = p->width[p->n_layers];
+        if (last != (cont ? 2 : (p->head == AH_HEAD_DUELING ? p->n_actions + 1 : p->n_actions))) return AH_EINVAL;
+        int off = 0;
+        d->n_layers = p->n_layers;
+        for (int l = 0; l <= p->n_layers; ++l) {
+            if (p->width[l] < 1 || p->width[l] > AH_POLICY_MAX_WIDTH) return AH_EINVAL;
+            d->width[l] = p->width[l];
+        }
+        for (int l = 0; l < p->n_layers; ++l) {
+            if (p->activation[l] < AH_ACTV_LINEAR || p->activation[l] > AH_ACTV_TANH) return AH_EINVAL;
+            d->act[l] = p->activation[l];
+            const int outp = (p->width[l + 1] + 3) & ~3;
+            d->w_off[l] = off; off += p->width[l] * outp;
+            d->b_off[l] = off; off += outp;
+        }
+        d->n_floats = off;
+        d->weights = p->weights;
+    }
+    // epsilon schedule: the number of decrements after which epsilon <= final_epsilon (strategies.py:39-43)
+    d->eps0 = p->epsilon; d->eps_final = p->final_epsilon; d->observe = p->observe;
+    d->eps_delta = p->explore > 0 ? (p->initial_epsilon - p->final_epsilon) / (float)p->explore : 0.0f;
+    d->max_decrements = 0;
+    if (d->eps_delta > 0.0f && p->epsilon > p->final_epsilon) {
+        double m = ceil(((double)p->epsilon - (double)p->final_epsilon) / (double)d->eps_delta);
+        d->max_decrements = m > 2e9 ? 2000000000 : (int)m;
+    }
+    d->inv_tau = p->tau != 0.0f ? 1.0f / p->tau : 1.0f; d->clip_lo = p->clip_lo; d->clip_hi = p->clip_hi;
+    d->mu = p->mu; d->sigma0 = p->sigma; d->theta = p->theta; d->dt = p->dt; d->sqrt_dt = sqrtf(p->dt > 0.0f ? p->dt : 0.0f);
+    if (p->sigma_min >= 0.0f && p->n_steps_annealing > 0) {      // random.py:17-24
+        d->sigma_m = -(p->sigma - p->sigma_min) / (float)p->n_steps_annealing; d->sigma_min = p->sigma_min;
+    } else { d->sigma_m = 0.0f; d->sigma_min = p->sigma; }
+    d->noise_state = p->noise_state;
+    return AH_OK;
+}
+
 template <typename R>
 int launch_step(ah_env* env, const ah_step_io* io, int K, cudaStream_t s) {
     ah::StepArgs<R> a;
@@ -770,7 +849,11 @@ int launch_step(ah_env* env, const ah_step_io* io, int K, cudaStream_t s) {
         a.ring_appended = reinterpret_cast<unsigned long long*>(io->ring->appended);
     }
     a.dot_fma = env->cfg.dot_fma; a.friction = env->cfg.friction; a.blk = env->blk; a.stats_bank = io->stats_bank;
-    a.actions_out = io->actions_out; a.probs_out = (R*)io->probs_out;
+    a.actions_out = io->actions_out; a.probs_out = (R*)io->probs_out; a.actions_real_out = (R*)io->actions_real_out;
+    if (io->action_kind == AH_ACT_POLICY_MLP) {
+        const int prc = make_policy_dev(io->policy, &a.pol, true);
+        if (prc != AH_OK) return prc;
+    }
     const int max_blocks = sizeof(R) == 4 ? env->blocks_f32 : env->blocks_f64;
     // block size: 256 threads, halved (down to 64) while the grid would leave SMs unevenly filled (< 4 blocks per SM):
     // a 65,536-env rollout is 256 blocks of 256 (1.7 per SM: some SMs get twice the work of others) but 1,024 of 64
@@ -798,7 +881,7 @@ int launch_step(ah_env* env, const ah_step_io* io, int K, cudaStream_t s) {
     const bool per_frame_any = io->reward || io->done || io->score || io->game_over;
     const bool per_frame_all = io->reward && io->done && io->score && io->game_over;
     const bool heavy = io->obs_state || io->obs_new_state || io->ring || env->cfg.friction || (io->obs_next && io->obs_next_per_frame) ||
-                       io->actions_out || io->probs_out || io->action_kind == AH_ACT_POLICY;
+                       io->actions_out || io->probs_out || io->action_kind == AH_ACT_POLICY || io->action_kind == AH_ACT_POLICY_MLP;
     int mode = ah::MODE_GENERIC;
     if (!heavy && per_frame_all && io->obs_next) mode = ah::MODE_LEAN;
     else if (!heavy && !per_frame_any) mode = ah::MODE_SIM;
@@ -808,6 +891,7 @@ int launch_step(ah_env* env, const ah_step_io* io, int K, cudaStream_t s) {
         case AH_ACT_CONTINUOUS: case AH_ACT_CONTINUOUS_REPEAT: act = 2; break;
         case AH_ACT_PHILOX: act = 3; break;
         case AH_ACT_POLICY: act = 4; break;
+        case AH_ACT_POLICY_MLP: act = 5; break;
         default: return AH_EINVAL;                            // AH_ACT_DISCRETE_PACKED4 is only valid with io->events
     }
 #define AH_LAUNCH(ACT_, MODE_) ah::step_kernel<R, ACT_, MODE_><<<grid, threads, 0, s>>>(a)
@@ -826,6 +910,9 @@ int launch_step(ah_env* env, const ah_step_io* io, int K, cudaStream_t s) {
     if (launched) {
     } else if (act == 4) {
         ah::step_kernel<R, 4, ah::MODE_GENERIC><<<grid, threads, 0, s>>>(a);
+    } else if (act == 5) {                                   // the activations array is sized for blocks of kPolThreads
+        const unsigned pg = (unsigned)((env->n + ah::kPolThreads - 1) / ah::kPolThreads);
+        ah::step_kernel<R, 5, ah::MODE_GENERIC><<<pg < (unsigned)max_blocks ? pg : (unsigned)max_blocks, ah::kPolThreads, 0, s>>>(a);
     } else if (act == 1) AH_LAUNCH_MODE(1); else if (act == 2) AH_LAUNCH_MODE(2); else AH_LAUNCH_MODE(3);
 #undef AH_LAUNCH_MODE
 #undef AH_LAUNCH
@@ -982,7 +1069,10 @@ int ah_step(ah_env* env, const ah_step_io* io, int K, void* stream) {
     if (!io || K < 1 || K > 4096) return AH_EINVAL;
     const int kind = io->action_kind;
     if (kind != AH_ACT_DISCRETE && kind != AH_ACT_CONTINUOUS && kind != AH_ACT_PHILOX && kind != AH_ACT_DISCRETE_REPEAT &&
-        kind != AH_ACT_CONTINUOUS_REPEAT && kind != AH_ACT_POLICY && kind != AH_ACT_DISCRETE_PACKED4) return AH_EINVAL;
+        kind != AH_ACT_CONTINUOUS_REPEAT && kind != AH_ACT_POLICY && kind != AH_ACT_DISCRETE_PACKED4 &&
+        kind != AH_ACT_POLICY_MLP) return AH_EINVAL;
+    if ((kind == AH_ACT_POLICY_MLP) != (io->policy != nullptr)) return AH_EINVAL;
+    if (io->actions_real_out && kind != AH_ACT_POLICY_MLP) return AH_EINVAL;
     if ((kind == AH_ACT_DISCRETE_PACKED4) != (io->events != nullptr)) return AH_EINVAL;   // the packed mode is all-or-nothing
     if (io->stats_bank != 0 && io->stats_bank != 1) return AH_EINVAL;
     if (io->env_first < 0 || io->env_count < 0 || io->env_first + io->env_count > env->n) return AH_EINVAL;
@@ -992,8 +1082,8 @@ int ah_step(ah_env* env, const ah_step_io* io, int K, void* stream) {
         if (io->reward || io->done || io->score || io->game_over || io->obs_state || io->obs_new_state || io->ring ||
             io->actions_out || io->probs_out || (io->obs_next && io->obs_next_per_frame) || env->cfg.friction) return AH_EINVAL;
     }
-    if (!aligned16(io->probs_out) || (io->probs_out && kind != AH_ACT_POLICY)) return AH_EINVAL;
-    if (kind != AH_ACT_PHILOX && !io->actions) return AH_EINVAL;
+    if ((io->probs_out && kind != AH_ACT_POLICY && kind != AH_ACT_POLICY_MLP) || (kind == AH_ACT_POLICY && !aligned16(io->probs_out))) return AH_EINVAL;
+    if (kind != AH_ACT_PHILOX && kind != AH_ACT_POLICY_MLP && !io->actions) return AH_EINVAL;
     if ((kind == AH_ACT_CONTINUOUS || kind == AH_ACT_CONTINUOUS_REPEAT) &&
         (reinterpret_cast<uintptr_t>(io->actions) & (env->dtype == AH_F32 ? 7u : 15u))) return AH_EINVAL;
     if (io->reset_table && (io->reset_table_len <= 0 || !aligned16(io->reset_table))) return AH_EINVAL;
@@ -1017,6 +1107,21 @@ int ah_actor_sample(ah_env* env, const float* d_weights, const void* d_obs, void
     cudaStream_t s = (cudaStream_t)stream;
     AH_DISPATCH(env, (ah::actor_sample_kernel<float><<<small_grid(env->n), 256, 0, s>>>(env->n, d_weights, (const float*)d_obs, (float*)d_probs, d_actions, greedy, env->seed, env->env_id0, env->blk)),
                 (ah::actor_sample_kernel<double><<<small_grid(env->n), 256, 0, s>>>(env->n, d_weights, (const double*)d_obs, (double*)d_probs, d_actions, greedy, env->seed, env->env_id0, env->blk)));
+    AH_LAUNCH_RC(env);
+}
+
+int ah_policy_act(ah_env* env, const ah_policy* policy, const void* d_obs, const void* d_values_in, int8_t* d_actions,
+                  void* d_actions_real, void* d_values_out, void* stream) {
+    if (!env || !policy || (!d_obs && !d_values_in) || (d_obs && !aligned16(d_obs))) return AH_EINVAL;
+    ah::PolicyDev pd;
+    const int prc = make_policy_dev(policy, &pd, d_values_in == nullptr);
+    if (prc != AH_OK) return prc;
+    if (policy->head == AH_HEAD_CONTINUOUS ? !d_actions_real : !d_actions) return AH_EINVAL;
+    DeviceGuard g(env->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)((env->n + ah::kPolThreads - 1) / ah::kPolThreads);
+    AH_DISPATCH(env, (ah::policy_act_kernel<float><<<grid, ah::kPolThreads, 0, s>>>(env->n, pd, (const float*)d_obs, (const float*)d_values_in, d_actions, (float*)d_actions_real, (float*)d_values_out, env->seed, env->env_id0, env->blk)),
+                (ah::policy_act_kernel<double><<<grid, ah::kPolThreads, 0, s>>>(env->n, pd, (const double*)d_obs, (const double*)d_values_in, d_actions, (double*)d_actions_real, (double*)d_values_out, env->seed, env->env_id0, env->blk)));
     AH_LAUNCH_RC(env);
 }
 

@@ -1,0 +1,225 @@
+// On-device action selection for ANY small dense policy (include/ah_b200.h: ah_policy): the hand-off the reference
+// does on the host every frame -- Agent.get_action (lib/agents/agent.py:42-48) -> model.predict -> exploration strategy
+// (lib/exploration/strategies.py, lib/exploration/random.py) -> Agent.move -- evaluated per env inside a kernel.
+//
+//   network   up to 4 dense layers, widths <= 32, relu / tanh / linear, BatchNorm folded by the caller.  Covers the
+//             reference's nets: PPO discrete actor 8-4-6-4-4 softmax and continuous actor 8-6-6-4-2 tanh
+//             (lib/agents/ppo/model.py:56-110), A2C actor and DDQN net 8-8-4 softmax (a2c/model.py:50-60,
+//             ddqn/model.py:39-53), the dueling Q-net 8-32-(8|8)-(1|4) as a block-structured chain
+//             (dueling/model.py:50-66).  (C51's 51-atom heads exceed the width; it goes through ah_policy_act with
+//             head values computed by the caller's network.)
+//   head      softmax probabilities | Q-values | dueling v + a - mean(a) | continuous mean
+//   select    SoftmaxPolicy / argmax / EpsilonGreedy / BoltzmannQPolicy / MaxBoltzmannQPolicy        strategies.py:7-123
+//             GaussianWhiteNoiseProcess / OrnsteinUhlenbeckProcess added to the continuous mean      random.py:11-67
+//
+// Evaluation: the weights (transposed, outputs padded to 4) are staged in shared memory once per block and read as
+// warp-uniform LDS.128 broadcasts; a thread's activations live in its own column of a [32][T] shared array (no bank
+// conflicts, no barriers: nobody else touches the column); four outputs are accumulated per pass over the inputs:
+// 1 LDS.128 + 1 LDS + 4 FFMA per 4 multiply-adds.
+//
+// Randomness: counter-based Philox keyed (seed, global env id), counter = frame, streams 2 (u0) and 3 (u1) -- the same
+// draw whether the policy runs in the step kernel (one launch per rollout) or frame by frame (ah_policy_act).
+#pragma once
+
+namespace ah {
+
+constexpr int kPolThreads = 128;                       // block size of every kernel that evaluates a policy
+constexpr int kPolMaxW = AH_POLICY_MAX_WIDTH;
+constexpr int kPolMaxFloats = (8 * kPolMaxW + kPolMaxW) + 3 * (kPolMaxW * kPolMaxW + kPolMaxW);
+
+struct PolicyDev {                                      // by value in the kernel arguments
+    int n_layers, width[5], act[4], w_off[4], b_off[4], n_floats;
+    int head, select, n_actions;
+    float eps0, eps_delta, eps_final; int observe, max_decrements;
+    float inv_tau, clip_lo, clip_hi;
+    float mu, sigma0, sigma_min, sigma_m, theta, dt, sqrt_dt;
+    const float* weights;
+    float* noise_state;                                 // [n][2], AH_SELECT_OU only
+};
+
+__device__ __forceinline__ void policy_stage(const PolicyDev& P, float* sw) {
+    for (int t = threadIdx.x; t < P.n_floats; t += blockDim.x) sw[t] = P.weights[t];
+}
+
+__device__ __forceinline__ float policy_activate(float v, int act) {
+    if (act == AH_ACTV_RELU) return fmaxf(v, 0.0f);
+    if (act == AH_ACTV_TANH) return tanhf(v);
+    return v;
+}
+
+// x[8] -> y[8] (the first width[n_layers] outputs of the last layer, zero-filled)
+__device__ __forceinline__ void policy_forward(const PolicyDev& P, const float* __restrict__ sw, float* hs, const float (&x)[8],
+                                               float (&y)[8]) {
+    const int T = kPolThreads, tid = threadIdx.x;
+    float* in = hs;
+    float* out = hs + kPolMaxW * T;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) in[c * T + tid] = x[c];
+    for (int l = 0; l < P.n_layers; ++l) {
+        const int win = P.width[l], outp = (P.width[l + 1] + 3) & ~3, act = P.act[l];
+        const float* W = sw + P.w_off[l];
+        const float* B = sw + P.b_off[l];
+        for (int j = 0; j < outp; j += 4) {
+            float4 acc = *reinterpret_cast<const float4*>(B + j);
+            for (int c = 0; c < win; ++c) {
+                const float4 w = *reinterpret_cast<const float4*>(W + c * outp + j);
+                const float h = in[c * T + tid];
+                acc.x = fmaf(w.x, h, acc.x); acc.y = fmaf(w.y, h, acc.y);
+                acc.z = fmaf(w.z, h, acc.z); acc.w = fmaf(w.w, h, acc.w);
+            }
+            out[(j + 0) * T + tid] = policy_activate(acc.x, act);
+            out[(j + 1) * T + tid] = policy_activate(acc.y, act);
+            out[(j + 2) * T + tid] = policy_activate(acc.z, act);
+            out[(j + 3) * T + tid] = policy_activate(acc.w, act);
+        }
+        float* t = in; in = out; out = t;
+    }
+    const int wl = P.width[P.n_layers];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) y[q] = q < wl ? in[q * T + tid] : 0.0f;
+}
+
+// head: y -> v[0..A) = probabilities (softmax head) or Q-values (values / dueling head); continuous: v[0..1] = mean
+__device__ __forceinline__ void policy_head(const PolicyDev& P, const float (&y)[8], float (&v)[8]) {
+    const int A = P.n_actions;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = 0.0f;
+    if (P.head == AH_HEAD_SOFTMAX) {
+        float m = y[0];
+#pragma unroll
+        for (int q = 1; q < 8; ++q) if (q < A) m = fmaxf(m, y[q]);
+        float s = 0.0f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) if (q < A) { v[q] = __expf(y[q] - m); s += v[q]; }
+        const float inv = 1.0f / s;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] *= inv;
+    } else if (P.head == AH_HEAD_DUELING) {             // q = v + a - mean(a)      dueling/model.py:58-66
+        float mean = 0.0f;
+#pragma unroll
+        for (int q = 1; q < 8; ++q) if (q <= A) mean += y[q];
+        mean /= (float)A;
+#pragma unroll
+        for (int q = 0; q < 7; ++q) if (q < A) v[q] = y[0] + (y[q + 1] - mean);
+    } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = y[q];
+    }
+}
+
+__device__ __forceinline__ int policy_argmax(const float (&v)[8], int A) {       // np.argmax: the first maximum
+    int best = 0; float bv = v[0];
+#pragma unroll
+    for (int q = 1; q < 8; ++q) if (q < A && v[q] > bv) { bv = v[q]; best = q; }
+    return best;
+}
+
+// np.random.choice(A, p): the first index whose cumulative probability exceeds u
+__device__ __forceinline__ int policy_choice(const float (&p)[8], int A, float u) {
+    float c = 0.0f; int act = A - 1;
+    bool found = false;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        if (q < A) { c += p[q]; if (!found && u < c) { act = q; found = true; } }
+    }
+    return act;
+}
+
+// EpsilonGreedy.decrease (strategies.py:39-43): epsilon after the step() call number t (1-based)
+__device__ __forceinline__ float policy_epsilon(const PolicyDev& P, unsigned long long t) {
+    unsigned long long m = P.observe > 0 ? t / (unsigned long long)P.observe : 0ull;
+    if (m > (unsigned long long)P.max_decrements) m = (unsigned long long)P.max_decrements;
+    return P.eps0 - (float)m * P.eps_delta;
+}
+
+struct PolicyAction { int ia; float ax, ay; };
+
+// One action for one env.  `f` = the global frame index (frames played before this one); v = policy_head's output.
+__device__ __forceinline__ PolicyAction policy_select(const PolicyDev& P, const float (&v)[8], uint64_t seed, uint64_t env_id,
+                                                      unsigned long long f, int64_t i) {
+    PolicyAction r; r.ia = -1; r.ax = 0.0f; r.ay = 0.0f;
+    const int A = P.n_actions, sel = P.select;
+    float u0 = 0.0f, u1 = 0.0f;
+    if (sel != AH_SELECT_GREEDY) {
+        u0 = sample_uniform(sample_block(seed, env_id, f), f);
+        if (sel != AH_SELECT_SAMPLE && sel != AH_SELECT_BOLTZMANN) u1 = sample_uniform(sample_block2(seed, env_id, f), f);
+    }
+    if (P.head == AH_HEAD_CONTINUOUS) {
+        r.ax = v[0]; r.ay = v[1];
+        if (sel == AH_SELECT_GAUSSIAN || sel == AH_SELECT_OU) {
+            // two standard normals from (u0, u1): Box-Muller
+            const float rad = sqrtf(-2.0f * __logf(1.0f - u0)), ang = 6.283185307179586f * u1;
+            const float z0 = rad * __cosf(ang), z1 = rad * __sinf(ang);
+            const float sigma = fmaxf(P.sigma_min, fmaf(P.sigma_m, (float)f, P.sigma0));      // random.py:26-28
+            if (sel == AH_SELECT_GAUSSIAN) {                                                     // random.py:38-41
+                r.ax += fmaf(sigma, z0, P.mu); r.ay += fmaf(sigma, z1, P.mu);
+            } else {                                                                             // random.py:56-63
+                float2 xp = reinterpret_cast<float2*>(P.noise_state)[i];
+                xp.x = xp.x + P.theta * (P.mu - xp.x) * P.dt + sigma * P.sqrt_dt * z0;
+                xp.y = xp.y + P.theta * (P.mu - xp.y) * P.dt + sigma * P.sqrt_dt * z1;
+                reinterpret_cast<float2*>(P.noise_state)[i] = xp;
+                r.ax += xp.x; r.ay += xp.y;
+            }
+        }
+        return r;
+    }
+    if (sel == AH_SELECT_SAMPLE) { r.ia = policy_choice(v, A, u0); return r; }              // strategies.py:17-19
+    if (sel == AH_SELECT_GREEDY) { r.ia = policy_argmax(v, A); return r; }
+    float b[8];                                                                             // Boltzmann law (strategies.py:73-75)
+    if (sel == AH_SELECT_BOLTZMANN || sel == AH_SELECT_MAX_BOLTZMANN) {
+        float s = 0.0f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { b[q] = q < A ? __expf(fminf(fmaxf(v[q] * P.inv_tau, P.clip_lo), P.clip_hi)) : 0.0f; s += b[q]; }
+        const float inv = 1.0f / s;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) b[q] *= inv;
+    }
+    if (sel == AH_SELECT_BOLTZMANN) { r.ia = policy_choice(b, A, u0); return r; }
+    const float eps = policy_epsilon(P, f + 1ull);                                          // self.t += 1; decrease()
+    if (u0 < eps) {
+        if (sel == AH_SELECT_EPS_GREEDY) { int a = (int)(u1 * (float)A); r.ia = a < A ? a : A - 1; }   // np.random.randint(0, A)
+        else r.ia = policy_choice(b, A, u1);
+    } else {
+        r.ia = policy_argmax(v, A);
+    }
+    return r;
+}
+
+// ---- stand-alone kernel: obs [n][8] -> action (+ head values), one frame (ah_policy_act)
+template <typename R>
+__global__ void __launch_bounds__(kPolThreads) policy_act_kernel(int64_t n, PolicyDev P, const R* __restrict__ obs, const R* __restrict__ values_in,
+                                                                 int8_t* __restrict__ actions, R* __restrict__ actions_real,
+                                                                 R* __restrict__ values_out, uint64_t seed, uint64_t env_id0,
+                                                                 const DevBlock* blk) {
+    __shared__ __align__(16) float sw[kPolMaxFloats];
+    __shared__ float hs[2 * kPolMaxW * kPolThreads];
+    if (!values_in) policy_stage(P, sw);
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float v[8];
+    if (values_in) {                                     // the caller's own network produced the head values
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = q < P.n_actions ? (float)values_in[i * P.n_actions + q] : 0.0f;
+    } else {
+        using V = typename Vec4T<R>::type;
+        const V o0 = reinterpret_cast<const V*>(obs)[2 * i], o1 = reinterpret_cast<const V*>(obs)[2 * i + 1];
+        const float x[8] = {(float)o0.x, (float)o0.y, (float)o0.z, (float)o0.w, (float)o1.x, (float)o1.y, (float)o1.z, (float)o1.w};
+        float y[8];
+        policy_forward(P, sw, hs, x, y);
+        policy_head(P, y, v);
+    }
+    const PolicyAction a = policy_select(P, v, seed, env_id0 + (uint64_t)i, blk->frame, i);
+    if (P.head == AH_HEAD_CONTINUOUS) {
+        if (actions_real) { actions_real[2 * i] = (R)a.ax; actions_real[2 * i + 1] = (R)a.ay; }
+    } else if (actions) {
+        actions[i] = (int8_t)a.ia;
+    }
+    if (values_out) {
+        const int nv = P.head == AH_HEAD_CONTINUOUS ? 2 : P.n_actions;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) if (q < nv) values_out[i * nv + q] = (R)v[q];
+    }
+}
+
+}  // namespace ah

@@ -62,6 +62,11 @@ __device__ __forceinline__ Philox4 sample_block(uint64_t seed, uint64_t env_id, 
     return philox4x32_10((uint32_t)env_id, (uint32_t)(env_id >> 32), (uint32_t)(frame >> 2), 2u ^ ((uint32_t)(frame >> 34) << 8),
                          (uint32_t)seed, (uint32_t)(seed >> 32));
 }
+// stream 3: a second, independent uniform per frame (epsilon-greedy's random action, Box-Muller's angle)
+__device__ __forceinline__ Philox4 sample_block2(uint64_t seed, uint64_t env_id, unsigned long long frame) {
+    return philox4x32_10((uint32_t)env_id, (uint32_t)(env_id >> 32), (uint32_t)(frame >> 2), 3u ^ ((uint32_t)(frame >> 34) << 8),
+                         (uint32_t)seed, (uint32_t)(seed >> 32));
+}
 __device__ __forceinline__ float sample_uniform(const Philox4& b, unsigned long long frame) {
     const uint32_t w = (uint32_t)(frame & 3u);
     const uint32_t v = w == 0 ? b.x : w == 1 ? b.y : w == 2 ? b.z : b.w;

@@ -26,7 +26,8 @@ from .exceptions import InvalidAgentError
 
 _AGENTS = {"robot": _capi.AH_AGENT_ROBOT, "human": _capi.AH_AGENT_HUMAN, "computer": _capi.AH_AGENT_COMPUTER}
 
-STEP_FIELDS = ("obs_state", "obs_new_state", "reward", "done", "score", "game_over", "obs_next", "actions", "probs", "events")
+STEP_FIELDS = ("obs_state", "obs_new_state", "reward", "done", "score", "game_over", "obs_next", "actions", "probs", "events",
+               "actions_real")
 
 
 def pack_actions(actions: torch.Tensor) -> torch.Tensor:
@@ -61,6 +62,7 @@ class StepOutputs:
     obs_next: Optional[torch.Tensor] = None        # real [N,8] or [K,N,8]: the next frame's policy input
     actions: Optional[torch.Tensor] = None         # i8   [K,N]    the discrete actions applied (Philox / in-kernel policy)
     probs: Optional[torch.Tensor] = None           # real [K,N,4]  the in-kernel actor's distribution (policy mode only)
+    actions_real: Optional[torch.Tensor] = None    # real [K,N,2]  the continuous actions a device policy chose
     events: Optional[torch.Tensor] = None          # u8   [ceil(K/4),N,4]  packed rollout mode: reward, done, score and
                                                    #               game_over of a frame in ONE byte (see unpack_events)
 
@@ -342,7 +344,7 @@ class BatchedAirHockey:
 
     # ------------------------------------------------------------------ the fused frame
     def make_outputs(self, K: int = 1, fields: Sequence[str] = ("reward", "done", "score", "game_over", "obs_next"),
-                     obs_next_per_frame: bool = False) -> StepOutputs:
+                     obs_next_per_frame: bool = False, n_values: int = 4) -> StepOutputs:
         """Preallocate output tensors for ``step`` (reuse them across steps: nothing is allocated per step)."""
         o = StepOutputs()
         for f in fields:
@@ -366,7 +368,9 @@ class BatchedAirHockey:
         if "actions" in fields:
             o.actions = torch.empty(K, self.n, dtype=torch.int8, device=self.device)
         if "probs" in fields:
-            o.probs = torch.empty(K, self.n, 4, **r)
+            o.probs = torch.empty(K, self.n, n_values, **r)     # a device policy's head values: n_actions (or 2: continuous)
+        if "actions_real" in fields:
+            o.actions_real = torch.empty(K, self.n, 2, **r)
         if "events" in fields:
             o.events = torch.empty((K + 3) // 4, self.n, 4, dtype=torch.uint8, device=self.device)
         return o
@@ -391,7 +395,7 @@ class BatchedAirHockey:
                   out: Optional[StepOutputs] = None, reset_table: Optional[torch.Tensor] = None,
                   ring: Optional[ReplayRing] = None, collect_stats: bool = True,
                   policy_weights: Optional[torch.Tensor] = None, env_range: Optional[Sequence[int]] = None,
-                  stats_bank: int = 0) -> "StepPlan":
+                  stats_bank: int = 0, policy=None) -> "StepPlan":
         """Validate the arguments of one step and freeze them into a ``StepPlan`` that ``launch`` can enqueue any number
         of times (the tensors are referenced, not copied: replays read / write the same memory).
 
@@ -402,6 +406,9 @@ class BatchedAirHockey:
                  real [K,N,2]        -> one continuous action per frame ([N,2] when K == 1 or ``repeat``)
         repeat:  apply the single given action to all K frames (frame-skip)
         out:     preallocated ``StepOutputs`` (see ``make_outputs``); default: reward/done/score/game_over/obs_next
+        policy:  a ``policy.DevicePolicy``: closed loop with ANY small dense policy + exploration strategy evaluated in the
+                 kernel every frame (``actions`` must be None); ``out.actions`` (discrete) / ``out.actions_real``
+                 (continuous head) / ``out.probs`` (head values, [K,N,n_actions]) receive what it did
         env_range: (first, count) -- packed mode only: step just that slice of the envs (tensor shapes stay those of the
                  full N), so one step can be issued as disjoint slices on different streams (host.InterleavedStepper)
         policy_weights: float32 [114] device tensor (``rollout.FusedActor.weights``): closed loop -- every frame the
@@ -411,7 +418,14 @@ class BatchedAirHockey:
         if out is None:
             out = self.make_outputs(K)
         io = _capi.AhStepIO()
-        if policy_weights is not None:
+        if policy is not None:
+            if actions is not None or policy_weights is not None:
+                raise ValueError("give either actions, policy_weights or policy")
+            if policy.module is None:
+                raise ValueError("a selection-only DevicePolicy has no network to run in the kernel (use policy_act)")
+            io.action_kind = _capi.AH_ACT_POLICY_MLP
+            io.policy = C.pointer(policy.c)
+        elif policy_weights is not None:
             if actions is not None:
                 raise ValueError("give either actions or policy_weights")
             self._check_tensor(policy_weights, (_capi.AH_ACTOR_NWEIGHTS,), torch.float32, "policy_weights")
@@ -461,9 +475,14 @@ class BatchedAirHockey:
         if out.actions is not None:
             io.actions_out = self._check_tensor(out.actions, (K, self.n), torch.int8, "actions").data_ptr()
         if out.probs is not None:
-            if policy_weights is None:
+            if policy_weights is None and policy is None:
                 raise ValueError("out.probs is only produced in policy mode")
-            io.probs_out = self._check_tensor(out.probs, (K, self.n, 4), r, "probs").data_ptr()
+            nv = 4 if policy is None else policy.n_actions
+            io.probs_out = self._check_tensor(out.probs, (K, self.n, nv), r, "probs").data_ptr()
+        if out.actions_real is not None:
+            if policy is None or not policy.continuous:
+                raise ValueError("out.actions_real is only produced by a continuous device policy")
+            io.actions_real_out = self._check_tensor(out.actions_real, (K, self.n, 2), r, "actions_real").data_ptr()
         if out.events is not None:
             io.events = self._check_tensor(out.events, ((K + 3) // 4, self.n, 4), torch.uint8, "events").data_ptr()
         io.collect_stats = int(collect_stats)
@@ -473,10 +492,39 @@ class BatchedAirHockey:
         if ring is not None:
             if ring.n != self.n or ring.state.dtype != self.dtype or ring.state.device != self.device:
                 raise ValueError("ring does not match this environment")
-            if ring.continuous != (io.action_kind in (_capi.AH_ACT_CONTINUOUS, _capi.AH_ACT_CONTINUOUS_REPEAT)):
+            if ring.continuous != (io.action_kind in (_capi.AH_ACT_CONTINUOUS, _capi.AH_ACT_CONTINUOUS_REPEAT)
+                                   or (policy is not None and policy.continuous)):
                 raise ValueError("ring action layout (discrete/continuous) does not match the actions given")
             io.ring = C.pointer(ring._c)
-        return StepPlan(io, C.byref(io), int(K), out, (actions, reset_table, ring, policy_weights))
+        return StepPlan(io, C.byref(io), int(K), out, (actions, reset_table, ring, policy_weights, policy))
+
+    def policy_act(self, policy, obs: Optional[torch.Tensor] = None, values: Optional[torch.Tensor] = None,
+                   actions: Optional[torch.Tensor] = None, values_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """One action per env from a ``policy.DevicePolicy`` at the env's current frame (``ah_policy_act``): the network is
+        evaluated on ``obs`` (real [N,8]; default: the current observation), or -- for ANY torch network -- the head values
+        it produced are passed as ``values`` (real [N,n_actions]) and only the exploration strategy runs on the device
+        (replaces ``torch.multinomial`` / ``argmax`` + host-side epsilon schedules).  Returns int8 [N] (discrete) or real
+        [N,2] (continuous head); ``values_out`` (real [N,n_actions]) receives the head values."""
+        if values is None and obs is None:
+            obs = self.get_state("robot")
+        if obs is not None:
+            self._check_tensor(obs, (self.n, 8), self.dtype, "obs")
+        if values is not None:
+            self._check_tensor(values, (self.n, policy.n_actions), self.dtype, "values")
+        if actions is None:
+            actions = (torch.empty(self.n, 2, dtype=self.dtype, device=self.device) if policy.continuous
+                       else torch.empty(self.n, dtype=torch.int8, device=self.device))
+        self._check_tensor(actions, (self.n, 2) if policy.continuous else (self.n,),
+                           self.dtype if policy.continuous else torch.int8, "actions")
+        if values_out is not None:
+            self._check_tensor(values_out, (self.n, policy.n_actions), self.dtype, "values_out")
+        _capi.check(self._lib.ah_policy_act(self._h, policy.ref(), None if obs is None else obs.data_ptr(),
+                                            None if values is None else values.data_ptr(),
+                                            None if policy.continuous else actions.data_ptr(),
+                                            actions.data_ptr() if policy.continuous else None,
+                                            None if values_out is None else values_out.data_ptr(), self._stream()),
+                    "ah_policy_act", self._h)
+        return actions
 
     # ------------------------------------------------------------------ statistics, counters, checkpoints
     def stats_tensor(self, clear: bool = False, out: Optional[torch.Tensor] = None, bank: int = 0) -> torch.Tensor:

@@ -92,12 +92,28 @@ class RolloutCollector:
 
     def __init__(self, env: BatchedAirHockey, T: int, policy: Optional[Callable[[torch.Tensor], torch.Tensor]] = None,
                  action_size: int = 4, use_graph: bool = True, seed: int = 0, fused_actor: bool = True,
-                 single_launch: Optional[bool] = None):
+                 single_launch: Optional[bool] = None, device_policy=None, device_select: bool = True):
+        """policy:        any callable obs [N,8] -> action probabilities [N,A] (a torch module); default: ``ActorMLP``
+        device_policy: a ``policy.DevicePolicy`` exported from a torch module: the WHOLE T-frame closed loop (network,
+                       exploration strategy, physics, rewards, resets) runs in ONE launch (AH_ACT_POLICY_MLP)
+        device_select: for a torch ``policy`` that cannot be exported, sample the action from its probabilities with
+                       ``ah_policy_act`` (Philox, on the device) instead of ``torch.multinomial`` + dtype copies"""
         self.env, self.T, self.A = env, int(T), int(action_size)
         n, dt, dev = env.n, env.dtype, env.device
+        self.device_policy = device_policy
+        if device_policy is not None:
+            if device_policy.continuous:
+                raise ValueError("RolloutCollector collects discrete-action rollouts")
+            self.A = action_size = device_policy.n_actions
+            policy = policy if policy is not None else device_policy.module
         self.policy = policy if policy is not None else ActorMLP(8, action_size).to(device=dev, dtype=dt)
+        self._selector = None
+        if device_select and device_policy is None:
+            from .policy import DevicePolicy
+            self._selector = DevicePolicy(None, dev, head="values", select="sample", n_actions=action_size)
         # the reference-shaped actor runs fused with the sampling in one kernel; any other callable goes through torch
-        self.fused = FusedActor(self.policy, env) if (fused_actor and isinstance(self.policy, ActorMLP)) else None
+        self.fused = (FusedActor(self.policy, env)
+                      if (fused_actor and device_policy is None and isinstance(self.policy, ActorMLP)) else None)
         self.obs = torch.zeros(T + 1, n, 8, dtype=dt, device=dev)
         self.actions = torch.zeros(T, n, dtype=torch.int8, device=dev)
         self.rewards = torch.zeros(T, n, dtype=dt, device=dev)
@@ -114,7 +130,7 @@ class RolloutCollector:
         # kernel launch with the env state in registers (BatchedAirHockey.step(policy_weights=...)); needs the fused actor
         if single_launch is None:                 # default: the fastest path the policy allows
             single_launch = self.fused is not None
-        self.single_launch = bool(single_launch and self.fused is not None)
+        self.single_launch = bool((single_launch and self.fused is not None) or device_policy is not None)
         self._out_all = StepOutputs(reward=self.rewards, done=self.dones, score=self.scores, game_over=self.game_over,
                                     obs_next=self.obs[1:], actions=self.actions, probs=self.probs)
         self.use_graph = use_graph and not self.single_launch
@@ -130,8 +146,11 @@ class RolloutCollector:
                     continue
                 p = self.policy(self.obs[t])
                 self.probs[t].copy_(p)
-                a = torch.multinomial(p.float(), 1, generator=self.gen).squeeze(1)
-                self.actions[t].copy_(a)                         # int64 -> int8, into the rollout tensor
+                if self._selector is not None:                   # SoftmaxPolicy on the device, straight into the rollout
+                    self.env.policy_act(self._selector, values=self.probs[t], actions=self.actions[t])
+                else:
+                    a = torch.multinomial(p.float(), 1, generator=self.gen).squeeze(1)
+                    self.actions[t].copy_(a)                     # int64 -> int8, into the rollout tensor
                 self.env.step(self.actions[t], K=1, out=self._outs[t], collect_stats=collect_stats)
 
     def _capture(self) -> None:
@@ -158,7 +177,10 @@ class RolloutCollector:
         if self.single_launch:
             if self._ran:
                 self.obs[0].copy_(self.obs[self.T])
-            self.env.step(None, K=self.T, out=self._out_all, policy_weights=self.fused.weights)
+            if self.device_policy is not None:
+                self.env.step(None, K=self.T, out=self._out_all, policy=self.device_policy)
+            else:
+                self.env.step(None, K=self.T, out=self._out_all, policy_weights=self.fused.weights)
         elif self.use_graph:
             if self._graph is None:
                 self._capture()

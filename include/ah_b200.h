@@ -72,6 +72,8 @@ enum {
     AH_ACT_POLICY = 6,       /* closed loop: every frame the reference's discrete PPO actor is evaluated IN the  */
                              /* kernel on the env's current observation and an action is sampled from its       */
                              /* softmax (see ah_actor_sample); `actions` = device float[AH_ACTOR_NWEIGHTS]       */
+    AH_ACT_POLICY_MLP = 8,   /* closed loop with ANY small dense policy: ah_step_io.policy (an ah_policy) is evaluated IN   */
+                             /* the kernel every frame and its exploration strategy picks the action; `actions` unused  */
     AH_ACT_DISCRETE_PACKED4 = 7 /* uint8 [ceil(K/4)][n][4], "quad-major": byte j of word (q, i) is env i's action of */
                              /* frame 4q + j (same action codes as AH_ACT_DISCRETE; 32-bit aligned).  The input     */
                              /* format of the packed rollout mode (ah_step_io.events)                               */
@@ -112,6 +114,47 @@ enum {
                                   /* exact for the run                                                                     */
     AH_NSTATS = 20                /* 17-19 reserved */
 };
+
+/* ---- a small dense policy + exploration strategy, evaluated on the device (ah_policy_act, AH_ACT_POLICY_MLP).
+ * Replaces the per-frame host hand-off Agent.get_action -> model.predict -> exploration strategy
+ * (lib/agents/agent.py:42-48, lib/exploration/strategies.py, lib/exploration/random.py). ---- */
+#define AH_POLICY_MAX_LAYERS 4
+#define AH_POLICY_MAX_WIDTH 32
+enum { AH_ACTV_LINEAR = 0, AH_ACTV_RELU = 1, AH_ACTV_TANH = 2 };
+enum {
+    AH_HEAD_SOFTMAX = 0,     /* last layer -> softmax probabilities (PPO / A2C actors, the reference's DDQN net)       */
+    AH_HEAD_VALUES = 1,      /* last layer = Q-values (or probabilities) as they are                                   */
+    AH_HEAD_DUELING = 2,     /* last layer = (v, a_0 .. a_{A-1}); q = v + a - mean(a)   lib/agents/dueling/model.py:50-66 */
+    AH_HEAD_CONTINUOUS = 3   /* last layer = (mx, my): the continuous action before noise  lib/agents/ppo/model.py:84-110 */
+};
+enum {
+    AH_SELECT_SAMPLE = 0,        /* SoftmaxPolicy: np.random.choice(A, p)                 strategies.py:7-19   */
+    AH_SELECT_GREEDY = 1,        /* np.argmax (what every agent does when not training); continuous: the mean  */
+    AH_SELECT_EPS_GREEDY = 2,    /* EpsilonGreedy, with its epsilon schedule              strategies.py:22-56  */
+    AH_SELECT_BOLTZMANN = 3,     /* BoltzmannQPolicy                                      strategies.py:59-76  */
+    AH_SELECT_MAX_BOLTZMANN = 4, /* MaxBoltzmannQPolicy                                   strategies.py:79-123 */
+    AH_SELECT_GAUSSIAN = 5,      /* continuous: mean + GaussianWhiteNoiseProcess.sample() random.py:31-41      */
+    AH_SELECT_OU = 6             /* continuous: mean + OrnsteinUhlenbeckProcess.sample()  random.py:44-67      */
+};
+typedef struct ah_policy {
+    int32_t n_layers;            /* 1 .. AH_POLICY_MAX_LAYERS dense layers                                          */
+    int32_t width[5];            /* width[0] = 8 (the observation), width[l] = outputs of layer l, each <= 32       */
+    int32_t activation[4];       /* AH_ACTV_* per layer (fold BatchNorm into the neighbouring layer)               */
+    int32_t head, select, n_actions;   /* n_actions <= 7; the last width is n_actions (softmax / values),          */
+                                 /* n_actions + 1 (dueling) or 2 (continuous)                                       */
+    /* epsilon schedule (strategies.py:31-43): epsilon starts at `epsilon`; on step() call t = 1, 2, ... it is lowered */
+    /* by (initial_epsilon - final_epsilon) / explore whenever t % observe == 0 and epsilon > final_epsilon            */
+    float epsilon, initial_epsilon, final_epsilon;
+    int32_t observe, explore;
+    float tau, clip_lo, clip_hi; /* Boltzmann: exp(clip(q / tau, clip_lo, clip_hi))        strategies.py:66-75      */
+    /* noise (random.py:11-67): sigma(t) = max(sigma_min, sigma - (sigma - sigma_min) * t / n_steps_annealing);    */
+    /* sigma_min < 0 means "no annealing" (the reference's sigma_min=None)                                          */
+    float mu, sigma, sigma_min; int32_t n_steps_annealing;
+    float theta, dt;             /* Ornstein-Uhlenbeck                                                               */
+    const float* weights;        /* device float[]: per layer Wt[in][outp] (TRANSPOSED, outputs zero-padded to a     */
+                                 /* multiple of 4 = outp) followed by b[outp]; 16-byte aligned                       */
+    float* noise_state;          /* device float [n][2]: the OU process' x_prev per env (AH_SELECT_OU), else NULL    */
+} ah_policy;
 
 /* ---- configuration (flags only; the physical constants of environment/config.py are compile-time) ---- */
 typedef struct ah_config {
@@ -165,6 +208,11 @@ typedef struct ah_step_io {
      * other per-frame outputs (reward, done, score, game_over, obs_state, obs_new_state, per-frame obs_next, ring,
      * actions_out, probs_out) and the friction flag; obs_next [n][8] stays available. */
     uint8_t* events;
+    /* AH_ACT_POLICY_MLP: the policy to evaluate (host struct; its weights are a device pointer), and where the continuous
+     * actions it chose go (real [K][n][2], nullable; discrete ones go to actions_out, head values to probs_out as
+     * real [K][n][n_actions], or [K][n][2] for the continuous head) */
+    const struct ah_policy* policy;
+    void* actions_real_out;
     /* Sub-range launch (packed mode only): step only the envs [env_first, env_first + env_count) of the bound arrays;
      * env_count == 0 means all n.  Array shapes and strides stay those of the full n, so a caller can split one step
      * into disjoint ranges on DIFFERENT streams: the tail of one range's launch then overlaps the head of the next
@@ -226,6 +274,14 @@ int ah_step(ah_env* env, const ah_step_io* io, int K, void* stream);
  * with the BatchNorm already folded into W2/b2.  d_probs (real [n][4], PPO's `old_prediction`) may be NULL. */
 int ah_actor_sample(ah_env* env, const float* d_weights, const void* d_obs, void* d_probs, int8_t* d_actions,
                     int greedy, void* stream);
+
+/* The generic form of ah_actor_sample: evaluate `policy` on obs real [n][8] -- or, when d_values_in (real
+ * [n][n_actions]) is given, take the head values from the caller's own network -- and select one action per env with
+ * the policy's exploration strategy, at the env's current frame (random draws as in AH_ACT_POLICY_MLP).  Outputs:
+ * d_actions int8 [n] (discrete heads) or d_actions_real real [n][2] (continuous head); d_values_out (nullable) receives
+ * the head values (probabilities / Q-values / mean).  The caller advances time with ah_step. */
+int ah_policy_act(ah_env* env, const ah_policy* policy, const void* d_obs, const void* d_values_in, int8_t* d_actions,
+                  void* d_actions_real, void* d_values_out, void* stream);
 
 /* Compact, lossless host-transfer encoding of one step's results (for callers that consume them on the HOST, where
  * PCIe, not the kernel, is the bound).  Inputs are the device outputs of ah_step:

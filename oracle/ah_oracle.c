@@ -489,6 +489,11 @@ int orc_puck_in_goal(double gx, double gy, double px, double py) {              
     return fabs(gx - px) < 2 * PUCK_R && fabs(gy - py) < 95;
 }
 /* which: 0 generic, 1 robot, 2 opponent (mallet.py:33-44) */
+void orc_friction_on_puck(double* dxdy) {                                         /* puck.py:73-88 */
+    body_t p; p.x = p.y = 0; p.dx = dxdy[0]; p.dy = dxdy[1];
+    friction_on_puck(&p);
+    dxdy[0] = p.dx; dxdy[1] = p.dy;
+}
 void orc_mallet_update(int which, double* xydxdy) {
     body_t m = {xydxdy[0], xydxdy[1], xydxdy[2], xydxdy[3]};
     double lx, ly;

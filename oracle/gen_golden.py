@@ -167,15 +167,57 @@ def gen_init_frame(seed=606, n=8, T=80):
                         reward=ref["reward"].astype(np.int8), score=ref["score"], done=ref["done"], **_header(seed))
 
 
+def gen_friction(seed=707, n=24, T=150):
+    """Pins the opt-in friction flag to the reference's OWN (dead) ``Puck.friction_on_puck`` (environment/puck.py:73-88):
+    (1) the function itself on a table of velocities around its +-1 thresholds, (2) a trajectory of the live reference
+    with that function hooked in immediately before ``Puck.limit_puck_speed`` -- the place ``ah_config.friction`` and
+    the oracle's ``friction`` switch apply it (every sub-update, airhockey.py:117)."""
+    refshim.install()
+    from environment.puck import Puck
+    rng = np.random.default_rng(seed)
+    v = np.concatenate([rng.uniform(-12, 12, (400, 2)),
+                        np.array([[1.0, 1.0], [-1.0, -1.0], [1.5, -1.5], [-1.25, 1.25], [0.0, 0.0], [1.0000001, -1.0000001],
+                                  [0.75, -0.75], [10.0, -10.0], [-10.5, 10.5]])])
+    out = np.zeros_like(v)
+    for i, (dx, dy) in enumerate(v):
+        p = Puck.__new__(Puck)
+        p.dx, p.dy = float(dx), float(dy)
+        p.friction_on_puck()
+        out[i] = (p.dx, p.dy)
+    actions = rng.integers(0, 4, (T, n)).astype(np.int8)
+    table = rng.uniform(-10, 10, (n, 32, 2))
+    init = scrambled_states(rng, n)
+    original = Puck.limit_puck_speed
+
+    def limit_with_friction(self):
+        self.friction_on_puck()
+        return original(self)
+
+    Puck.limit_puck_speed = limit_with_friction
+    try:
+        ref = ref_loop.run_reference(actions, table, init_state=init)
+    finally:
+        Puck.limit_puck_speed = original
+    np.savez_compressed(os.path.join(GOLDEN, "friction_24x150.npz"), fn_in=v, fn_out=out, actions=actions, reset_table=table,
+                        init_state=init, states=ref["states"], scores=ref["scores"], reward=ref["reward"].astype(np.int8),
+                        score=ref["score"], done=ref["done"],
+                        game_over=(ref["robot_win"] + 2 * ref["opponent_win"]).astype(np.uint8),
+                        reset_cursor=ref["reset_cursor"], **_header(seed))
+
+
 def main():
     refshim.install()
     os.makedirs(GOLDEN, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "friction":      # add the friction fixture without regenerating the others
+        gen_friction()
+        return
     gen_canonical()
     gen_long()
     gen_scrambled()
     gen_continuous()
     gen_substeps()
     gen_init_frame()
+    gen_friction()
     for f in sorted(os.listdir(GOLDEN)):
         print(f, os.path.getsize(os.path.join(GOLDEN, f)))
 

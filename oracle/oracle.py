@@ -60,6 +60,7 @@ def lib() -> C.CDLL:
         _lib.orc_puck_in_goal.restype = C.c_int
         _lib.orc_puck_in_goal.argtypes = [C.c_double] * 4
         _lib.orc_mallet_update.argtypes = [C.c_int, C.c_void_p]
+        _lib.orc_friction_on_puck.argtypes = [C.c_void_p]
     return _lib
 
 
@@ -162,3 +163,10 @@ def rng_reset_pair(seed: int, env_id: int, reset_idx: int) -> np.ndarray:
 
 def rng_action(seed: int, env_id: int, frame: int) -> int:
     return lib().orc_rng_action(seed, env_id, frame)
+
+
+def friction_on_puck(dx: float, dy: float):
+    """``Puck.friction_on_puck`` (environment/puck.py:73-88) on one velocity."""
+    v = np.array([dx, dy], np.float64)
+    lib().orc_friction_on_puck(_p(v))
+    return float(v[0]), float(v[1])
