@@ -23,7 +23,7 @@ STAT_NAMES = ("frames", "robot_goals", "opponent_goals", "robot_wins", "opponent
 
 # every symbol include/ah_b200.h declares (tests/test_capi_symbols.py checks header <-> library <-> this list)
 SYMBOLS = ("ah_strerror", "ah_abi_version", "ah_last_cuda_error", "ah_create", "ah_destroy", "ah_bind_state",
-           "ah_init_state", "ah_reset", "ah_update_state", "ah_get_state", "ah_update_score", "ah_rewards", "ah_step", "ah_pack_host", "ah_actor_sample", "ah_policy_act", "ah_stats", "ah_stats_bank",
+           "ah_init_state", "ah_reset", "ah_update_state", "ah_get_state", "ah_update_score", "ah_rewards", "ah_step", "ah_pack_host", "ah_actor_sample", "ah_policy_act", "ah_c51_project", "ah_stats", "ah_stats_bank",
            "ah_set_counters", "ah_get_counters", "ah_ring_sample", "ah_launch_info", "ah_selftest_nofma")
 
 
@@ -121,6 +121,8 @@ def lib() -> C.CDLL:
     L.ah_actor_sample.argtypes = [vp, vp, vp, vp, vp, i32, vp]
     L.ah_policy_act.restype = i32
     L.ah_policy_act.argtypes = [vp, C.POINTER(AhPolicy), vp, vp, vp, vp, vp, vp]
+    L.ah_c51_project.restype = i32
+    L.ah_c51_project.argtypes = [vp, i64, i32, i32, C.c_double, C.c_double, C.c_double, vp, vp, vp, vp, vp, vp]
     L.ah_stats.restype = i32
     L.ah_stats.argtypes = [vp, vp, i32, vp]
     L.ah_stats_bank.restype = i32

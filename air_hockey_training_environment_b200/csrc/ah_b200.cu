@@ -737,6 +737,42 @@ __global__ void ring_sample_kernel(int64_t n, int64_t capacity, const unsigned l
     if (index) index[s] = (int64_t)f;
 }
 
+// ---- C51's categorical projection (lib/agents/c51/c51.py:175-190) as ONE kernel: a thread owns sample i and writes the
+// A x atoms entries of m_prob[.][i][.] -- zeros except the row of the action taken, which receives the projected
+// distribution of the optimal next action, accumulated in the reference's order (j ascending, lower atom first).
+// As written there: m_l = floor(bj), m_u = ceil(bj); when bj is an integer both weights are 0 and the mass is dropped.
+template <typename R>
+__global__ void c51_project_kernel(int64_t B, int A, int atoms, R v_min, R v_max, R gamma, const R* __restrict__ z_opt,
+                                   const int8_t* __restrict__ action, const R* __restrict__ reward, const uint8_t* __restrict__ done,
+                                   R* __restrict__ m_prob) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const R dz = (v_max - v_min) / (R)(atoms - 1);
+    for (int a = 0; a < A; ++a)
+        for (int j = 0; j < atoms; ++j) m_prob[((int64_t)a * B + i) * atoms + j] = R(0);
+    const int act = action[i];
+    if (act < 0 || act >= A) return;
+    R* row = m_prob + ((int64_t)act * B + i) * atoms;
+    const R rw = reward[i];
+    if (done[i]) {                                                   // :181-187 the distribution collapses to one point
+        const R tz = fmin(v_max, fmax(v_min, rw));
+        const R bj = (tz - v_min) / dz;
+        const R ml = floor(bj), mu = ceil(bj);
+        row[(int)ml] += mu - bj;
+        row[(int)mu] += bj - ml;
+    } else {
+        for (int j = 0; j < atoms; ++j) {                            // :189-194
+            const R zj = v_min + (R)j * dz;
+            const R tz = fmin(v_max, fmax(v_min, rw + gamma * zj));
+            const R bj = (tz - v_min) / dz;
+            const R ml = floor(bj), mu = ceil(bj);
+            const R p = z_opt[i * atoms + j];
+            row[(int)ml] += p * (mu - bj);
+            row[(int)mu] += p * (bj - ml);
+        }
+    }
+}
+
 // a*b+c must NOT be contracted in this translation unit (FP64 validation build): discriminating probe
 __global__ void nofma_probe_kernel(double a, double b, double c, double* out) { out[0] = a * b + c; }
 
@@ -1122,6 +1158,21 @@ int ah_policy_act(ah_env* env, const ah_policy* policy, const void* d_obs, const
     const unsigned grid = (unsigned)((env->n + ah::kPolThreads - 1) / ah::kPolThreads);
     AH_DISPATCH(env, (ah::policy_act_kernel<float><<<grid, ah::kPolThreads, 0, s>>>(env->n, pd, (const float*)d_obs, (const float*)d_values_in, d_actions, (float*)d_actions_real, (float*)d_values_out, env->seed, env->env_id0, env->blk)),
                 (ah::policy_act_kernel<double><<<grid, ah::kPolThreads, 0, s>>>(env->n, pd, (const double*)d_obs, (const double*)d_values_in, d_actions, (double*)d_actions_real, (double*)d_values_out, env->seed, env->env_id0, env->blk)));
+    AH_LAUNCH_RC(env);
+}
+
+int ah_c51_project(ah_env* env, int64_t batch, int n_actions, int n_atoms, double v_min, double v_max, double gamma,
+                   const void* d_z_opt, const int8_t* d_action, const void* d_reward, const uint8_t* d_done, void* d_m_prob,
+                   void* stream) {
+    if (!env || batch <= 0 || n_actions < 1 || n_atoms < 2 || !(v_max > v_min) || !d_z_opt || !d_action || !d_reward || !d_done ||
+        !d_m_prob) return AH_EINVAL;
+    DeviceGuard g(env->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)((batch + 127) / 128);
+    AH_DISPATCH(env, (ah::c51_project_kernel<float><<<grid, 128, 0, s>>>(batch, n_actions, n_atoms, (float)v_min, (float)v_max, (float)gamma,
+                          (const float*)d_z_opt, d_action, (const float*)d_reward, d_done, (float*)d_m_prob)),
+                (ah::c51_project_kernel<double><<<grid, 128, 0, s>>>(batch, n_actions, n_atoms, v_min, v_max, gamma,
+                          (const double*)d_z_opt, d_action, (const double*)d_reward, d_done, (double*)d_m_prob)));
     AH_LAUNCH_RC(env);
 }
 

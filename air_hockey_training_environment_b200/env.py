@@ -526,6 +526,23 @@ class BatchedAirHockey:
                     "ah_policy_act", self._h)
         return actions
 
+    def c51_project(self, z_opt: torch.Tensor, action: torch.Tensor, reward: torch.Tensor, done: torch.Tensor, n_actions: int,
+                    gamma: float, v_min: float, v_max: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """C51's categorical projection of a replay minibatch (lib/agents/c51/c51.py:175-190) in one kernel
+        (``ah_c51_project``).  z_opt real [B, atoms], action int8 [B], reward real [B], done u8 [B] (the tensors
+        ``ReplayRing.sample`` returns) -> m_prob real [n_actions, B, atoms]."""
+        B, atoms = z_opt.shape
+        for t, shape, dt, name in ((z_opt, (B, atoms), self.dtype, "z_opt"), (action, (B,), torch.int8, "action"),
+                                   (reward, (B,), self.dtype, "reward"), (done, (B,), torch.uint8, "done")):
+            if t.device != self.device or t.dtype != dt or tuple(t.shape) != shape or not t.is_contiguous():
+                raise ValueError(f"{name}: expected contiguous {dt} {shape} on {self.device}")
+        if out is None:
+            out = torch.empty(n_actions, B, atoms, dtype=self.dtype, device=self.device)
+        _capi.check(self._lib.ah_c51_project(self._h, B, int(n_actions), atoms, float(v_min), float(v_max), float(gamma),
+                                             z_opt.data_ptr(), action.data_ptr(), reward.data_ptr(), done.data_ptr(),
+                                             out.data_ptr(), self._stream()), "ah_c51_project", self._h)
+        return out
+
     # ------------------------------------------------------------------ statistics, counters, checkpoints
     def stats_tensor(self, clear: bool = False, out: Optional[torch.Tensor] = None, bank: int = 0) -> torch.Tensor:
         """int64 [AH_NSTATS] device tensor of the AH_STAT_* counters accumulated by ``step`` (no host sync).  ``bank``:

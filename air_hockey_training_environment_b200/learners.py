@@ -190,3 +190,200 @@ class A2CLearner:
             la, lc = float(loss_a.detach()), float(loss_c.detach())
         self.actor.eval(); self.critic.eval()
         return {"actor_loss": la, "critic_loss": lc, "mean_reward": float(c.rewards.mean())}
+
+
+# ------------------------------------------------------------------------------------------------ value-based learners
+# DDQN / Dueling DDQN / C51 on minibatches drawn by the device sampler (``ReplayRing.sample`` -> ``ah_ring_sample``).  The
+# reference's update rules are restated AS WRITTEN (their quirks are listed at each function and reproduced, not
+# corrected); the one structural change is that a minibatch is fitted in one Adam step instead of the reference's
+# sample-by-sample ``model.fit`` calls (lib/agents/ddqn/ddqn.py:103-125).
+def continuous_ppo_actor_loss(y_true: torch.Tensor, y_pred: torch.Tensor, advantage: torch.Tensor,
+                              old_prediction: torch.Tensor, loss_clipping: float = 0.2, noise: float = 1.0) -> torch.Tensor:
+    """The reference's continuous PPO loss (lib/utils/helpers.py:49-69): Gaussian likelihood ratio with a FIXED sigma = 1
+    around the predicted mean, clipped surrogate, mean over all B x 2 entries.  y_true = the action taken [B, 2]."""
+    var = noise * noise
+    denom = (2 * torch.pi * var) ** 0.5
+    prob = torch.exp(-(y_true - y_pred) ** 2 / (2 * var)) / denom
+    old_prob = torch.exp(-(y_true - old_prediction) ** 2 / (2 * var)) / denom
+    r = prob / (old_prob + 1e-10)
+    return -torch.minimum(r * advantage, r.clamp(1 - loss_clipping, 1 + loss_clipping) * advantage).mean()
+
+
+def ddqn_targets(q_new_online: torch.Tensor, q_new_target: torch.Tensor, action: torch.Tensor, reward: torch.Tensor,
+                 done: torch.Tensor, gamma: float) -> torch.Tensor:
+    """lib/agents/ddqn/ddqn.py:108-121, as written: the regression target starts from the ONLINE net's prediction for the
+    NEW state (:108, not the current one), and its ``action`` entry becomes ``reward`` when done, else
+    ``reward + gamma * np.argmax(t)`` -- the INDEX of the target net's best action, not its value (:121)."""
+    target = q_new_online.clone()
+    boot = reward + gamma * q_new_target.argmax(dim=1).to(reward.dtype)
+    target.scatter_(1, action.long().unsqueeze(1), torch.where(done.bool(), reward, boot).unsqueeze(1))
+    return target
+
+
+def dueling_targets(q_online: torch.Tensor, q_new_online: torch.Tensor, q_new_target: torch.Tensor, action: torch.Tensor,
+                    reward: torch.Tensor, done: torch.Tensor, gamma: float) -> torch.Tensor:
+    """lib/agents/dueling/dueling.py:148-176 (double DQN): the online net picks the next action, the target net values it."""
+    target = q_online.clone()
+    a = q_new_online.argmax(dim=1, keepdim=True)
+    boot = reward + gamma * q_new_target.gather(1, a).squeeze(1)
+    target.scatter_(1, action.long().unsqueeze(1), torch.where(done.bool(), reward, boot).unsqueeze(1))
+    return target
+
+
+def c51_optimal_actions(z_online: torch.Tensor, support: torch.Tensor) -> torch.Tensor:
+    """lib/agents/c51/c51.py:169-172: q[i, a] = sum_j z[a][i][j] * support[j]; argmax over a.  z_online: [A, B, atoms]."""
+    return (z_online * support).sum(dim=2).argmax(dim=0)
+
+
+def c51_project(z_target_opt: torch.Tensor, action: torch.Tensor, reward: torch.Tensor, done: torch.Tensor, n_actions: int,
+                gamma: float, v_min: float, v_max: float) -> torch.Tensor:
+    """The categorical projection of lib/agents/c51/c51.py:175-190, vectorised in torch (the one-kernel device version
+    is ``BatchedAirHockey.c51_project`` / ``ah_c51_project``).  z_target_opt [B, atoms] = the target net's distribution of
+    the optimal next action; returns m_prob [A, B, atoms], non-zero only in row ``action[i]``.
+    As written in the reference: ``m_l, m_u = floor(bj), ceil(bj)`` -- when bj is an integer both weights (m_u - bj) and
+    (bj - m_l) are 0 and that atom's mass is dropped."""
+    B, atoms = z_target_opt.shape
+    dz = (v_max - v_min) / (atoms - 1)
+    support = v_min + dz * torch.arange(atoms, dtype=z_target_opt.dtype, device=z_target_opt.device)
+    dn = done.bool()
+    tz = (reward.unsqueeze(1) + gamma * support.unsqueeze(0)).clamp(v_min, v_max)            # [B, atoms]
+    tz = torch.where(dn.unsqueeze(1), reward.clamp(v_min, v_max).unsqueeze(1).expand(B, atoms), tz)
+    mass = torch.where(dn.unsqueeze(1), torch.zeros_like(z_target_opt), z_target_opt)
+    mass[:, 0] = torch.where(dn, torch.ones_like(reward), mass[:, 0])                       # terminal: a single unit point
+    bj = (tz - v_min) / dz
+    ml, mu = bj.floor(), bj.ceil()
+    row = torch.zeros(B, atoms, dtype=z_target_opt.dtype, device=z_target_opt.device)
+    row.scatter_add_(1, ml.long(), mass * (mu - bj))
+    row.scatter_add_(1, mu.long(), mass * (bj - ml))
+    m = torch.zeros(n_actions, B, atoms, dtype=z_target_opt.dtype, device=z_target_opt.device)
+    m[action.long(), torch.arange(B, device=m.device)] = row
+    return m
+
+
+class QNet(nn.Module):
+    """The reference's DDQN network: Dense(8, relu) - BatchNorm - Dense(4, softmax) (lib/agents/ddqn/model.py:39-53; yes,
+    a softmax on Q-values -- as written)."""
+
+    def __init__(self, state_size: int = 8, action_size: int = 4):
+        super().__init__()
+        self.net = nn.Sequential(nn.Linear(state_size, state_size), nn.ReLU(), nn.BatchNorm1d(state_size, eps=1e-3, momentum=0.01),
+                                 nn.Linear(state_size, action_size), nn.Softmax(dim=-1))
+
+    def forward(self, obs: torch.Tensor) -> torch.Tensor:
+        return self.net(obs)
+
+
+class C51Net(nn.Module):
+    """lib/agents/c51/model.py:44-63 as written: Dense(32, relu) - BatchNorm, then the A "heads" are CHAINED
+    (``x = Dense(atoms)(x)`` reuses x), linear, un-normalised.  forward -> [A, B, atoms]."""
+
+    def __init__(self, action_size: int = 4, atoms: int = 51, state_size: int = 8):
+        super().__init__()
+        self.trunk = nn.Sequential(nn.Linear(state_size, 32), nn.ReLU(), nn.BatchNorm1d(32, eps=1e-3, momentum=0.01))
+        self.heads = nn.ModuleList([nn.Linear(32 if k == 0 else atoms, atoms) for k in range(action_size)])
+
+    def forward(self, obs: torch.Tensor) -> torch.Tensor:
+        x, outs = self.trunk(obs), []
+        for h in self.heads:
+            x = h(x)
+            outs.append(x)
+        return torch.stack(outs, 0)
+
+
+class ReplayLearner:
+    """Shared machinery: minibatch from the device ring, online / target networks, Adam, target sync."""
+
+    def __init__(self, env, ring, online: nn.Module, target: nn.Module, gamma: float, lr: float, batch_size: int):
+        self.env, self.ring, self.online, self.target = env, ring, online, target
+        self.gamma, self.batch_size = gamma, int(batch_size)
+        self.opt = torch.optim.Adam(online.parameters(), lr=lr)
+        self.update_target_model()
+
+    def update_target_model(self) -> None:
+        self.target.load_state_dict(self.online.state_dict())
+        self.target.eval()
+
+    def minibatch(self) -> Dict[str, torch.Tensor]:
+        held = len(self.ring) * self.ring.n
+        return self.ring.sample(min(self.batch_size, held), self.env, check=False)      # lib/agents/ddqn/ddqn.py:101-102
+
+    def fit(self, loss: torch.Tensor) -> float:
+        self.opt.zero_grad(set_to_none=True)
+        loss.backward()
+        self.opt.step()
+        return float(loss.detach())
+
+
+class DDQNLearner(ReplayLearner):
+    """lib/agents/ddqn/ddqn.py:95-125 (gamma 0.95, lr 1e-3; Huber loss, ddqn/model.py:27-53)."""
+
+    def __init__(self, env, ring, gamma: float = 0.95, lr: float = 1e-3, batch_size: int = 10000):
+        dev, dt = env.device, env.dtype
+        super().__init__(env, ring, QNet().to(device=dev, dtype=dt), QNet().to(device=dev, dtype=dt), gamma, lr, batch_size)
+
+    def update(self) -> Dict[str, float]:
+        b = self.minibatch()
+        self.online.eval()
+        with torch.no_grad():
+            target = ddqn_targets(self.online(b["new_state"]), self.target(b["new_state"]), b["action"], b["reward"], b["done"],
+                                  self.gamma)
+        if bool(b["done"].any()):                      # "if observation.done: self.update_target_model()"  (:111-113)
+            self.update_target_model()
+        self.online.train()
+        loss = self.fit(huber_loss(target, self.online(b["state"])).mean())
+        self.online.eval()
+        return {"loss": loss, "batch": int(b["reward"].numel())}
+
+
+class DuelingLearner(ReplayLearner):
+    """lib/agents/dueling/dueling.py:125-178 (gamma 0.9, lr 1e-5; the target net is synced on every update, :131)."""
+
+    def __init__(self, env, ring, gamma: float = 0.9, lr: float = 1e-5, batch_size: int = 10000):
+        from .policy import DuelingQNet
+        dev, dt = env.device, env.dtype
+        super().__init__(env, ring, DuelingQNet().to(device=dev, dtype=dt), DuelingQNet().to(device=dev, dtype=dt), gamma, lr, batch_size)
+
+    def update(self) -> Dict[str, float]:
+        self.update_target_model()
+        b = self.minibatch()
+        with torch.no_grad():
+            target = dueling_targets(self.online(b["state"]), self.online(b["new_state"]), self.target(b["new_state"]),
+                                     b["action"], b["reward"], b["done"], self.gamma)
+        loss = self.fit(huber_loss(target, self.online(b["state"])).mean())
+        return {"loss": loss, "batch": int(b["reward"].numel())}
+
+
+class C51Learner(ReplayLearner):
+    """lib/agents/c51/c51.py:139-195 (51 atoms on [-10, 10], gamma 0.95, 10 epochs per update); the projection runs as one
+    kernel on the device (``ah_c51_project``)."""
+
+    def __init__(self, env, ring, gamma: float = 0.95, lr: float = 1e-4, batch_size: int = 10000, atoms: int = 51,
+                 v_min: float = -10.0, v_max: float = 10.0, epochs: int = 10, device_projection: bool = True):
+        dev, dt = env.device, env.dtype
+        super().__init__(env, ring, C51Net(atoms=atoms).to(device=dev, dtype=dt), C51Net(atoms=atoms).to(device=dev, dtype=dt),
+                         gamma, lr, batch_size)
+        self.atoms, self.v_min, self.v_max, self.epochs, self.device_projection = atoms, v_min, v_max, epochs, device_projection
+        self.support = torch.linspace(v_min, v_max, atoms, dtype=dt, device=dev)
+
+    def q_values(self, obs: torch.Tensor) -> torch.Tensor:
+        """lib/agents/c51/c51.py:124-131: Q[i, a] = sum_j z[a][i][j] * support[j] -- the head values for ``policy_act``."""
+        return (self.online(obs) * self.support).sum(dim=2).t().contiguous()
+
+    def update(self) -> Dict[str, float]:
+        self.update_target_model()
+        b = self.minibatch()
+        self.online.eval()
+        with torch.no_grad():
+            best = c51_optimal_actions(self.online(b["new_state"]), self.support)
+            z_t = self.target(b["new_state"])                                              # [A, B, atoms]
+            z_opt = z_t[best, torch.arange(best.numel(), device=best.device)].contiguous()
+            if self.device_projection:
+                m_prob = self.env.c51_project(z_opt, b["action"], b["reward"], b["done"], 4, self.gamma, self.v_min, self.v_max)
+            else:
+                m_prob = c51_project(z_opt, b["action"], b["reward"], b["done"], 4, self.gamma, self.v_min, self.v_max)
+        self.online.train()
+        loss = 0.0
+        for _ in range(self.epochs):
+            loss = self.fit(huber_loss(m_prob, self.online(b["state"])).mean())
+        self.online.eval()
+        return {"loss": loss, "batch": int(b["reward"].numel())}

@@ -283,6 +283,16 @@ int ah_actor_sample(ah_env* env, const float* d_weights, const void* d_obs, void
 int ah_policy_act(ah_env* env, const ah_policy* policy, const void* d_obs, const void* d_values_in, int8_t* d_actions,
                   void* d_actions_real, void* d_values_out, void* stream);
 
+/* C51's categorical projection of a replay minibatch (lib/agents/c51/c51.py:175-190) in one kernel: for sample i the row
+ * m_prob[action[i]][i][:] receives the distribution d_z_opt[i][:] (the target network's distribution of the optimal next
+ * action) shifted by reward + gamma * z and projected onto the fixed support of n_atoms atoms on [v_min, v_max] (terminal
+ * samples collapse to one point); every other row of m_prob[.][i][:] is zeroed.  Arithmetic and accumulation order are the
+ * reference's (including floor/ceil dropping the mass of integer bj).  d_z_opt real [batch][n_atoms], d_action int8
+ * [batch], d_reward real [batch], d_done u8 [batch], d_m_prob real [n_actions][batch][n_atoms]. */
+int ah_c51_project(ah_env* env, int64_t batch, int n_actions, int n_atoms, double v_min, double v_max, double gamma,
+                   const void* d_z_opt, const int8_t* d_action, const void* d_reward, const uint8_t* d_done, void* d_m_prob,
+                   void* stream);
+
 /* Compact, lossless host-transfer encoding of one step's results (for callers that consume them on the HOST, where
  * PCIe, not the kernel, is the bound).  Inputs are the device outputs of ah_step:
  *   reward real [K][n] (integer-valued, -4..6: lib/rewards.py:118-142), done u8 [K][n], obs_next real [n][8].
