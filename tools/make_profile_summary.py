@@ -4,7 +4,10 @@ import csv, io, json, os, subprocess, sys
 from collections import Counter
 tag = sys.argv[1]; wf = float(sys.argv[2]) if len(sys.argv) > 2 else 262144.0
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-rep = os.path.join(ROOT, "gpurun_out", f"prof_{tag}.ncu-rep")
+rep = sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, "gpurun_out", f"prof_{tag}.ncu-rep")
+launches = sys.argv[4] if len(sys.argv) > 4 else os.path.join(ROOT, "gpurun_out", f"launches_{tag}.csv")
+command = sys.argv[5] if len(sys.argv) > 5 else "python bench.py --steps 20 --warmup 30 --no-cpu-baseline --no-e2e"
+capture = sys.argv[6] if len(sys.argv) > 6 else "ncu --set full --clock-control none --import-source on -k regex:step_kernel -s 35 -c 1"
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw))); hdr, units, d = rows[0], rows[1], rows[2]
 m = {h: (d[i], units[i]) for i, h in enumerate(hdr)}
@@ -39,8 +42,8 @@ os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
 json.dump(facts, open(os.path.join(ROOT, "profiles", "step_kernel_facts.json"), "w"), indent=1)
 with open(os.path.join(ROOT, "profiles", f"{tag}_step_kernel.md"), "w") as o:
     o.write(f"# ncu --set full, {tag}: `{kname}`\n\n")
-    o.write("Command: `python bench.py --steps 20 --warmup 30 --no-cpu-baseline --no-e2e` (n = 2^20 envs, K = 8, FP32), one launch "
-            "captured with `ncu --set full --clock-control none --import-source on -k regex:step_kernel -s 35 -c 1` after the same "
+    o.write(f"Command: `{command}` (n = 2^20 envs, K = 8, FP32), one launch "
+            f"captured with `{capture}` after the same "
             "command exited 0 without ncu.  Numbers under ncu are cold-cache/serialised: use shares, not absolutes.\n\n| metric | value | unit |\n|---|---|---|\n")
     for k in keys:
         if k in m: o.write(f"| `{k}` | {m[k][0]} | {m[k][1]} |\n")
@@ -51,7 +54,7 @@ with open(os.path.join(ROOT, "profiles", f"{tag}_step_kernel.md"), "w") as o:
         if v >= 0.05: o.write(f"| {k} | {v:.3f} |\n")
     o.write("\n## Executed opcode mix (warp-instructions per warp-frame)\n\n| opcode | per warp-frame |\n|---|---|\n")
     for op, v in c.most_common(30): o.write(f"| {op} | {v / wf:.1f} |\n")
-lp = os.path.join(ROOT, "gpurun_out", f"launches_{tag}.csv")
+lp = launches
 if os.path.exists(lp):
     rows = [r for r in csv.reader(open(lp)) if len(r) > 10 and r[0].isdigit()]
     agg = Counter(); cnt = Counter()
@@ -59,8 +62,8 @@ if os.path.exists(lp):
         agg[r[4]] += float(r[-1]); cnt[r[4]] += 1
     total = sum(agg.values())
     with open(os.path.join(ROOT, "profiles", f"{tag}_launches.md"), "w") as o:
-        o.write(f"# ncu launch list, {tag} (`--metrics gpu__time_duration.sum --clock-control none`, first 120 launches of the bench command: "
-                "setup + warm-up + timed steps)\n\n| kernel | launches | total ns | share |\n|---|---|---|---|\n")
+        o.write(f"# ncu launch list, {tag} (`--metrics gpu__time_duration.sum --clock-control none`, the first {len(rows)} launches of "
+                f"`{command}`: setup + warm-up + timed steps)\n\n| kernel | launches | total ns | share |\n|---|---|---|---|\n")
         for k, v in agg.most_common():
             o.write(f"| `{k[:110]}` | {cnt[k]} | {v:.0f} | {100 * v / total:.1f} % |\n")
     import shutil; shutil.copy(lp, os.path.join(ROOT, "profiles", f"{tag}_launches.csv"))
