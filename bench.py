@@ -1,25 +1,30 @@
 #!/usr/bin/env python
 """Benchmark of the ONE hot path: env-steps/s of the batched air-hockey frame loop on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--parts P]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 Workload (BASELINE.json configs[2]; configs[3] = the same per-GPU work sharded over N GPUs): per GPU 2^20
-environments, FP32 throughput build, one bench "step" = ONE launch of the fused step kernel = 8 frames per env with
-per-frame discrete actions read from an int8 [8, n] tensor, the in-kernel computerAI opponent and Rewards reward,
-writing reward/done/score/game_over [8, n] and the next observation [n, 8]; statistics are reduced in-kernel and
-(N > 1) all-reduced over NCCL once per step.  1 env-step = 1 frame of Game.play (3 physics sub-updates + reward +
-score / game-over handling).
+environments, FP32 throughput build, one bench "step" = 8 fused frames for every env in the PACKED rollout mode
+(csrc/ah_step_packed.cuh): per-frame discrete actions read as quad-major uint8 [2, n, 4], the in-kernel computerAI
+opponent and Rewards reward, one event byte (reward, done, score, game_over) per env-frame and the next observation
+[n, 8] written, statistics reduced in-kernel.  A step is issued as `--parts` (default 2) disjoint env slices on as many
+streams (sub-range launches of the same kernel; consecutive steps overlap tail-to-head); the statistics are copied out --
+and at N > 1 all-reduced over NCCL -- once per rollout of 16 steps and at the end of the timed region, and the reduced
+payload is verified.  1 env-step = 1 frame of Game.play (3 physics sub-updates + reward + score / game-over handling).
 
 `value`        device-resident throughput (actions already in HBM), CUDA events, max over ranks.
-`e2e`          same public-API call, but every step's actions come from pinned HOST memory (H2D inside the timed
-               region) and the step's results (reward, done, next observation) go back to pinned host memory.
-`roofline`     the fused K=8 kernel is bound by FP32/ALU-pipe issue, not by HBM (DESIGN.md §5): `achieved` counts the
-               ALGORITHMIC lane-ops (254 per env-step) per second against 148 SMs x 128 lanes x
-               SM clock; the HBM view of the same launch is reported beside it (`hbm_*`).
-`rollout_k1`   the HBM-bound mode (one policy decision per launch, all outputs written) with its own HBM roofline.
-`cpu_baseline` / `--impl reference`: the C restatement of the reference (oracle/, kind "port") on the host cores
-               with OpenMP -- the Python reference itself cannot travel to the GPU box.
+`e2e`          the public HOST-buffer API (host.HostStepper): every step's actions come from pinned HOST memory (H2D inside
+               the timed region) and the step's results (event bytes, next observation) go back to pinned host memory;
+               `e2e.roofline` = the same copies without the kernels (the host link's measured ceiling).
+`roofline`     the fused K=8 kernel is bound by FP32/ALU-pipe issue, not by HBM (DESIGN.md section 5): `achieved` counts the
+               ALGORITHMIC lane-ops (254 per env-step) per second against 148 SMs x 128 lanes x SM
+               clock; `single_launch_*` = one whole-n launch per step; the HBM view of the same step is beside it.
+`extras`       BASELINE configs 4 (fused ring append) and 5 (PPO rollouts) at this world size, the HBM-bound K=1 mode,
+               round 1's unpacked kernel, the FP64 validation build.
+`cpu_baseline` the reference's OWN Python implementation (oracle/_ref: byte-compiled from /root/reference by
+               oracle/fetch_ref.py) on this box's host cores: BASELINE config 1, one process and a pool over all cores
+               (kind "reference"); the C port (kind "port") beside it.  `--impl reference` times the same reference.
 """
 from __future__ import annotations
 
