@@ -23,7 +23,7 @@ STAT_NAMES = ("frames", "robot_goals", "opponent_goals", "robot_wins", "opponent
 
 # every symbol include/ah_b200.h declares (tests/test_capi_symbols.py checks header <-> library <-> this list)
 SYMBOLS = ("ah_strerror", "ah_abi_version", "ah_last_cuda_error", "ah_create", "ah_destroy", "ah_bind_state",
-           "ah_init_state", "ah_reset", "ah_update_state", "ah_get_state", "ah_update_score", "ah_rewards", "ah_step", "ah_pack_host", "ah_actor_sample", "ah_policy_act", "ah_c51_project", "ah_stats", "ah_stats_bank",
+           "ah_init_state", "ah_reset", "ah_update_state", "ah_get_state", "ah_update_score", "ah_rewards", "ah_step", "ah_pack_host", "ah_actor_sample", "ah_policy_act", "ah_c51_project", "ah_stats", "ah_stats_bank", "ah_peer_export", "ah_peer_attach", "ah_stats_allreduce",
            "ah_set_counters", "ah_get_counters", "ah_ring_sample", "ah_launch_info", "ah_selftest_nofma")
 
 
@@ -41,6 +41,7 @@ AH_HEAD_SOFTMAX, AH_HEAD_VALUES, AH_HEAD_DUELING, AH_HEAD_CONTINUOUS = 0, 1, 2, 
 (AH_SELECT_SAMPLE, AH_SELECT_GREEDY, AH_SELECT_EPS_GREEDY, AH_SELECT_BOLTZMANN, AH_SELECT_MAX_BOLTZMANN, AH_SELECT_GAUSSIAN,
  AH_SELECT_OU) = range(7)
 AH_POLICY_MAX_LAYERS, AH_POLICY_MAX_WIDTH = 4, 32
+AH_MAX_PEERS, AH_IPC_HANDLE_BYTES = 8, 64
 
 
 class AhPolicy(C.Structure):
@@ -127,6 +128,12 @@ def lib() -> C.CDLL:
     L.ah_stats.argtypes = [vp, vp, i32, vp]
     L.ah_stats_bank.restype = i32
     L.ah_stats_bank.argtypes = [vp, i32, vp, i32, vp]
+    L.ah_peer_export.restype = i32
+    L.ah_peer_export.argtypes = [vp, vp]
+    L.ah_peer_attach.restype = i32
+    L.ah_peer_attach.argtypes = [vp, i32, i32, vp]
+    L.ah_stats_allreduce.restype = i32
+    L.ah_stats_allreduce.argtypes = [vp, i32, vp, i32, vp]
     L.ah_set_counters.restype = i32
     L.ah_set_counters.argtypes = [vp, u64, vp]
     L.ah_get_counters.restype = i32

@@ -25,11 +25,20 @@ namespace ah {
 struct DevBlock {
     unsigned long long stats[2][AH_NSTATS];   // AH_STAT_*, two banks (ah_step_io.stats_bank)
     unsigned long long frame;              // global frame counter (Philox action index)
-    unsigned long long reserved;
+    unsigned long long xchg_epoch;         // ah_stats_allreduce: exchanges done so far (all ranks call it equally often)
     unsigned int ticket;                   // last-block-done detection
     unsigned int pad[43];
 };
 static_assert(sizeof(DevBlock) == 512, "DevBlock is 512 bytes");
+
+// One contribution to the fused statistics all-reduce: written by its source rank straight into every rank's receive
+// buffer over NVLink (P2P stores), `epoch` last (release) -- the flag the receiver spins on.
+struct PeerSlot {
+    long long vals[AH_NSTATS];
+    unsigned long long epoch;
+    unsigned long long pad[11];
+};
+static_assert(sizeof(PeerSlot) == 256, "PeerSlot is 256 bytes");
 
 template <typename R> struct Vec4T;
 template <> struct Vec4T<float> { using type = float4; };
@@ -671,6 +680,53 @@ __global__ void stats_copy_kernel(DevBlock* blk, int bank, int64_t* out, int cle
     }
 }
 
+// ---- statistics copy + clear + all-reduce over NVLink peer memory in ONE kernel (no NCCL launch, no host round trip):
+// every rank pushes its vector into its slot of every rank's receive buffer (P2P stores, then a system-scope fence, then
+// the epoch flag), spins until all `world` slots of its OWN buffer carry the current epoch, and sums them in rank order
+// (so every rank computes the same sum).  Two parities: a rank can be at most one exchange ahead of a peer (it needs the
+// peer's contribution to finish its own), so the slot it overwrites two exchanges later has been consumed.  A spin that
+// exceeds ~2 s (a peer that never calls) reports -1 in out[AH_NSTATS - 1] instead of hanging the GPU.
+struct PeerPtrs { PeerSlot* p[AH_MAX_PEERS]; };
+
+__global__ void stats_allreduce_kernel(DevBlock* blk, int bank, int clear, int rank, int world, PeerPtrs peers, int64_t* out) {
+    const int q = threadIdx.x;                       // one warp: lane q owns statistic q
+    __shared__ unsigned long long s_epoch;
+    if (q == 0) { s_epoch = blk->xchg_epoch + 1ull; blk->xchg_epoch = s_epoch; }
+    __syncwarp();
+    const unsigned long long epoch = s_epoch;
+    const int par = (int)(epoch & 1ull);
+    long long mine = 0;
+    if (q < AH_NSTATS) {
+        mine = (long long)blk->stats[bank][q];
+        if (clear) blk->stats[bank][q] = 0ull;
+        for (int r = 0; r < world; ++r) peers.p[r][par * AH_MAX_PEERS + rank].vals[q] = mine;
+    }
+    __threadfence_system();
+    __syncwarp();
+    if (q < world) {
+        volatile unsigned long long* flag = &peers.p[q][par * AH_MAX_PEERS + rank].epoch;
+        *flag = epoch;
+    }
+    __threadfence_system();
+    // wait for every source's slot in MY buffer
+    bool ok = true;
+    if (q < world) {
+        volatile unsigned long long* flag = &peers.p[rank][par * AH_MAX_PEERS + q].epoch;
+        const long long t0 = clock64();
+        while (*flag != epoch) {
+            if (clock64() - t0 > 4000000000ll) { ok = false; break; }
+            __nanosleep(200);
+        }
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    __threadfence_system();
+    if (q < AH_NSTATS) {
+        long long sum = 0;
+        for (int r = 0; r < world; ++r) sum += ((volatile long long*)peers.p[rank][par * AH_MAX_PEERS + r].vals)[q];
+        out[q] = (ok || q != AH_NSTATS - 1) ? sum : -1;
+    }
+}
+
 __global__ void counters_set_kernel(DevBlock* blk, unsigned long long frame) { blk->frame = frame; }
 __global__ void counters_get_kernel(const DevBlock* blk, unsigned long long* out1) { out1[0] = blk->frame; }
 
@@ -789,6 +845,10 @@ struct ah_env {
     ah::DevBlock* blk;
     int sms, blocks_f32, blocks_f64;
     int last_cuda;
+    // peer statistics exchange (ah_peer_export / ah_peer_attach / ah_stats_allreduce)
+    ah::PeerSlot* xchg;                    // this rank's receive buffer [2 parities][AH_MAX_PEERS]
+    ah::PeerSlot* peer[AH_MAX_PEERS];      // every rank's receive buffer, mapped into this process (peer[rank] == xchg)
+    int rank, world;
 };
 
 namespace {
@@ -1015,6 +1075,9 @@ int ah_destroy(ah_env* env) {
     if (!env) return AH_EINVAL;
     DeviceGuard g(env->device);
     if (env->blk) cudaFree(env->blk);
+    for (int r = 0; r < env->world; ++r)
+        if (r != env->rank && env->peer[r]) cudaIpcCloseMemHandle(env->peer[r]);
+    if (env->xchg) cudaFree(env->xchg);
     delete env;
     return AH_OK;
 }
@@ -1196,6 +1259,48 @@ int ah_stats_bank(ah_env* env, int bank, int64_t* d_out, int clear, void* stream
 }
 
 int ah_stats(ah_env* env, int64_t* d_out, int clear, void* stream) { return ah_stats_bank(env, 0, d_out, clear, stream); }
+
+int ah_peer_export(ah_env* env, uint8_t* handle64) {
+    if (!env || !handle64) return AH_EINVAL;
+    DeviceGuard g(env->device);
+    if (!env->xchg) {
+        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&env->xchg), 2 * AH_MAX_PEERS * sizeof(ah::PeerSlot));
+        if (e == cudaSuccess) e = cudaMemset(env->xchg, 0, 2 * AH_MAX_PEERS * sizeof(ah::PeerSlot));
+        if (e != cudaSuccess) return cuda_fail(env, e);
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == AH_IPC_HANDLE_BYTES, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    const cudaError_t e = cudaIpcGetMemHandle(&h, env->xchg);
+    if (e != cudaSuccess) return cuda_fail(env, e);
+    memcpy(handle64, &h, sizeof h);
+    return AH_OK;
+}
+
+int ah_peer_attach(ah_env* env, int rank, int world, const uint8_t* handles) {
+    if (!env || !handles || world < 1 || world > AH_MAX_PEERS || rank < 0 || rank >= world || !env->xchg) return AH_EINVAL;
+    DeviceGuard g(env->device);
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) { env->peer[r] = env->xchg; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)r * AH_IPC_HANDLE_BYTES, sizeof h);
+        void* p = nullptr;
+        const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) return cuda_fail(env, e);
+        env->peer[r] = reinterpret_cast<ah::PeerSlot*>(p);
+    }
+    env->rank = rank; env->world = world;
+    return AH_OK;
+}
+
+int ah_stats_allreduce(ah_env* env, int bank, int64_t* d_out, int clear, void* stream) {
+    if (!env || !d_out || (bank != 0 && bank != 1)) return AH_EINVAL;
+    if (env->world < 1) return AH_ESTATE;                    // ah_peer_attach first
+    DeviceGuard g(env->device);
+    ah::PeerPtrs pp;
+    for (int r = 0; r < AH_MAX_PEERS; ++r) pp.p[r] = r < env->world ? env->peer[r] : nullptr;
+    ah::stats_allreduce_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(env->blk, bank, clear, env->rank, env->world, pp, d_out);
+    AH_LAUNCH_RC(env);
+}
 
 int ah_set_counters(ah_env* env, uint64_t frame, void* stream) {
     if (!env) return AH_EINVAL;

@@ -104,6 +104,43 @@ def all_reduce_stats(stats: torch.Tensor, group=None) -> torch.Tensor:
     return stats
 
 
+class PeerStats:
+    """The per-rollout statistics exchange fused over NVLink peer memory (``ah_stats_allreduce``): copy + clear + sum
+    over all ranks of ONE box in a single one-warp kernel -- each rank stores its vector straight into every rank's
+    receive buffer (P2P), flags it and waits for the others' -- instead of a copy kernel followed by an NCCL all-reduce.
+    Set-up (once, collective): the ranks exchange CUDA IPC handles of their receive buffers through the process group.
+    ``available`` is False (and callers fall back to ``all_reduce_stats``) when IPC / peer access cannot be set up."""
+
+    def __init__(self, env, group=None):
+        import ctypes as C
+        self.env, self.available, self.error = env, False, None
+        if not (dist.is_available() and dist.is_initialized()):
+            self.error = "no process group"
+            return
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        handle = torch.zeros(_capi.AH_IPC_HANDLE_BYTES, dtype=torch.uint8)
+        rc = env._lib.ah_peer_export(env._h, handle.data_ptr()) if world <= _capi.AH_MAX_PEERS else _capi.AH_EINVAL
+        ok = torch.tensor([1 if rc == _capi.AH_OK else 0], device=env.device)
+        gathered = [torch.zeros(_capi.AH_IPC_HANDLE_BYTES, dtype=torch.uint8, device=env.device) for _ in range(world)]
+        dist.all_gather(gathered, handle.to(env.device), group=group)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 1:
+            blob = torch.stack(gathered).cpu().contiguous()
+            rc = env._lib.ah_peer_attach(env._h, rank, world, blob.data_ptr())
+            ok = torch.tensor([1 if rc == _capi.AH_OK else 0], device=env.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)      # all ranks or none
+        self.available = int(ok.item()) == 1
+        if not self.available:
+            self.error = f"IPC set-up failed (rc {rc})"
+
+    def allreduce(self, out: torch.Tensor, bank: int = 0, clear: bool = True, stream: Optional[int] = None) -> torch.Tensor:
+        """``out`` (int64 [AH_NSTATS], device) <- the sum over all ranks of the env's statistics bank; no host sync."""
+        env = self.env
+        _capi.check(env._lib.ah_stats_allreduce(env._h, int(bank), out.data_ptr(), int(clear),
+                                                env._stream() if stream is None else stream), "ah_stats_allreduce", env._h)
+        return out
+
+
 def summarize(stats: torch.Tensor) -> Dict[str, float]:
     """Host-side summary of a (reduced) statistics vector: the aggregates the reference logs per frame / per
     episode (robot_goal, opponent_goal, robot_win, opponent_win, mean reward), as rates."""

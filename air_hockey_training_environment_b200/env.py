@@ -630,11 +630,12 @@ class InterleavedStepper:
             self.env.launch(plan, s)
         return out
 
-    def close_rollout(self, stats_out: torch.Tensor) -> torch.cuda.Stream:
+    def close_rollout(self, stats_out: torch.Tensor, peer=None) -> torch.cuda.Stream:
         """End of a rollout, WITHOUT draining the GPU: the statistics bank the steps so far accumulated into is copied
         to ``stats_out`` and cleared on a private stream that waits for exactly those steps, and later steps switch to
         the other bank -- they neither wait for the copy nor race with it.  Returns the stream the copy was queued on
-        (queue the all-reduce there, or make a consumer stream wait for it)."""
+        (queue the all-reduce there, or make a consumer stream wait for it).  ``peer`` (a ``dist.PeerStats``): the copy
+        IS the all-reduce (fused over NVLink peer memory)."""
         done = []
         for s in self.streams:
             ev = torch.cuda.Event()
@@ -644,8 +645,11 @@ class InterleavedStepper:
             self.stats_stream.wait_stream(torch.cuda.current_stream(self.env.device))
         for ev in done:
             self.stats_stream.wait_event(ev)
-        with torch.cuda.stream(self.stats_stream):
-            self.env.stats_tensor(clear=True, out=stats_out, bank=self.bank)
+        if peer is not None:                                 # dist.PeerStats: copy + clear + sum over the ranks, one kernel
+            peer.allreduce(stats_out, bank=self.bank, clear=True, stream=self.stats_stream.cuda_stream)
+        else:
+            with torch.cuda.stream(self.stats_stream):
+                self.env.stats_tensor(clear=True, out=stats_out, bank=self.bank)
         self.bank ^= 1
         return self.stats_stream
 

@@ -247,10 +247,11 @@ class StatsReducer:
     kernel does not wait for NCCL.  The reduced vectors are accumulated so that the payload can be checked:
     frames == world x envs x K x steps."""
 
-    def __init__(self, env, world, dev, every=ROLLOUT_STEPS, stepper=None):
+    def __init__(self, env, world, dev, every=ROLLOUT_STEPS, stepper=None, peer=None):
         import torch
         from air_hockey_training_environment_b200 import STAT_NAMES
         self.env, self.world, self.every, self.stepper, self.dev = env, world, every, stepper, dev
+        self.peer = peer if (peer is not None and peer.available and world > 1) else None   # fused P2P all-reduce
         self.bufs = [torch.zeros(len(STAT_NAMES), dtype=torch.int64, device=dev) for _ in range(2)]
         self.acc = torch.zeros(len(STAT_NAMES), dtype=torch.int64, device=dev)
         self.pending, self.j, self.count, self.reductions = None, 0, 0, 0
@@ -275,9 +276,14 @@ class StatsReducer:
         side = None
         if self.stepper is not None:
             self.stepper.stats_stream.wait_stream(torch.cuda.current_stream(self.dev))   # buf's previous reader is done
-            side = self.stepper.close_rollout(buf)
-            with torch.cuda.stream(side):
-                work = dist.all_reduce(buf, async_op=True) if self.world > 1 else None
+            side = self.stepper.close_rollout(buf, peer=self.peer)
+            work = None
+            if self.peer is None and self.world > 1:
+                with torch.cuda.stream(side):
+                    work = dist.all_reduce(buf, async_op=True)
+        elif self.peer is not None:
+            self.peer.allreduce(buf, clear=True)
+            work = None
         else:
             self.env.stats_tensor(clear=True, out=buf)
             work = dist.all_reduce(buf, async_op=True) if self.world > 1 else None
@@ -326,6 +332,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"],
+                    help="statistics all-reduce at N > 1: fused over NVLink peer memory (default) or copy + NCCL")
     ap.add_argument("--parts", type=int, default=2, help="env slices (streams) per step; 1 = a single launch per step")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -366,7 +374,11 @@ def main():
     # next one's.  --parts 1 = one launch per step on the current stream.
     from air_hockey_training_environment_b200 import InterleavedStepper
     stepper = InterleavedStepper(env, parts=args.parts) if args.parts > 1 else None
-    red = StatsReducer(env, world, dev, stepper=stepper)
+    # the statistics exchange: fused over NVLink peer memory (ah_stats_allreduce) when the ranks can map each other's
+    # receive buffers (CUDA IPC), else a copy kernel + an NCCL all-reduce; --collective nccl forces the latter
+    from air_hockey_training_environment_b200.dist import PeerStats
+    peer = PeerStats(env) if (world > 1 and args.collective == "p2p") else None
+    red = StatsReducer(env, world, dev, stepper=stepper, peer=peer)
 
     def one_step(i: int):
         if stepper is not None:
@@ -493,6 +505,9 @@ def main():
         # per rank: one step kernel per step + one ah_stats copy kernel per rollout (every 16 steps and at the end)
         "gpu_launches": args.steps * max(1, args.parts) + stats_check["reductions"],
         "stats_allreduce": dict(stats_check, every_steps=ROLLOUT_STEPS,
+                                collective=("none (1 GPU)" if world == 1 else
+                                            ("fused P2P over NVLink peer memory (ah_stats_allreduce)" if red.peer is not None
+                                             else "ah_stats_bank + NCCL all-reduce" + (f" [p2p unavailable: {peer.error}]" if peer is not None else ""))),
                                 what="int64[20] episode/score statistics, summed over ranks (NCCL) once per rollout, "
                                      "inside the timed region; frames verified against world x envs x K x steps"),
         "clocks": clocks,

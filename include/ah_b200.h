@@ -310,6 +310,20 @@ int ah_pack_host(ah_env* env, int K, const void* d_reward, const uint8_t* d_done
 int ah_stats(ah_env* env, int64_t* d_out, int clear, void* stream);
 int ah_stats_bank(ah_env* env, int bank, int64_t* d_out, int clear, void* stream);
 
+/* The per-rollout exchange of the statistics vector, fused over NVLink peer memory for ranks on
+ * ONE box (one process per GPU): ah_stats_allreduce = ah_stats_bank's copy + clear AND the sum over all ranks in a single
+ * one-warp kernel -- every rank stores its vector straight into every rank's receive buffer (P2P), flags it, and spins
+ * until all contributions of the current exchange have landed; no NCCL launch, every rank gets the same sum.  It is a
+ * collective: every rank must call it equally often (a rank that never shows up makes the others report -1 in
+ * d_out[AH_NSTATS - 1] after ~2 s instead of hanging).  Set-up, once: each rank exports a handle of its receive buffer
+ * (ah_peer_export: cudaIpcGetMemHandle), the AH_IPC_HANDLE_BYTES x world handles are exchanged by the caller (e.g. an
+ * all_gather) and attached (ah_peer_attach: cudaIpcOpenMemHandle). */
+#define AH_MAX_PEERS 8
+#define AH_IPC_HANDLE_BYTES 64
+int ah_peer_export(ah_env* env, uint8_t* handle64);
+int ah_peer_attach(ah_env* env, int rank, int world, const uint8_t* handles /* [world][AH_IPC_HANDLE_BYTES] */);
+int ah_stats_allreduce(ah_env* env, int bank, int64_t* d_out, int clear, void* stream);
+
 /* Global frame counter (Philox action / sampling index), kept on the device so that captured graphs advance it;
  * get copies it (uint64[1]) to a caller device buffer.  (The ring's append counter lives in the ring: ah_ring.appended.) */
 int ah_set_counters(ah_env* env, uint64_t frame, void* stream);
