@@ -423,10 +423,13 @@ def main():
     barrier()
     t_wall1 = time.time()
     total_ms = ev0.elapsed_time(ev1)
+    per_rank_ms = [total_ms]
     if world > 1:
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
+        every = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(every, t)
+        per_rank_ms = [float(x.item()) for x in every]
+        total_ms = max(per_rank_ms)                              # the MAX over ranks is the job's time
     value = world * n * K * args.steps / (total_ms * 1e-3)
     stats_check = red.check(world * n * K * args.steps)          # the collective's payload, verified on every rank
 
@@ -500,6 +503,7 @@ def main():
                    "l2": "no flush: each step touches %.0f MB of distinct HBM lines (> 126 MB L2)" % (bytes_per_launch / 1e6),
                    "launch": env.launch_info(),
                    "launches_per_step": max(1, args.parts), "host_issue_us_per_step": host_issue_us,
+                   "per_rank_ms_per_step": [round(x / args.steps, 5) for x in per_rank_ms],
                    "interleaving": (f"each step = {args.parts} disjoint env slices on {args.parts} streams (sub-range launches of the same "
                                     "kernel); consecutive steps overlap tail-to-head" if args.parts > 1 else "one launch per step")},
         # per rank: one step kernel per step + one ah_stats copy kernel per rollout (every 16 steps and at the end)
@@ -553,18 +557,19 @@ _align_buf = {}
 
 
 def align_start(dev, world):
-    """Queued right before a start event.  (1) At N > 1 a one-element NCCL all-reduce: it completes on every GPU at the
-    same moment, so the ranks' timed regions open together ON THE DEVICE (the host barrier before it only aligns the
-    hosts to a few hundred microseconds, which a collective inside a ~2 ms timed region would otherwise expose as rank
-    skew).  (2) The GPU then spins (0.1 ms; 1 ms at N > 1) so that the host's first launches are already queued when the
-    region opens: the region measures K steps of device work, not the host's latency to issue the first one."""
+    """Queued right before a start event.  (1) The GPU spins (0.1 ms; ~1 ms at N > 1) so that the host's first launches
+    are already queued when the region opens: the region measures K steps of device work, not the host's latency to
+    issue the first one.  (2) At N > 1, AFTER the spin (whose length depends on each GPU's momentary clock), a
+    one-element NCCL all-reduce: it completes on every GPU at the same moment, so the ranks' timed regions open together
+    ON THE DEVICE -- the host barrier before it only aligns the hosts to a few hundred microseconds, which the collective
+    that closes a ~2 ms timed region would otherwise expose as rank skew in the max-over-ranks time."""
     import torch
     import torch.distributed as dist
+    torch.cuda._sleep(2_000_000 if world > 1 else 200_000)
     if world > 1:
         if dev not in _align_buf:
             _align_buf[dev] = torch.zeros(1, device=dev)
         dist.all_reduce(_align_buf[dev])
-    torch.cuda._sleep(2_000_000 if world > 1 else 200_000)
 
 
 def _time_loop(dev, fn, warm, reps, world=1, red=None):
