@@ -9,7 +9,17 @@ Restated from the reference (paths relative to the reference root):
     Monte-Carlo discounted returns, advantage = return - V(s)                lib/agents/ppo/ppo.py:142-160
     Adam, lr 1e-5, gamma 0.8, 10 epochs                                      lib/agents/ppo/model.py:30-44
 The reference's Keras/TF 1.12 learner cannot run in this image, so this module is checked against numpy
-restatements of the two loss formulas (tests/test_learners.py), not against the reference itself.
+restatements of the loss formulas and literal loops of the reference's target / projection code (tests/test_learners.py),
+not against the reference itself.
+
+Deliberate deviations of the policy-gradient learners (the value-based ones list theirs at each function):
+  * returns: the reference discounts over ``MemoryBuffer.retreive()``, which is NEWEST-FIRST (lib/buffer.py:27,45), i.e.
+    backwards in time; here rollouts are time-major with index 0 the OLDEST frame and ``discounted_returns`` is the
+    ordinary reward-to-go (the one function used by both learners; the collector has no copy of it);
+  * inputs: the reference trains on ``Observation.state``, the observation AFTER the first application of the action
+    (lib/agents/agent.py:61); PPO / A2C here train on ``obs[t]``, the policy's own input at the start of frame t
+    (lib/agents/agent.py:46) -- the state the stored action probabilities were computed from;
+  * BatchNorm uses Keras' defaults (eps 1e-3, momentum 0.99 = torch 0.01) so that exported / folded statistics match.
 """
 from __future__ import annotations
 
@@ -26,7 +36,7 @@ class CriticMLP(nn.Module):
 
     def __init__(self, state_size: int = 8):
         super().__init__()
-        self.net = nn.Sequential(nn.Linear(state_size, 6), nn.Tanh(), nn.Linear(6, 6), nn.Tanh(), nn.BatchNorm1d(6),
+        self.net = nn.Sequential(nn.Linear(state_size, 6), nn.Tanh(), nn.Linear(6, 6), nn.Tanh(), nn.BatchNorm1d(6, eps=1e-3, momentum=0.01),
                                  nn.Linear(6, 4), nn.Tanh(), nn.Linear(4, 1))
         for m in self.net:
             if isinstance(m, nn.Linear):
@@ -124,7 +134,7 @@ class A2CActor(nn.Module):
 
     def __init__(self, state_size: int = 8, action_size: int = 4):
         super().__init__()
-        self.net = nn.Sequential(nn.Linear(state_size, state_size), nn.ReLU(), nn.BatchNorm1d(state_size),
+        self.net = nn.Sequential(nn.Linear(state_size, state_size), nn.ReLU(), nn.BatchNorm1d(state_size, eps=1e-3, momentum=0.01),
                                  nn.Linear(state_size, action_size))
         for m in self.net:
             if isinstance(m, nn.Linear):
@@ -141,7 +151,7 @@ class A2CCritic(nn.Module):
 
     def __init__(self, state_size: int = 8):
         super().__init__()
-        self.net = nn.Sequential(nn.Linear(state_size, state_size), nn.ReLU(), nn.BatchNorm1d(state_size), nn.Linear(state_size, 1))
+        self.net = nn.Sequential(nn.Linear(state_size, state_size), nn.ReLU(), nn.BatchNorm1d(state_size, eps=1e-3, momentum=0.01), nn.Linear(state_size, 1))
 
     def forward(self, obs: torch.Tensor) -> torch.Tensor:
         return self.net(obs).squeeze(-1)

@@ -26,12 +26,12 @@ from .env import BatchedAirHockey, StepOutputs
 
 class ActorMLP(nn.Module):
     """The reference's discrete PPO actor: Dense(4, relu) - BatchNorm - Dense(6, relu) - Dense(4, relu) -
-    Dense(4, softmax)  (lib/agents/ppo/model.py:63-74; ``kernel_initializer="normal"`` is N(0, 0.05) in Keras).
-    Inference only (BatchNorm in eval mode)."""
+    Dense(4, softmax)  (lib/agents/ppo/model.py:63-74; ``kernel_initializer="normal"`` is N(0, 0.05) in Keras; BatchNorm
+    with Keras' defaults eps = 1e-3, momentum = 0.99, i.e. torch momentum 0.01).  Inference only (BatchNorm in eval mode)."""
 
     def __init__(self, state_size: int = 8, action_size: int = 4):
         super().__init__()
-        self.net = nn.Sequential(nn.Linear(state_size, 4), nn.ReLU(), nn.BatchNorm1d(4), nn.Linear(4, 6), nn.ReLU(),
+        self.net = nn.Sequential(nn.Linear(state_size, 4), nn.ReLU(), nn.BatchNorm1d(4, eps=1e-3, momentum=0.01), nn.Linear(4, 6), nn.ReLU(),
                                  nn.Linear(6, 4), nn.ReLU(), nn.Linear(4, action_size))
         for m in self.net:
             if isinstance(m, nn.Linear):
@@ -196,11 +196,3 @@ class RolloutCollector:
                 "scores": self.scores, "game_over": self.game_over, "probs": self.probs}
 
     _ran = False
-
-    def discounted_returns(self, gamma: float = 0.8) -> torch.Tensor:
-        """Monte-Carlo discounted returns over the rollout, ``rewards[j] += rewards[j+1] * gamma`` backwards in
-        time (lib/agents/ppo/ppo.py:142-146; gamma = 0.8 is the reference's PPO setting, ppo/model.py:37)."""
-        ret = self.rewards.clone()
-        for t in range(self.T - 2, -1, -1):
-            ret[t] += gamma * ret[t + 1]
-        return ret

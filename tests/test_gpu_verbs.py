@@ -109,7 +109,8 @@ def test_rollout_collector_is_zero_copy_and_consistent(use_graph):
         assert torch.allclose(r["probs"].sum(-1), torch.ones(T, n, device=env.device), atol=1e-5)
         assert int(r["actions"].min()) >= 0 and int(r["actions"].max()) <= 3
         assert len(torch.unique(r["actions"])) == 4
-    ret = col.discounted_returns(0.8)
+    from air_hockey_training_environment_b200.learners import discounted_returns
+    ret = discounted_returns(col.rewards, 0.8)
     assert torch.allclose(ret[-1], col.rewards[-1]) and torch.allclose(ret[-2], col.rewards[-2] + 0.8 * col.rewards[-1])
     assert env.stats()["frames"] == 3 * T * n
 
