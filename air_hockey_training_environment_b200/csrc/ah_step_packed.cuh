@@ -17,8 +17,8 @@
 //   and a POPC per 4 frames instead of three accumulations per frame.
 //
 // Other common-path savings over step_kernel (all result-preserving; FP64 stays bit-exact):
-//   * the action -> nudge map is a 256-entry shared table indexed by the raw action byte (no clamp), its shared
-//     address hoisted out of the loop;
+//   * the action -> nudge map is a 256-entry table indexed by the raw action byte (no clamp), in global memory read
+//     through L1 (no per-block table to fill);
 //   * "the puck's velocity may be out of limits" is carried as the contact-test threshold (1225, or +inf when
 //     dirty) instead of a flag tested beside it;
 //   * FP32 only: the goal / wall predicates of Rewards are single compares (valid because the puck has just been
@@ -120,18 +120,6 @@ __device__ const float2 g_nudge_f32[256] = {{0.f, 10.f}, {0.f, -10.f}, {-10.f, 0
 __device__ const double2 g_nudge_f64[256] = {{0., 10.}, {0., -10.}, {-10., 0.}, {10., 0.}};
 __device__ __forceinline__ float2 nudge_of(const float2* t, uint32_t byte) { return __ldg(t + byte); }
 __device__ __forceinline__ double2 nudge_of(const double2* t, uint32_t byte) { return __ldg(t + byte); }
-
-template <typename V2> __device__ __forceinline__ V2 lds_v2(uint32_t addr);
-template <> __device__ __forceinline__ float2 lds_v2<float2>(uint32_t addr) {
-    float2 v;
-    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
-    return v;
-}
-template <> __device__ __forceinline__ double2 lds_v2<double2>(uint32_t addr) {
-    double2 v;
-    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
-    return v;
-}
 
 // Launch geometry (measured on B200, n = 2^20, K = 8, FP32; gpurun_out r2c-r2e): blocks of 128
 // threads, 9 per SM (56 registers; the kernel needs 51) beat 256 x 4 by 1.5-2 us per launch -- a block's registers are
