@@ -254,3 +254,41 @@ def test_close_rollout_banks_partition_the_statistics():
     assert total == a.stats()
     assert b.stats(clear=False)["frames"] == 0 and int(b.stats_tensor(bank=1)[0]) == 0
     assert same(snapshot(a), snapshot(b))
+
+
+def test_interleaved_steps_inside_a_cuda_graph():
+    """A rollout of interleaved steps (2 slices on 2 streams per step, fork / join through events) captured in ONE CUDA
+    graph and replayed: same state, events and statistics as the eager single-stream path."""
+    from air_hockey_training_environment_b200 import InterleavedStepper
+    n, K, steps = 1 << 15, 8, 4
+    a, b = make_env(n, seed=6), make_env(n, seed=6)
+    for env in (a, b):
+        env.step(None, K=500, out=env.make_outputs(500, ()))
+        env.stats(clear=True)
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    acts = [torch.randint(0, 4, (2, n, 4), dtype=torch.uint8, device="cuda", generator=gen) for _ in range(steps)]
+    outs_a = [a.make_outputs(K, ("events", "obs_next")) for _ in range(steps)]
+    outs_b = [b.make_outputs(K, ("events", "obs_next")) for _ in range(steps)]
+    st = InterleavedStepper(b, parts=2)
+    saved = b.state_dict()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):                            # warm-up outside the capture
+        st.step(acts[0], K, outs_b[0]); st.join()
+    torch.cuda.current_stream().wait_stream(side)
+    b.load_state_dict(saved)
+    b.stats(clear=True)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for k in range(steps):
+            st.step(acts[k], K, outs_b[k])
+        st.join()
+    for rep in range(3):
+        for k in range(steps):
+            a.step(acts[k], K=K, out=outs_a[k])
+        g.replay()
+        torch.cuda.synchronize()
+        for k in range(steps):
+            assert torch.equal(outs_a[k].events, outs_b[k].events) and torch.equal(outs_a[k].obs_next, outs_b[k].obs_next)
+    assert same(snapshot(a), snapshot(b)) and a.stats() == b.stats()
+    assert a.counters() == b.counters()
