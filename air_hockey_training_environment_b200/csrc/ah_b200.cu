@@ -224,7 +224,9 @@ __device__ __forceinline__ void finish_stats(BlockStats& bs, DevBlock* blk, int 
     }
     if (lane != 0) return;
     if (!ORDERED) {
-        if (blockIdx.x == 0) blk->frame = *(volatile unsigned long long*)&blk->frame + (unsigned long long)K;
+        // (K == 0: a sub-range launch that does not own env 0 -- it must not touch the counter at all: a read-modify-write
+        //  of "+ 0" would race with the concurrent slice that does advance it)
+        if (blockIdx.x == 0 && K != 0) blk->frame = *(volatile unsigned long long*)&blk->frame + (unsigned long long)K;
         return;
     }
     __threadfence();

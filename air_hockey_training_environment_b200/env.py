@@ -609,6 +609,7 @@ class InterleavedStepper:
         self.stats_stream = torch.cuda.Stream(env.device)
         self.bank = 0
         self._forked = False
+        self._stats_pending = False                          # close_rollout queued work on stats_stream since the last join
         self._plans: Dict[tuple, list] = {}
 
     def step(self, actions: torch.Tensor, K: int, out: StepOutputs, **kw) -> StepOutputs:
@@ -651,12 +652,16 @@ class InterleavedStepper:
             with torch.cuda.stream(self.stats_stream):
                 self.env.stats_tensor(clear=True, out=stats_out, bank=self.bank)
         self.bank ^= 1
+        self._stats_pending = True
         return self.stats_stream
 
     def join(self) -> None:
         """Make the caller's current stream wait for every slice issued so far (no host sync)."""
         cur = torch.cuda.current_stream(self.env.device)
-        for s in self.streams:
-            cur.wait_stream(s)
-        cur.wait_stream(self.stats_stream)
+        if self._forked:
+            for s in self.streams:
+                cur.wait_stream(s)
+        if self._stats_pending:                              # (never wait on an idle stream: inside a CUDA-graph capture that
+            cur.wait_stream(self.stats_stream)               #  would be a dependency on uncaptured work)
+            self._stats_pending = False
         self._forked = False

@@ -515,3 +515,42 @@ def test_fp64_scrambled_states_at_scale_vs_oracle():
     g = env.stats()
     assert g["contacts_robot"] == o["contacts_robot"] > 20000 and g["contacts_opponent"] == o["contacts_opponent"] > 20000
     assert (ref["game_over"] != 0).sum() > 5000
+
+
+# ------------------------------------------------------------------------------ the LIVE reference, on this box
+def test_cuda_fp64_vs_the_live_reference_on_this_box():
+    """The reference itself (oracle/_ref: byte-compiled from /root/reference by oracle/fetch_ref.py; the live sources in
+    the development container) is run HERE, next to the GPU, on fresh seeded inputs -- not a committed fixture -- and the
+    FP64 CUDA path (unpacked and packed), the C oracle and the reference must agree bit for bit."""
+    from oracle import ref_loop, refshim
+    if not refshim.reference_available():
+        pytest.skip("oracle/_ref has not been built (run oracle/fetch_ref.py where /root/reference exists)")
+    from air_hockey_training_environment_b200.env import pack_actions, unpack_events
+    n, T = 12, 320
+    seed = int.from_bytes(os.urandom(4), "little")                                # fresh inputs every run
+    print("seed of this run:", seed)
+    rng = np.random.default_rng(seed)
+    actions = rng.integers(-1, 5, (T, n)).astype(np.int8)
+    table = rng.uniform(-10, 10, (n, 48, 2))
+    ref = ref_loop.run_reference(actions, table)
+    st, sc = oracle.initial_state(n)
+    orc = oracle.run_frames(st, sc, T, actions=actions, reset_table=table, record_every=1, want=("reward", "score", "done", "game_over"))
+    assert np.array_equal(bits(ref["states"]), bits(orc["states_rec"])) and np.array_equal(ref["reward"], orc["reward"])
+    env = make_env(n)
+    res = run_gpu(env, T, actions, table, 8)
+    assert np.array_equal(bits(ref["states"][7::8]), bits(res["states"]))
+    assert np.array_equal(ref["reward"].astype(np.float64), res["reward"].astype(np.float64))
+    assert np.array_equal(ref["score"], res["score"]) and np.array_equal(ref["done"], res["done"])
+    assert np.array_equal((ref["robot_win"] + 2 * ref["opponent_win"]).astype(np.uint8), res["game_over"])
+    for k in ("obs_state", "obs_new_state", "obs_next"):
+        assert np.array_equal(bits(ref[k]), bits(res[k]))
+    pk = make_env(n)
+    tab = torch.as_tensor(table, dtype=torch.float64).cuda().contiguous()
+    acts = torch.as_tensor(actions).cuda()
+    for t0 in range(0, T, 8):
+        out = pk.step(pack_actions(acts[t0:t0 + 8]), K=8, out=pk.make_outputs(8, ("events", "obs_next")), reset_table=tab)
+        ev = unpack_events(out.events, 8)
+        assert np.array_equal(ev["reward"].cpu().numpy().astype(np.int32), ref["reward"][t0:t0 + 8])
+        assert np.array_equal(ev["done"].cpu().numpy().astype(np.uint8), ref["done"][t0:t0 + 8])
+        assert np.array_equal(get_state13(pk).view(np.uint64), ref["states"][t0 + 7].view(np.uint64))
+    assert pk.stats()["done_ambiguous"] == 0
