@@ -79,6 +79,35 @@ __device__ __forceinline__ void rewards_bits(Env<R>& e, bool dot_fma, int& score
     e.prev_dist = nd;
 }
 
+// ---- FP32 only: Rewards.__call__ + the event byte WITHOUT the ALU pipe.  The frame loop is bound by the ALU pipe
+// (compares, selects, min/max: one warp-instruction per 2 cycles), not by issue slots, so the seven compares and the
+// integer assembly of the event byte are re-expressed on the FMA pipes: a predicate `a > b` becomes the 0/1 value
+// sat((a - b) * 2^40) -- one FFMA.SAT; IEEE subtraction gives the exact sign and an exact zero, and any non-zero
+// difference of these operands times 2^40 exceeds 1 -- and the byte is a short FFMA chain on those 0/1 values, biased
+// by 2^23 so that the integer sits in the low mantissa bits of the result, from where PRMT takes it.  Same results as
+// rewards_bits (tests/test_gpu_packed.py compares the packed kernel with step_kernel bit for bit).
+__device__ __forceinline__ float gt01(float a, float b) {            // (a > b) ? 1.0f : 0.0f
+    return __saturatef(fmaf(a, 1099511627776.0f, -b * 1099511627776.0f));
+}
+__device__ __forceinline__ float lt01(float a, float b) {            // (a < b) ? 1.0f : 0.0f
+    return __saturatef(fmaf(a, -1099511627776.0f, b * 1099511627776.0f));
+}
+__device__ __forceinline__ uint32_t rewards_event_fma(Env<float>& e, float& score_f) {
+    const float in_y = lt01(fabsf(240.0f - e.py), 95.0f);
+    score_f = in_y * (gt01(e.px, 870.0f) - lt01(e.px, 30.0f));      // +1 right goal, -1 left goal (the zones are disjoint)
+    float ex, ey;
+    Math<float>::sub2(ex, ey, e.px, e.py, e.rx, e.ry);
+    const float dsq = fmaf(ey, ey, ex * ex);
+    const float dn = lt01(dsq, 1225.0f);
+    const float nd = Math<float>::sqrt_(dsq);
+    const float closer = __saturatef((e.prev_dist - nd) * 1099511627776.0f);     // prev_dist may be +inf: inf -> 1
+    e.prev_dist = nd;
+    const float wall = gt01(e.px, 867.0f) - lt01(e.px, 28.0f);
+    // 2^23 + 0x11 + closer + wall + 10 done + 16 score: exact small integers, the byte is the low 8 mantissa bits
+    const float b = fmaf(score_f, 16.0f, fmaf(dn, 10.0f, (closer + wall) + 8388625.0f));
+    return __float_as_uint(b);
+}
+
 // the common tail of a sub-update with the speed-limit bookkeeping carried in `thr` (see file header)
 template <typename R, bool COMPUTER>
 __device__ __forceinline__ void physics_tail_thr(Env<R>& e, bool dot_fma, R& thr, int& contacts) {
@@ -136,6 +165,22 @@ constexpr int kPackedThreads = AH_PACKED_THREADS;
 template <typename R> struct PackedOcc { static constexpr int blocks = AH_PACKED_OCC_F32; };
 template <> struct PackedOcc<double> { static constexpr int blocks = 512 / AH_PACKED_THREADS; };
 
+// AirHockey.reset with the env's NEXT Philox draw precomputed: the draw for reset index `resets` depends only on
+// (seed, env id, resets), so every thread computes it once at the top of the launch -- all 32 lanes together, in the
+// shadow of the state loads -- instead of one lane of the warp running the 80-instruction generator inside the goal
+// branch (23 % of warp-frames).  A second reset of the same env in the launch (a game-over frame, or two goals within
+// K frames) falls back to the in-branch draw.  Same values either way: bitwise-identical results.
+template <typename R>
+__device__ __forceinline__ void env_reset_cached(Env<R>& e, bool total, const ResetSrc& rs, int64_t i, unsigned& overflow,
+                                                 R& next_dx, R& next_dy, bool& next_valid) {
+    if (rs.table != nullptr || !next_valid) { env_reset<R>(e, total, rs, i, overflow); return; }
+    if (total) { e.opp_score = 0; e.robot_score = 0; }
+    next_valid = false;
+    e.resets += 1;
+    e.px = K<R>::mid_x; e.py = K<R>::mid_y; e.pdx = next_dx; e.pdy = next_dy;
+    e.rdx = R(0); e.rdy = R(0); e.odx = R(0); e.ody = R(0);
+}
+
 template <typename R>
 __global__ void __launch_bounds__(kPackedThreads, PackedOcc<R>::blocks)
 step_packed_kernel(const PackedArgs<R> a) {
@@ -161,6 +206,13 @@ step_packed_kernel(const PackedArgs<R> a) {
         // contact-test threshold: radius^2, or +inf while the velocity may be outside the speed limits (injected
         // state, table resets): the rare branch then runs once and clamps (limit_puck_speed is idempotent)
         R thr = speed_out_of_limits<R>(e.pdx, e.pdy) ? (R)INFINITY : K<R>::radius_sq;
+        R next_dx = R(0), next_dy = R(0);
+#ifdef AH_RESET_CACHE                                      /* measured: no gain (section 4.5 of DESIGN.md); off by default */
+        bool next_valid = a.rs.table == nullptr;
+#else
+        bool next_valid = false;
+#endif
+        if (next_valid) reset_velocity(a.rs.seed, a.rs.env_id0 + (uint64_t)i, e.resets, next_dx, next_dy);
         int gf_base = e.game_frames;        // frames-in-game = gf_base + frames done in this launch
         // The current game's return is kept as "sum of r3 since r3_mark": reward = 2 r3 - 4, so
         // return = 2 (r3sum - r3_mark) - 4 frames_in_game.  One accumulator (r3sum) serves the launch statistics too.
@@ -185,16 +237,24 @@ step_packed_kernel(const PackedArgs<R> a) {
                 move_robot<R>(e, false, nd.x, nd.y);
                 physics_tail_thr<R, false>(e, dot_fma, thr, contacts);
                 // ---- Rewards                                           agent.py:70-71
-                int sc; bool dn, wl, wr, closer;
-                rewards_bits<R>(e, dot_fma, sc, dn, wl, wr, closer, amb);
                 // event byte: (reward + 4) / 2 = 1 + closer + wall + 2 done, done << 3, (score + 1) << 4, game_over << 6
-                uint32_t byte = (closer ? 0x12u : 0x11u) + (wr ? 1u : (wl ? 0xffffffffu : 0u)) + (dn ? 10u : 0u);
+                uint32_t byte; bool scored; int sc = 0;
+                if constexpr (Math<R>::exact) {
+                    bool dn, wl, wr, closer;
+                    rewards_bits<R>(e, dot_fma, sc, dn, wl, wr, closer, amb);
+                    byte = (closer ? 0x12u : 0x11u) + (wr ? 1u : (wl ? 0xffffffffu : 0u)) + (dn ? 10u : 0u) + (uint32_t)(sc * 16);
+                    scored = sc != 0;
+                } else {
+                    float score_f;
+                    byte = rewards_event_fma(e, score_f);     // (only byte 0 is meaningful: PRMT takes exactly that)
+                    scored = score_f != 0.0f;
+                    if (scored) sc = score_f > 0.0f ? 1 : -1;
+                }
                 // ---- env.update_score(score)                           game.py:142 -> airhockey.py:149-169
-                if (sc != 0) {
-                    byte += (uint32_t)(sc * 16);
+                if (scored) {
                     if (sc > 0) { e.robot_score += 1; stat_add(bs, AH_STAT_ROBOT_GOALS, 1); }
                     else { e.opp_score += 1; stat_add(bs, AH_STAT_OPPONENT_GOALS, 1); }
-                    env_reset<R>(e, false, a.rs, i, overflow);
+                    env_reset_cached<R>(e, false, a.rs, i, overflow, next_dx, next_dy, next_valid);
                     if (a.rs.table != nullptr) thr = (R)INFINITY;         // table values may exceed the limits
                     go = (e.robot_score == 10) ? 1 : go;                  // stats(): game.py:101-109
                     go = (e.opp_score == 10) ? 2 : go;
@@ -220,7 +280,7 @@ step_packed_kernel(const PackedArgs<R> a) {
                     stat_add(bs, AH_STAT_GAME_RETURN_SUM, 2 * (r3sum + part - r3_mark) - 4 * len);
                     r3_mark = r3sum + part;
                     gf_base = -kk;
-                    env_reset<R>(e, true, a.rs, i, overflow);
+                    env_reset_cached<R>(e, true, a.rs, i, overflow, next_dx, next_dy, next_valid);
                     if (a.rs.table != nullptr) thr = (R)INFINITY;
                     go = 0;
                 }
