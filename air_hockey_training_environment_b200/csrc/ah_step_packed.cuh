@@ -108,6 +108,34 @@ __device__ __forceinline__ uint32_t rewards_event_fma(Env<float>& e, float& scor
     return __float_as_uint(b);
 }
 
+// ---- FP32 only: AirHockey.computerAI (environment/airhockey.py:270-308) without compares and selects, in the same
+// spirit: the branch conditions become 0/1 values on the FMA pipes and the chosen velocity is a short arithmetic blend of
+// small exact integers.  Uses what Mallet.update guarantees, 470 <= opponent.x <= 880 and 20 <= opponent.y <= 460:
+//   x:  puck.x < 470 implies puck.x < opponent.x, puck.x > 880 implies puck.x > opponent.x, so
+//       dx = +1 (px < 470) | -1 (px > 880) | -2 / +2 / unchanged by the sign of px - ox in between          :272-283
+//   y:  py < oy -> (py < 20 ? +1 : -6)  [py < 20 implies py < oy];
+//       py > oy -> (py <= 360 ? +6 : (oy > 200 ? -2 : 0));  equal: unchanged                                    :285-300
+//   the +2, +2 puck nudge only when py > oy and |dy| < 40 and |dx| < 40                                       :303-305
+// All values are small exact integers and every blend coefficient is 0 or 1, so the arithmetic is exact.
+__device__ __forceinline__ float pos01(float d) { return __saturatef(d * 1099511627776.0f); }      // (d > 0) ? 1 : 0
+__device__ __forceinline__ void computer_ai_fma(Env<float>& e) {
+    float gx, gy;
+    Math<float>::sub2(gx, gy, e.px, e.py, e.ox, e.oy);               // puck - opponent: the AI's compares AND the nudge test
+    // x: dx = sign(gx) * (2 - 3 * [px < 470 or px > 880]); gx == 0 keeps the old value
+    const float sx = pos01(gx) - pos01(-gx);
+    const float far = lt01(e.px, 470.0f) + gt01(e.px, 880.0f);
+    e.odx = fmaf(sx, fmaf(far, -3.0f, 2.0f), (1.0f - fabsf(sx)) * e.odx);
+    // y: dy = 6 sign(gy) + 7 [py < 20] - [py > oy] [py > 360] (6 + 2 [oy > 200]); gy == 0 keeps the old value
+    const float y_gt = pos01(gy);
+    const float sy = y_gt - pos01(-gy);
+    const float up = fmaf(lt01(e.py, 20.0f), 7.0f, sy * 6.0f);
+    const float cap = (y_gt * gt01(e.py, 360.0f)) * fmaf(gt01(e.oy, 200.0f), 2.0f, 6.0f);
+    e.ody = fmaf(1.0f - fabsf(sy), e.ody, up - cap);
+    const float inc = (y_gt + y_gt) * (lt01(fabsf(gy), 40.0f) * lt01(fabsf(gx), 40.0f));      // 2 or 0      :303-305
+    Math<float>::add2(e.pdx, e.pdy, inc, inc);
+    mallet_update<float>(e.ox, e.oy, e.odx, e.ody, K<float>::opp_lo, K<float>::opp_hi);      // :307
+}
+
 // the common tail of a sub-update with the speed-limit bookkeeping carried in `thr` (see file header)
 template <typename R, bool COMPUTER>
 __device__ __forceinline__ void physics_tail_thr(Env<R>& e, bool dot_fma, R& thr, int& contacts) {
@@ -262,7 +290,8 @@ step_packed_kernel(const PackedArgs<R> a) {
                 byte += (uint32_t)go << 6;
                 ev = __byte_perm(ev, byte, 0x4321);                       // frames land in byte order
                 // ---- env.update_state(agent_name="computer"): sub-update #3   game.py:166
-                computer_ai<R>(e);
+                if constexpr (Math<R>::exact) computer_ai<R>(e);
+                else computer_ai_fma(e);
                 physics_tail_thr<R, true>(e, dot_fma, thr, contacts);
                 // ---- 10-goal game over                                 game.py:169-177
                 if (go != 0) {
