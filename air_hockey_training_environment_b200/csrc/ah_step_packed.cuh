@@ -189,6 +189,10 @@ __device__ __forceinline__ double2 nudge_of(const double2* t, uint32_t byte) { r
 #ifndef AH_PACKED_OCC_F32
 #define AH_PACKED_OCC_F32 9
 #endif
+#ifndef AH_FRAME_UNROLL
+#define AH_FRAME_UNROLL 1
+#endif
+constexpr int kFrameUnroll = AH_FRAME_UNROLL;        // frames of a quad unrolled together (tuning: section 4.5 of DESIGN.md)
 constexpr int kPackedThreads = AH_PACKED_THREADS;
 template <typename R> struct PackedOcc { static constexpr int blocks = AH_PACKED_OCC_F32; };
 template <> struct PackedOcc<double> { static constexpr int blocks = 512 / AH_PACKED_THREADS; };
@@ -254,7 +258,7 @@ step_packed_kernel(const PackedArgs<R> a) {
             if (left > 4) aw_next = a.actions[off + n];
             uint32_t ev = 0;
             int jr = kc;                    // frames left in the quad, counting the current one
-#pragma unroll 1
+#pragma unroll (kFrameUnroll)
             do {
                 const V2 nd = nudge_of(nudge_tab, aw & 0xffu);
                 aw >>= 8;
