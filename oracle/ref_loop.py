@@ -147,6 +147,7 @@ def run_reference(actions: np.ndarray, reset_table: np.ndarray,
             out["final_scores"][e] = (env.robot_score, env.opponent_score)
     finally:
         np.random.uniform = saved_uniform
+        refshim.uninstall()                    # leave no stub modules behind in the calling process
     return out
 
 
@@ -168,4 +169,5 @@ def run_reference_substeps(calls, init_state: Optional[np.ndarray] = None) -> np
         env.update_state(action, name)
         p, r, o = env.puck, env.robot, env.opponent
         rows.append([p.x, p.y, p.dx, p.dy, r.x, r.y, r.dx, r.dy, o.x, o.y, o.dx, o.dy])
+    refshim.uninstall()
     return np.array(rows, dtype=np.float64)

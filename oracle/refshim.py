@@ -81,6 +81,19 @@ def reference_kind() -> str:
 
 
 _installed = False
+_stubbed = {}
+
+
+def uninstall() -> None:
+    """Take the stub modules out of ``sys.modules`` again (the already-imported reference keeps its own references).
+    A process that goes on to use torch must not be left with a ``MagicMock`` named ``tensorflow``: optional-dependency
+    probes (``importlib.util.find_spec``) choke on a module without ``__spec__``."""
+    global _installed
+    for name, mod in _stubbed.items():
+        if sys.modules.get(name) is mod:
+            del sys.modules[name]
+    _stubbed.clear()
+    _installed = False
 
 
 def install() -> None:
@@ -112,16 +125,19 @@ def install() -> None:
     redis.StrictRedis = _Redis
     redis.ConnectionError = type("ConnectionError", (Exception,), {})
     sys.modules["redis"] = redis
+    _stubbed["redis"] = redis
 
     for name in ("keras", "keras.backend", "keras.layers", "keras.models", "keras.optimizers",
                  "keras.initializers", "keras.utils", "tensorflow", "imp"):
-        sys.modules.setdefault(name, MagicMock())
+        if name not in sys.modules:
+            sys.modules[name] = _stubbed[name] = MagicMock()
     # `class NoisyDense(Layer)` must be definable
     sys.modules["keras.layers"].Layer = type("Layer", (object,), {})
 
     pytz = types.ModuleType("pytz")
     pytz.timezone = lambda name: datetime.timezone.utc
-    sys.modules["pytz"] = pytz
+    if "pytz" not in sys.modules:
+        sys.modules["pytz"] = _stubbed["pytz"] = pytz
 
     if not hasattr(np, "Infinity"):
         np.Infinity = np.inf
