@@ -501,7 +501,9 @@ def main():
         "config": {"workload": workload_name(world), "envs_per_gpu": n, "frames_per_step": K,
                    "sub_updates_per_sec": 3 * value,
                    "l2": "no flush: each step touches %.0f MB of distinct HBM lines (> 126 MB L2)" % (bytes_per_launch / 1e6),
-                   "launch": env.launch_info(),
+                   # packed rollout kernel (csrc/ah_step_packed.cuh): one env per thread, 128-thread blocks, 9 resident per SM
+                   "launch": {"kernel": "step_packed_kernel<float>", "threads": 128, "blocks_per_step": -(-n // 128),
+                              "resident_blocks_per_sm": 9, "sms": env.launch_info()["sms"]},
                    "launches_per_step": max(1, args.parts), "host_issue_us_per_step": host_issue_us,
                    "per_rank_ms_per_step": [round(x / args.steps, 5) for x in per_rank_ms],
                    "interleaving": (f"each step = {args.parts} disjoint env slices on {args.parts} streams (sub-range launches of the same "

@@ -341,7 +341,8 @@ int ah_get_counters(ah_env* env, uint64_t* d_out1, void* stream);
 int ah_ring_sample(ah_env* env, const ah_ring* ring, int continuous, int64_t batch, uint64_t draw, void* d_state,
                    void* d_action, void* d_reward, uint8_t* d_done, void* d_new_state, int64_t* d_index, void* stream);
 
-/* Launch geometry actually used by ah_step (for reports): blocks, threads per block, SM count. */
+/* Launch geometry of the general step kernels (for reports): blocks, threads per block, SM count.  The packed rollout
+ * kernel (AH_ACT_DISCRETE_PACKED4) always launches ceil(env_count / 128) blocks of 128 threads, one env per thread. */
 int ah_launch_info(const ah_env* env, int* blocks, int* threads, int* sms);
 
 /* Build self-test: writes a*b+c of a discriminating triple to d_scratch (device double[1]); the value is 0.0
