@@ -182,6 +182,7 @@ class DevicePolicy:
         self.c.theta, self.c.dt = theta, dt
         self.weights: Optional[torch.Tensor] = None
         self.noise_state: Optional[torch.Tensor] = None
+        self.source, self._seen_version = module, None        # export_if_dense: the module whose parameters are watched
         if select == "ou":                                   # OrnsteinUhlenbeckProcess.reset_states (random.py:66-67)
             if n_envs is None:
                 raise ValueError("the OU process keeps one state per env: pass n_envs")
@@ -230,6 +231,18 @@ class DevicePolicy:
             self.weights.copy_(packed)                       # same storage: captured graphs keep seeing the new weights
         self.c.weights = self.weights.data_ptr()
 
+    def refresh_if_changed(self) -> bool:
+        """``refresh()`` only if a parameter / buffer of the source module was written since the last export (torch bumps a
+        tensor's version counter on every in-place write, which is how optimisers update)."""
+        if self.source is None:
+            return False
+        v = _param_version(self.source)
+        if v == self._seen_version:
+            return False
+        self.refresh()
+        self._seen_version = v
+        return True
+
     @property
     def n_actions(self) -> int:
         return int(self.c.n_actions)
@@ -240,3 +253,56 @@ class DevicePolicy:
 
     def ref(self):
         return C.byref(self.c)
+
+
+def _param_version(module: nn.Module) -> int:
+    """Changes whenever an optimiser (or anyone) writes a parameter or buffer of ``module`` in place."""
+    return sum(int(t._version) for t in list(module.parameters()) + list(module.buffers()))
+
+
+def export_if_dense(policy, env, select: str = "sample", rtol: float = 1e-4, atol: float = 2e-5) -> Optional[DevicePolicy]:
+    """Try to export a torch policy ``obs [N,8] -> action probabilities / values [N,A]`` for the kernels, and VERIFY the
+    export: the device network is evaluated on the envs' current observations (``ah_policy_act``) and must reproduce
+    ``policy(obs)``.  Candidates: the module itself when it is a dense chain (``dense_chain_of``), else its only
+    ``nn.Sequential`` child (a wrapper whose ``forward`` is the chain, or a softmax over it -- ``rollout.ActorMLP``,
+    ``learners.A2CActor``).  Returns None when the policy is not a module, has no exportable chain, is too wide / deep
+    for the kernel, or does anything in ``forward`` the export cannot see -- callers then evaluate it with torch."""
+    if not isinstance(policy, nn.Module) or policy.training and any(isinstance(m, nn.BatchNorm1d) for m in policy.modules()):
+        return None
+    candidates = []
+    try:
+        _, implied = dense_chain_of(policy)
+        candidates.append((policy, implied or "values"))
+    except (TypeError, ValueError):
+        seqs = [m for m in policy.children() if isinstance(m, nn.Sequential)]
+        if len(seqs) == 1 and len(list(policy.children())) == 1:
+            candidates += [(seqs[0], "softmax"), (seqs[0], "values")]
+    if not candidates:
+        return None
+    # two probes: the envs' current observations, and the same scaled down (networks saturate on raw pixel coordinates,
+    # and a saturated softmax hides what happened to the logits)
+    real = env.get_state("robot")
+    probes = [real, (real * 0.01).contiguous()]
+    try:
+        with torch.no_grad():
+            wants = [policy(o) for o in probes]
+    except RuntimeError:                           # e.g. a float32 module on a float64 env: not ours to run
+        return None
+    if any(not torch.is_tensor(w) or w.dim() != 2 or w.shape[0] != env.n for w in wants):
+        return None
+    for module, head in candidates:
+        try:
+            dp = DevicePolicy(module, env.device, head=head, select=select)
+        except (TypeError, ValueError):
+            continue
+        if dp.continuous or dp.n_actions != wants[0].shape[1]:
+            continue
+        got = torch.empty(env.n, dp.n_actions, dtype=env.dtype, device=env.device)
+        same = True
+        for o, want in zip(probes, wants):
+            env.policy_act(dp, obs=o, values_out=got)
+            same = same and torch.allclose(got.to(want.dtype), want, rtol=rtol, atol=atol)
+        if same:
+            dp.source, dp._seen_version = policy, _param_version(policy)
+            return dp
+    return None

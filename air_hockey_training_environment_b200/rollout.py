@@ -92,21 +92,34 @@ class RolloutCollector:
 
     def __init__(self, env: BatchedAirHockey, T: int, policy: Optional[Callable[[torch.Tensor], torch.Tensor]] = None,
                  action_size: int = 4, use_graph: bool = True, seed: int = 0, fused_actor: bool = True,
-                 single_launch: Optional[bool] = None, device_policy=None, device_select: bool = True):
+                 single_launch: Optional[bool] = None, device_policy=None, device_select: bool = True,
+                 auto_export: bool = True):
         """policy:        any callable obs [N,8] -> action probabilities [N,A] (a torch module); default: ``ActorMLP``
         device_policy: a ``policy.DevicePolicy`` exported from a torch module: the WHOLE T-frame closed loop (network,
                        exploration strategy, physics, rewards, resets) runs in ONE launch (AH_ACT_POLICY_MLP)
+        auto_export:   a torch ``policy`` that is a small dense network (``policy.export_if_dense``: a Linear / ReLU / Tanh /
+                       BatchNorm chain, or a module wrapping one, verified numerically against the module on the envs'
+                       observations) is exported and run as a ``device_policy``; its parameters are re-exported at the
+                       next ``collect()`` whenever an optimiser has written them.  ``single_launch=False`` opts out
         device_select: for a torch ``policy`` that cannot be exported, sample the action from its probabilities with
                        ``ah_policy_act`` (Philox, on the device) instead of ``torch.multinomial`` + dtype copies"""
         self.env, self.T, self.A = env, int(T), int(action_size)
         n, dt, dev = env.n, env.dtype, env.device
+        self.auto_exported = False
+        if device_policy is None and policy is None:
+            policy = ActorMLP(8, action_size).to(device=dev, dtype=dt)
+        if (device_policy is None and auto_export and single_launch is not False and isinstance(policy, nn.Module)
+                and not (fused_actor and isinstance(policy, ActorMLP))):
+            from .policy import export_if_dense
+            device_policy = export_if_dense(policy, env)
+            self.auto_exported = device_policy is not None
         self.device_policy = device_policy
         if device_policy is not None:
             if device_policy.continuous:
                 raise ValueError("RolloutCollector collects discrete-action rollouts")
             self.A = action_size = device_policy.n_actions
             policy = policy if policy is not None else device_policy.module
-        self.policy = policy if policy is not None else ActorMLP(8, action_size).to(device=dev, dtype=dt)
+        self.policy = policy
         self._selector = None
         if device_select and device_policy is None:
             from .policy import DevicePolicy
@@ -178,6 +191,8 @@ class RolloutCollector:
             if self._ran:
                 self.obs[0].copy_(self.obs[self.T])
             if self.device_policy is not None:
+                if self.auto_exported:
+                    self.device_policy.refresh_if_changed()      # the torch module stays the owner of the parameters
                 self.env.step(None, K=self.T, out=self._out_all, policy=self.device_policy)
             else:
                 self.env.step(None, K=self.T, out=self._out_all, policy_weights=self.fused.weights)

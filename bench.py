@@ -685,18 +685,22 @@ def run_philox_sim(env, dev, n, K):
 def run_ppo_rollout(dev, world=1, rank=0):
     """BASELINE config 5: per GPU 65,536 envs x 128 frames under a torch policy (the reference-shaped actor MLP), the
     rollout tensors written zero-copy on the device; one all-reduce of the statistics per rollout, inside the timed
-    region.  Variants: (a) ANY torch module evaluated by torch + the library's fused categorical sampler + env.step per
-    frame, captured in one CUDA graph; (b) the fused actor+sampling kernel + env.step per frame in one CUDA graph;
+    region.  Variants: (a) ANY torch callable evaluated by torch + the library's fused categorical sampler + env.step per
+    frame, captured in one CUDA graph; (a') the same torch module handed to the collector as it is: recognised as a small
+    dense network, exported (checked against the module) and run in ONE launch per rollout; (b) the fused actor+sampling kernel + env.step per frame in one CUDA graph;
     (c) the whole closed loop in ONE launch (in-kernel actor); (d) the same single launch for ANY small torch MLP exported
     with policy.DevicePolicy (the reference's PPO actor shape; the dueling Q-net with epsilon-greedy exploration).  At
-    world > 1 only (a), (c) and the first (d) are timed."""
+    world > 1 only (a), (a') and (c) are timed."""
     import torch
     from air_hockey_training_environment_b200 import BatchedAirHockey
     from air_hockey_training_environment_b200.rollout import RolloutCollector
     n, T = 65536, 128
     res = {"envs_per_gpu": n, "frames": T, "unit": UNIT, "n_gpus": world}
     from air_hockey_training_environment_b200 import policy as ahp
-    variants = [("torch_policy_graph", dict(fused_actor=False)), ("fused_actor_graph", dict(single_launch=False)),
+    variants = [("torch_policy_graph", dict(fused_actor=False, auto_export=False)),
+                # a plain torch module handed to the collector: exported after a numerical check, then ONE launch per rollout
+                ("torch_module_auto_exported", dict(fused_actor=False)),
+                ("fused_actor_graph", dict(single_launch=False)),
                 ("single_launch", dict(single_launch=True)),
                 # ANY small torch MLP, exported (policy.DevicePolicy): network + exploration strategy + physics in ONE launch
                 ("exported_ppo_actor_single_launch", lambda: dict(device_policy=ahp.DevicePolicy(ahp.ppo_actor_discrete().to(dev), dev))),
@@ -704,7 +708,7 @@ def run_ppo_rollout(dev, world=1, rank=0):
                  lambda: dict(device_policy=ahp.DevicePolicy(ahp.DuelingQNet(4).to(dev), dev, select="eps_greedy", epsilon=0.1,
                                                              initial_epsilon=0.1, final_epsilon=0.1)))]
     if world > 1:
-        variants = [variants[0], variants[2], variants[3]]
+        variants = [variants[0], variants[1], variants[3]]
     for name, kw in variants:
         env = BatchedAirHockey(n, dtype=torch.float32, device=dev, seed=7, env_id0=rank * n)
         env.step(None, K=2000, out=env.make_outputs(2000, ()))        # decorrelate the games

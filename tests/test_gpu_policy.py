@@ -236,3 +236,47 @@ def test_policy_argument_errors():
     with pytest.raises(AhError):
         bad = policy.DevicePolicy(policy.a2c_actor().cuda(), env.device, select="gaussian")   # noise on a discrete head
         env.policy_act(bad)
+
+
+# ---------------------------------------------------------------- a plain torch module handed to the rollout collector
+def test_rollout_collector_exports_dense_torch_policies_and_follows_the_optimiser():
+    """``RolloutCollector(policy=<torch module>)``: a small dense network (here a wrapper whose forward is a softmax over an
+    nn.Sequential, like the reference-shaped actors) is exported after a numerical check against the module and the whole
+    rollout runs in one launch; its probabilities equal the module's; parameters written by an optimiser reach the
+    kernel at the next collect(); a callable the library cannot see into stays on the torch path."""
+    from air_hockey_training_environment_b200 import policy
+    from air_hockey_training_environment_b200.learners import A2CActor
+    from air_hockey_training_environment_b200.rollout import RolloutCollector
+    n, T = 2048, 12
+    torch.manual_seed(3)
+    actor = randomize(A2CActor(), 0.3).cuda().eval()
+    a, b, c = make_env(n, seed=5), make_env(n, seed=5), make_env(n, seed=5)
+    col = RolloutCollector(a, T, policy=actor)
+    assert col.auto_exported and col.single_launch and col.device_policy.head == "softmax"
+    ref = RolloutCollector(b, T, device_policy=policy.DevicePolicy(actor.net, b.device, head="softmax"))
+    r, rr = col.collect(), ref.collect()
+    for k in ("obs", "actions", "rewards", "dones", "probs"):
+        assert torch.equal(r[k], rr[k]), k
+    with torch.no_grad():
+        assert torch.allclose(r["probs"][T - 1], actor(r["obs"][T - 1]), rtol=1e-4, atol=2e-5)
+    # an optimiser step (in-place parameter write) is picked up without an explicit refresh
+    opt = torch.optim.SGD(actor.parameters(), lr=0.02)
+    sum(p.sum() for p in actor.parameters()).backward()                    # every parameter moves by -0.02
+    opt.step()
+    r = col.collect()
+    with torch.no_grad():
+        want = actor(r["obs"][3])
+    assert torch.allclose(r["probs"][3], want, rtol=1e-4, atol=2e-5)
+    assert not col.device_policy.refresh_if_changed()                      # nothing written since
+    # not exportable: an opaque callable, a module that does more than its chain, a network wider than the kernel's limit
+    opaque = RolloutCollector(c, T, policy=lambda obs: actor(obs))
+    assert not opaque.auto_exported and not opaque.single_launch
+
+    class Tempered(A2CActor):
+        def forward(self, obs):
+            return torch.softmax(self.net(obs) / 3.0, dim=-1)
+    assert policy.export_if_dense(randomize(Tempered(), 0.3).cuda().eval(), c) is None
+    assert policy.export_if_dense(randomize(A2CActor(), 0.3).cuda().eval(), c) is not None
+    wide = nn.Sequential(nn.Linear(8, 64), nn.ReLU(), nn.Linear(64, 4), nn.Softmax(dim=-1)).cuda().eval()
+    assert policy.export_if_dense(wide, c) is None
+    assert policy.export_if_dense(policy.DuelingQNet(4).cuda().eval(), c).head == "dueling"
