@@ -457,9 +457,9 @@ def main():
     # --parts 1 that IS the average launch duration; with slices the launches of consecutive steps overlap tail-to-head
     # and it is the time per step's worth of launches.  Beside it: a single whole-n launch timed back-to-back on one
     # stream (`single_launch_ms`) and with an event pair around every launch (`kernel_ms_isolated`).
-    kernel_ms = kernel_ms_isolated = single_launch_ms = None
+    kernel_ms_isolated = single_launch_ms = None
+    kernel_ms = total_ms / args.steps                # at N > 1: the slowest rank's; the roofline below is per GPU
     if world == 1:
-        kernel_ms = total_ms / args.steps
         barrier()
         single_launch_ms = _time_loop(dev, lambda i: env.step(acts[i % n_act], K=K, out=out), 20, max(args.steps, 100))
         reps = min(args.steps, 200)
@@ -527,11 +527,11 @@ def main():
         hbm_ach = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
         line["roofline"] = {
             "bound": "fp32", "achieved": lane_ach, "peak": lane_peak, "unit": "Glane-op/s", "frac": lane_ach / lane_peak,
-            "traffic": profile_fact("dram_bytes_per_launch"),
+            "traffic": profile_fact("dram_bytes_per_launch"), "per": "GPU",
             "kernel": "ah::step_packed_kernel<float>", "kernel_ms": kernel_ms,
             "kernel_ms_isolated": kernel_ms_isolated, "single_launch_ms": single_launch_ms,
             "single_launch_frac": (LANE_OPS_PER_ENV_STEP * n * K / (single_launch_ms * 1e-3) / 1e9 / lane_peak) if single_launch_ms else None,
-            "note": "K=8 fused frames: bound by FP32/ALU-pipe issue, not HBM (north_star: the slower of FP32 peak and "
+            "note": "K=8 fused frames: bound by FP32 instruction issue, not HBM (north_star: the slower of FP32 peak and "
                     "state bytes over HBM bandwidth). achieved = 254 algorithmic lane-ops/env-step x env-steps/s; "
                     "peak = 148 SMs x 128 FP32 lanes x SM clock under load. kernel_ms = timed region / steps (each step = "
                     "`launches_per_step` sub-range launches whose tails and heads overlap across steps); single_launch_* = one "
