@@ -971,7 +971,15 @@ int launch_step(ah_env* env, const ah_step_io* io, int K, cudaStream_t s) {
         while (pth > 64 && (count + pth - 1) / pth < 4 * (int64_t)env->sms) pth >>= 1;
         const int64_t pwant = (count + pth - 1) / pth;
         const unsigned pgrid = (unsigned)(pwant < max_blocks ? pwant : max_blocks);
-        ah::step_packed_kernel<R><<<pgrid, pth, 0, s>>>(p);
+        if (io->ring) {
+            p.ring_state = (R*)io->ring->state; p.ring_new_state = (R*)io->ring->new_state;
+            p.ring_action = reinterpret_cast<int8_t*>(io->ring->action);
+            p.ring_reward = (R*)io->ring->reward; p.ring_done = io->ring->done; p.ring_capacity = io->ring->capacity;
+            p.ring_appended = reinterpret_cast<unsigned long long*>(io->ring->appended);
+            ah::step_packed_kernel<R, true><<<pgrid, pth, 0, s>>>(p);
+        } else {
+            ah::step_packed_kernel<R, false><<<pgrid, pth, 0, s>>>(p);
+        }
         const cudaError_t pe = cudaGetLastError();
         return pe == cudaSuccess ? AH_OK : cuda_fail(env, pe);
     }
@@ -1180,7 +1188,8 @@ int ah_step(ah_env* env, const ah_step_io* io, int K, void* stream) {
     if ((io->env_first != 0 || io->env_count != 0) && !io->events) return AH_EINVAL;     // sub-ranges: packed mode only
     if (io->events) {
         if ((reinterpret_cast<uintptr_t>(io->events) & 3u) || (reinterpret_cast<uintptr_t>(io->actions) & 3u)) return AH_EINVAL;
-        if (io->reward || io->done || io->score || io->game_over || io->obs_state || io->obs_new_state || io->ring ||
+        if (io->ring && (io->env_first != 0 || (io->env_count != 0 && io->env_count != env->n))) return AH_EINVAL;   // ring append: whole-n launches
+        if (io->reward || io->done || io->score || io->game_over || io->obs_state || io->obs_new_state ||
             io->actions_out || io->probs_out || (io->obs_next && io->obs_next_per_frame) || env->cfg.friction) return AH_EINVAL;
     }
     if ((io->probs_out && kind != AH_ACT_POLICY && kind != AH_ACT_POLICY_MLP) || (kind == AH_ACT_POLICY && !aligned16(io->probs_out))) return AH_EINVAL;

@@ -40,6 +40,13 @@ struct PackedArgs {
     int collect_stats, dot_fma, stats_bank;
     DevBlock* blk;
     uint32_t i0, i_end;           // envs [i0, i_end) are stepped by this launch (row strides stay n)
+    // RING variant: the fused MemoryBuffer.append of every frame's Observation tuple (lib/buffer.py:24-32), slot of
+    // frame k = (appended + k) mod capacity, the ring's own device counter advanced by K at the end of the launch
+    R* ring_state; R* ring_new_state;     // [capacity][n][8]
+    int8_t* ring_action;                  // [capacity][n]
+    R* ring_reward; uint8_t* ring_done;   // [capacity][n]
+    int64_t ring_capacity;
+    unsigned long long* ring_appended;
 };
 
 // ---- Rewards.__call__ as predicates (lib/rewards.py:118-142); see rewards_call for the line-by-line citations.
@@ -194,8 +201,14 @@ __device__ __forceinline__ double2 nudge_of(const double2* t, uint32_t byte) { r
 #endif
 constexpr int kFrameUnroll = AH_FRAME_UNROLL;        // frames of a quad unrolled together (tuning: section 4.5 of DESIGN.md)
 constexpr int kPackedThreads = AH_PACKED_THREADS;
-template <typename R> struct PackedOcc { static constexpr int blocks = AH_PACKED_OCC_F32; };
-template <> struct PackedOcc<double> { static constexpr int blocks = 512 / AH_PACKED_THREADS; };
+#ifndef AH_PACKED_OCC_RING
+#define AH_PACKED_OCC_RING 6
+#endif
+// RING: the append variant is bound by the write path (70 B per env-frame) and carries the ring cursor.  Measured (2^20 envs,
+// K = 8): 6 (66 registers, 7 resident blocks) 140.7 us, 8 (60 registers) 154.5 us, 9 (56, spills) 191 us -- more resident
+// warps put more half-row stores in flight than L1 can merge before they leave for L2.
+template <typename R, bool RING> struct PackedOcc { static constexpr int blocks = RING ? AH_PACKED_OCC_RING : AH_PACKED_OCC_F32; };
+template <bool RING> struct PackedOcc<double, RING> { static constexpr int blocks = 512 / AH_PACKED_THREADS; };
 
 // AirHockey.reset with the env's NEXT Philox draw precomputed: the draw for reset index `resets` depends only on
 // (seed, env id, resets), so every thread computes it once at the top of the launch -- all 32 lanes together, in the
@@ -213,8 +226,8 @@ __device__ __forceinline__ void env_reset_cached(Env<R>& e, bool total, const Re
     e.rdx = R(0); e.rdy = R(0); e.odx = R(0); e.ody = R(0);
 }
 
-template <typename R>
-__global__ void __launch_bounds__(kPackedThreads, PackedOcc<R>::blocks)
+template <typename R, bool RING>
+__global__ void __launch_bounds__(kPackedThreads, PackedOcc<R, RING>::blocks)
 step_packed_kernel(const PackedArgs<R> a) {
     using V2 = typename std::conditional<sizeof(R) == 4, float2, double2>::type;
     __shared__ BlockStats bs;
@@ -230,6 +243,10 @@ step_packed_kernel(const PackedArgs<R> a) {
     const int quads = (nK + 3) >> 2;
     int r3sum = 0, r3sq = 0, dones = 0, contacts = 0, frames = 0, bad = 0, amb = 0;
     unsigned overflow = 0;
+    // RING: every block reads the ring's counter at its start, so it may only advance once every block is done
+    // (finish_stats<true>: fence + ticket); the launch covers all envs (the host refuses sub-ranges with a ring)
+    int64_t slot0 = 0;
+    if constexpr (RING) slot0 = (int64_t)(*a.ring_appended % (unsigned long long)a.ring_capacity);
 
     for (uint32_t i = a.i0 + blockIdx.x * blockDim.x + threadIdx.x; i < a.i_end; i += stride) {
         Env<R> e = load_env<R>(a.st, i);
@@ -251,6 +268,7 @@ step_packed_kernel(const PackedArgs<R> a) {
         int r3_mark = r3sum - ((e.game_return + 4 * e.game_frames) >> 1);
         uint32_t off = i;                   // word (q, i) of the quad-major action / event arrays: q * n + i
         int left = nK;                      // frames left at the start of the quad
+        int64_t slot = slot0, rrow = slot0 * (int64_t)n + i;      // RING: row (slot, i) of the [capacity][n] ring arrays
 #pragma unroll 1
         do {
             const int kc = left < 4 ? left : 4;
@@ -260,14 +278,26 @@ step_packed_kernel(const PackedArgs<R> a) {
             int jr = kc;                    // frames left in the quad, counting the current one
 #pragma unroll (kFrameUnroll)
             do {
-                const V2 nd = nudge_of(nudge_tab, aw & 0xffu);
+                V2 nd;
+                if constexpr (RING) {
+                    // no table load here: with 70 B of stores per frame in flight, a load that the frame's first instruction
+                    // depends on queues behind them in the L1 pipeline (ncu: long_scoreboard 6.5 warps per issue slot)
+                    const uint32_t ab = aw & 0xffu;
+                    nd.y = ab == 0u ? K<R>::step : (ab == 1u ? -K<R>::step : R(0));
+                    nd.x = ab == 3u ? K<R>::step : (ab == 2u ? -K<R>::step : R(0));
+                    a.ring_action[rrow] = (int8_t)ab;
+                } else {
+                    nd = nudge_of(nudge_tab, aw & 0xffu);
+                }
                 aw >>= 8;
                 // ---- robot.move(a): sub-update #1                      game.py:136 -> agent.py:32-36
                 move_robot<R>(e, false, nd.x, nd.y);
                 physics_tail_thr<R, false>(e, dot_fma, thr, contacts);
+                if constexpr (RING) store_obs<R>(a.ring_state, rrow, get_state<R>(e, true));       // Observation.state      agent.py:61
                 // ---- robot.step(a) -> self.move(a): sub-update #2      agent.py:64
                 move_robot<R>(e, false, nd.x, nd.y);
                 physics_tail_thr<R, false>(e, dot_fma, thr, contacts);
+                if constexpr (RING) store_obs<R>(a.ring_new_state, rrow, get_state<R>(e, true));   // Observation.new_state  agent.py:67
                 // ---- Rewards                                           agent.py:70-71
                 // event byte: (reward + 4) / 2 = 1 + closer + wall + 2 done, done << 3, (score + 1) << 4, game_over << 6
                 uint32_t byte; bool scored; int sc = 0;
@@ -281,6 +311,12 @@ step_packed_kernel(const PackedArgs<R> a) {
                     byte = rewards_event_fma(e, score_f);     // (only byte 0 is meaningful: PRMT takes exactly that)
                     scored = score_f != 0.0f;
                     if (scored) sc = score_f > 0.0f ? 1 : -1;
+                }
+                if constexpr (RING) {        // the rest of the Observation tuple: reward = 2 (byte & 7) - 4, done = bit 3
+                    a.ring_reward[rrow] = (R)(2 * (int)(byte & 7u) - 4);
+                    a.ring_done[rrow] = (uint8_t)((byte >> 3) & 1u);
+                    slot += 1; rrow += (int64_t)n;
+                    if (slot == a.ring_capacity) { slot = 0; rrow = i; }
                 }
                 // ---- env.update_score(score)                           game.py:142 -> airhockey.py:149-169
                 if (scored) {
@@ -340,8 +376,8 @@ step_packed_kernel(const PackedArgs<R> a) {
     // reward = 2 r3 - 4  =>  sum = 2 S1 - 4 F,  sum of squares = 4 S2 - 16 S1 + 16 F
     const int reward_sum = 2 * r3sum - 4 * frames;
     const int reward_sq = 4 * r3sq - 16 * r3sum + 16 * frames;
-    finish_stats<false>(bs, a.blk, a.stats_bank, a.collect_stats, frames, reward_sum, reward_sq, dones, contacts & 0xffff, contacts >> 16,
-                 (int)overflow, bad, amb, a.i0 == 0 ? nK : 0, nullptr);
+    finish_stats<RING>(bs, a.blk, a.stats_bank, a.collect_stats, frames, reward_sum, reward_sq, dones, contacts & 0xffff, contacts >> 16,
+                       (int)overflow, bad, amb, a.i0 == 0 ? nK : 0, RING ? a.ring_appended : nullptr);
 }
 
 }  // namespace ah

@@ -58,9 +58,12 @@ def peaks():
 
 def profile_fact(name, default=None):
     """Numbers that only ncu can provide (committed under profiles/ from the last capture of this kernel)."""
-    p = os.path.join(ROOT, "profiles", "step_kernel_facts.json")
-    if os.path.exists(p):
-        return json.load(open(p)).get(name, default)
+    for f in ("step_kernel_facts.json", "ring_kernel_facts.json"):
+        p = os.path.join(ROOT, "profiles", f)
+        if os.path.exists(p):
+            facts = json.load(open(p))
+            if name in facts:
+                return facts[name]
     return default
 
 
@@ -645,22 +648,24 @@ def run_ring_append(env, dev, n, K, world=1):
     timed region and its payload checked.  HBM-bound (write-heavy): the roofline is per GPU."""
     import torch
     from air_hockey_training_environment_b200 import ReplayRing
+    from air_hockey_training_environment_b200.env import pack_actions
     ring = ReplayRing(2 * K, n, env.dtype, dev)
-    out = env.make_outputs(K, ("reward", "done", "score", "game_over", "obs_next"))
-    acts = [torch.randint(0, 4, (K, n), dtype=torch.int8, device=dev) for _ in range(4)]
+    out = env.make_outputs(K, ("events", "obs_next"))
+    acts = [pack_actions(torch.randint(0, 4, (K, n), dtype=torch.int8, device=dev)) for _ in range(4)]
     red = StatsReducer(env, world, dev)
     reps = 96
     ms = _time_loop(dev, lambda i: env.step(acts[i % 4], K=K, out=out, ring=ring), 16, reps, world, red)
     chk = red.check(world * n * K * reps)
     hbm_peak, src, _ = peaks()
-    b = n * (2 * STATE_BYTES + 32 + K * (1 + 4 + 1 + 1 + 1) + K * 70)
+    b = n * (2 * STATE_BYTES + 32 + K * (1 + 1) + K * 70)      # state in + out, obs_next, action + event byte, the 70-B tuple
     ach = b / (ms * 1e-3) / 1e9
     del ring
     torch.cuda.empty_cache()
     return {"value": world * n * K / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "n_gpus": world, "envs_total": world * n,
             "ring_capacity_frames": 2 * K, "stats_allreduce": chk,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                         "per": "GPU", "traffic": None, "algorithmic_bytes_per_launch": b, "bytes_per_env_step": b / (n * K)}}
+                         "per": "GPU", "traffic": profile_fact("ring_dram_bytes_per_launch"), "kernel": "ah::step_packed_kernel<float, RING>",
+                         "algorithmic_bytes_per_launch": b, "bytes_per_env_step": b / (n * K)}}
 
 
 def run_unpacked(env, dev, n, K):

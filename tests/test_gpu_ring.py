@@ -247,3 +247,64 @@ def test_memory_buffer_retrieve_average():
     assert avg["state"].shape == (1, 1, 8) and avg["state"][0, 0, :2].tolist() == [3, 4]
     newest = ring.retreive()["state"][:, 0, :2].tolist()
     assert newest == [[2, 1], [4, 6], [5, 6], [3, 4]]        # appendleft: newest first (lib/buffer.py:27)
+
+
+# ---------------------------------------------------------------- the packed rollout mode with the fused append
+@pytest.mark.parametrize("dtype,K,cap", [(torch.float32, 8, 16), (torch.float64, 6, 5), (torch.float32, 3, 7)])
+def test_packed_mode_ring_append_equals_the_general_kernel(dtype, K, cap):
+    """``step(packed actions, out.events, ring=...)`` (ah::step_packed_kernel<R, RING>) appends exactly what the general
+    kernel appends -- state, action, reward, done, new_state of every frame, slot by slot, across launches that wrap the
+    ring -- and leaves the same env state, event bytes and ring counter."""
+    from air_hockey_training_environment_b200 import ReplayRing
+    from air_hockey_training_environment_b200.env import pack_actions, unpack_events
+    n = 1000                                             # not a multiple of the block size
+    a, b = make_env(n, dtype, seed=12), make_env(n, dtype, seed=12)
+    for env in (a, b):
+        env.step(None, K=700, out=env.make_outputs(700, ()))         # contacts, goals and resets are happening
+    ra, rb = ReplayRing(cap, n, a.dtype, a.device), ReplayRing(cap, n, b.dtype, b.device)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for launch in range(4):
+        acts = torch.randint(0, 4, (K, n), dtype=torch.int8, device="cuda", generator=g)
+        oa = a.step(pack_actions(acts), K=K, out=a.make_outputs(K, ("events", "obs_next")), ring=ra)
+        ob = b.step(acts, K=K, out=b.make_outputs(K, ("reward", "done", "score", "game_over", "obs_next")), ring=rb)
+        ev = unpack_events(oa.events, K)
+        assert torch.equal(ev["reward"].to(b.dtype), ob.reward) and torch.equal(ev["done"], ob.done.bool())
+        assert torch.equal(oa.obs_next, ob.obs_next)
+        assert ra.appended == rb.appended == (launch + 1) * K
+        for x, y in ((ra.state, rb.state), (ra.new_state, rb.new_state), (ra.action, rb.action), (ra.reward, rb.reward),
+                     (ra.done, rb.done)):
+            assert torch.equal(x, y)
+    for x, y in zip((a.puck, a.robot, a.opponent, a.prev_dist, a.meta), (b.puck, b.robot, b.opponent, b.prev_dist, b.meta)):
+        assert torch.equal(x, y)
+    assert a.stats() == b.stats() and a.counters() == b.counters()
+    got, want = ra.retreive(), rb.retreive()
+    assert all(torch.equal(got[k], want[k]) for k in want)
+
+
+def test_packed_mode_ring_append_under_graph_replay_and_argument_errors():
+    from air_hockey_training_environment_b200 import AhError, ReplayRing
+    from air_hockey_training_environment_b200.env import pack_actions
+    n, K, cap = 512, 4, 6
+    env, ref = make_env(n, seed=3), make_env(n, seed=3)
+    ring, rref = ReplayRing(cap, n, env.dtype, env.device), ReplayRing(cap, n, ref.dtype, ref.device)
+    acts = pack_actions(torch.randint(0, 4, (K, n), dtype=torch.int8, device="cuda"))
+    out = env.make_outputs(K, ("events", "obs_next"))
+    plan = env.plan_step(acts, K=K, out=out, ring=ring)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        env.launch(plan)                                  # warm-up launch outside the capture
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        env.launch(plan)
+    for _ in range(3):
+        g.replay()
+    for _ in range(4):
+        ref.step(acts, K=K, out=ref.make_outputs(K, ("events", "obs_next")), ring=rref)
+    assert ring.appended == rref.appended == 16           # the device counter advanced inside the replays
+    assert torch.equal(ring.state, rref.state) and torch.equal(ring.reward, rref.reward)
+    got, want = ring.retreive(), rref.retreive()
+    assert all(torch.equal(got[k], want[k]) for k in want)
+    with pytest.raises(AhError):                          # the append needs the whole env range in one launch
+        env.step(acts, K=K, out=out, ring=ring, env_range=(0, 256))
