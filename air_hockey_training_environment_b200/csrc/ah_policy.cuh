@@ -23,7 +23,10 @@
 
 namespace ah {
 
-constexpr int kPolThreads = 128;                       // block size of every kernel that evaluates a policy
+#ifndef AH_POL_THREADS
+#define AH_POL_THREADS 128
+#endif
+constexpr int kPolThreads = AH_POL_THREADS;            // block size of every kernel that evaluates a policy
 constexpr int kPolMaxW = AH_POLICY_MAX_WIDTH;
 constexpr int kPolMaxFloats = (8 * kPolMaxW + kPolMaxW) + 3 * (kPolMaxW * kPolMaxW + kPolMaxW);
 
