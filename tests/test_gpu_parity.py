@@ -554,3 +554,44 @@ def test_cuda_fp64_vs_the_live_reference_on_this_box():
         assert np.array_equal(ev["done"].cpu().numpy().astype(np.uint8), ref["done"][t0:t0 + 8])
         assert np.array_equal(get_state13(pk).view(np.uint64), ref["states"][t0 + 7].view(np.uint64))
     assert pk.stats()["done_ambiguous"] == 0
+
+
+def test_cuda_fp64_vs_the_live_reference_from_scrambled_states():
+    """Same as above from random NON-integer states (contacts, wall clamps, both speed-clamp signs, goals, scores one goal
+    from game over, out-of-range actions) drawn fresh every run: reference == oracle == CUDA FP64 (unpacked, K = 8 packed)."""
+    from oracle import ref_loop, refshim
+    from oracle.gen_golden import scrambled_states
+    if not refshim.reference_available():
+        pytest.skip("oracle/_ref has not been built (run oracle/fetch_ref.py where /root/reference exists)")
+    from air_hockey_training_environment_b200.env import pack_actions, unpack_events
+    n, T = 24, 160
+    seed = int.from_bytes(os.urandom(4), "little")
+    print("seed of this run:", seed)
+    rng = np.random.default_rng(seed)
+    actions = rng.integers(-1, 6, (T, n)).astype(np.int8)
+    table = rng.uniform(-10, 10, (n, 40, 2))
+    init = scrambled_states(rng, n)
+    init_scores = rng.integers(0, 10, (n, 2)).astype(np.int32)
+    init_scores[: n // 3] = rng.integers(8, 10, (n // 3, 2))
+    ref = ref_loop.run_reference(actions, table, init_state=init, init_scores=init_scores)
+    assert ref["reset_cursor"].max() < 40
+    env = make_env(n)
+    put_state(env, init, init_scores)
+    res = run_gpu(env, T, actions, table, 1)
+    assert np.array_equal(bits(ref["states"]), bits(res["states"])) and np.array_equal(ref["scores"], res["scores"])
+    assert np.array_equal(ref["reward"].astype(np.float64), res["reward"].astype(np.float64))
+    assert np.array_equal(ref["score"], res["score"]) and np.array_equal(ref["done"], res["done"])
+    assert np.array_equal((ref["robot_win"] + 2 * ref["opponent_win"]).astype(np.uint8), res["game_over"])
+    for k in ("obs_state", "obs_new_state", "obs_next"):
+        assert np.array_equal(bits(ref[k]), bits(res[k])), k
+    assert env.stats()["done_ambiguous"] == 0
+    pk = make_env(n)
+    put_state(pk, init, init_scores)
+    tab = torch.as_tensor(table, dtype=torch.float64).cuda().contiguous()
+    acts = torch.as_tensor(actions).cuda()
+    for t0 in range(0, T, 8):
+        out = pk.step(pack_actions(acts[t0:t0 + 8]), K=8, out=pk.make_outputs(8, ("events", "obs_next")), reset_table=tab)
+        ev = unpack_events(out.events, 8)
+        assert np.array_equal(ev["reward"].cpu().numpy().astype(np.int32), ref["reward"][t0:t0 + 8])
+        assert np.array_equal(ev["score"].cpu().numpy().astype(np.int32), ref["score"][t0:t0 + 8].astype(np.int32))
+        assert np.array_equal(get_state13(pk).view(np.uint64), ref["states"][t0 + 7].view(np.uint64))
