@@ -10,18 +10,19 @@ environments, FP32 throughput build, one bench "step" = 8 fused frames for every
 opponent and Rewards reward, one event byte (reward, done, score, game_over) per env-frame and the next observation
 [n, 8] written, statistics reduced in-kernel.  A step is issued as `--parts` (default 2) disjoint env slices on as many
 streams (sub-range launches of the same kernel; consecutive steps overlap tail-to-head); the statistics are copied out --
-and at N > 1 all-reduced over NCCL -- once per rollout of 16 steps and at the end of the timed region, and the reduced
-payload is verified.  1 env-step = 1 frame of Game.play (3 physics sub-updates + reward + score / game-over handling).
+and at N > 1 all-reduced (by the library's fused exchange over NVLink peer memory, `--collective p2p`, or NCCL,
+`--collective nccl`) -- once per rollout of 16 steps and at the end of the timed region, and the reduced payload is verified.  1 env-step = 1 frame of Game.play (3 physics sub-updates + reward + score / game-over handling).
 
 `value`        device-resident throughput (actions already in HBM), CUDA events, max over ranks.
 `e2e`          the public HOST-buffer API (host.HostStepper): every step's actions come from pinned HOST memory (H2D inside
                the timed region) and the step's results (event bytes, next observation) go back to pinned host memory;
                `e2e.roofline` = the same copies without the kernels (the host link's measured ceiling).
-`roofline`     the fused K=8 kernel is bound by FP32/ALU-pipe issue, not by HBM: `achieved` counts the
-               ALGORITHMIC lane-ops (254 per env-step) per second against 148 SMs x 128 lanes x SM
-               clock; `single_launch_*` = one whole-n launch per step; the HBM view of the same step is beside it.
-`extras`       BASELINE configs 4 (fused ring append) and 5 (PPO rollouts) at this world size, the HBM-bound K=1 mode,
-               round 1's unpacked kernel, the FP64 validation build.
+`roofline`     the fused K=8 kernel is bound by FP32 instruction issue, not by HBM: `achieved` counts
+               the ALGORITHMIC lane-ops (254 per env-step) per second against 148 SMs x 128 lanes x SM
+               clock, per GPU; `single_launch_*` = one whole-n launch per step (N = 1); the HBM view of the same step is
+               beside it.
+`extras`       BASELINE configs 4 (the packed step with the fused ring append; HBM roofline) and 5 (PPO rollouts) at this
+               world size; at N = 1 also the HBM-bound K=1 mode, round 1's unpacked kernel, the FP64 validation build.
 `cpu_baseline` the reference's OWN Python implementation (oracle/_ref: byte-compiled from /root/reference by
                oracle/fetch_ref.py) on this box's host cores: BASELINE config 1, one process and a pool over all cores
                (kind "reference"); the C port (kind "port") beside it.  `--impl reference` times the same reference.
