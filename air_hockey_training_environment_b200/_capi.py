@@ -28,7 +28,8 @@ SYMBOLS = ("ah_strerror", "ah_abi_version", "ah_last_cuda_error", "ah_create", "
 
 
 class AhConfig(C.Structure):
-    _fields_ = [("dot_fma", C.c_int32), ("friction", C.c_int32), ("no_prefetch", C.c_int32), ("reserved", C.c_int32 * 5)]
+    _fields_ = [("dot_fma", C.c_int32), ("friction", C.c_int32), ("no_prefetch", C.c_int32), ("no_packed_core", C.c_int32),
+                ("reserved", C.c_int32 * 4)]
 
 
 class AhRing(C.Structure):

@@ -959,26 +959,27 @@ int launch_step(ah_env* env, const ah_step_io* io, int K, cudaStream_t s) {
     while (threads > 64 && (env->n + threads - 1) / threads < 4 * (int64_t)env->sms) threads >>= 1;
     int64_t want = (env->n + threads - 1) / threads;
     const unsigned grid = (unsigned)(want < max_blocks ? want : max_blocks);
-    if (io->events) {                                        // PACKED rollout mode (ah_step_packed.cuh)
-        ah::PackedArgs<R> p;
-        memset(&p, 0, sizeof p);
-        p.st = a.st; p.n = env->n; p.K = K;
+    // the packed-core kernel (ah_step_packed.cuh): one env per thread, blocks of kPackedThreads
+    ah::PackedArgs<R> p;
+    memset(&p, 0, sizeof p);
+    p.st = a.st; p.n = env->n; p.K = K;
+    p.obs_next = (R*)io->obs_next; p.rs = a.rs; p.collect_stats = io->collect_stats; p.dot_fma = env->cfg.dot_fma; p.blk = env->blk; p.stats_bank = io->stats_bank;
+    const int64_t count = io->env_count > 0 ? io->env_count : env->n;
+    p.i0 = (uint32_t)io->env_first; p.i_end = (uint32_t)(io->env_first + count);
+    int pth = ah::kPackedThreads;
+    while (pth > 64 && (count + pth - 1) / pth < 4 * (int64_t)env->sms) pth >>= 1;
+    const int64_t pwant = (count + pth - 1) / pth;
+    const unsigned pgrid = (unsigned)(pwant < max_blocks ? pwant : max_blocks);
+    if (io->events) {                                        // PACKED rollout mode
         p.actions = reinterpret_cast<const uint32_t*>(io->actions); p.events = reinterpret_cast<uint32_t*>(io->events);
-        p.obs_next = (R*)io->obs_next; p.rs = a.rs; p.collect_stats = io->collect_stats; p.dot_fma = env->cfg.dot_fma; p.blk = env->blk; p.stats_bank = io->stats_bank;
-        const int64_t count = io->env_count > 0 ? io->env_count : env->n;
-        p.i0 = (uint32_t)io->env_first; p.i_end = (uint32_t)(io->env_first + count);
-        int pth = ah::kPackedThreads;
-        while (pth > 64 && (count + pth - 1) / pth < 4 * (int64_t)env->sms) pth >>= 1;
-        const int64_t pwant = (count + pth - 1) / pth;
-        const unsigned pgrid = (unsigned)(pwant < max_blocks ? pwant : max_blocks);
         if (io->ring) {
             p.ring_state = (R*)io->ring->state; p.ring_new_state = (R*)io->ring->new_state;
             p.ring_action = reinterpret_cast<int8_t*>(io->ring->action);
             p.ring_reward = (R*)io->ring->reward; p.ring_done = io->ring->done; p.ring_capacity = io->ring->capacity;
             p.ring_appended = reinterpret_cast<unsigned long long*>(io->ring->appended);
-            ah::step_packed_kernel<R, true><<<pgrid, pth, 0, s>>>(p);
+            ah::step_packed_kernel<R, ah::IO_RING><<<pgrid, pth, 0, s>>>(p);
         } else {
-            ah::step_packed_kernel<R, false><<<pgrid, pth, 0, s>>>(p);
+            ah::step_packed_kernel<R, ah::IO_PACKED><<<pgrid, pth, 0, s>>>(p);
         }
         const cudaError_t pe = cudaGetLastError();
         return pe == cudaSuccess ? AH_OK : cuda_fail(env, pe);
@@ -999,6 +1000,20 @@ int launch_step(ah_env* env, const ah_step_io* io, int K, cudaStream_t s) {
         case AH_ACT_POLICY: act = 4; break;
         case AH_ACT_POLICY_MLP: act = 5; break;
         default: return AH_EINVAL;                            // AH_ACT_DISCRETE_PACKED4 is only valid with io->events
+    }
+    // the same arithmetic core behind the general API's tensors (K > 2: the small-K launches are HBM-bound and keep the
+    // prefetching variant below) and for the pure simulation with in-kernel Philox actions
+    if (mode == ah::MODE_LEAN && io->action_kind == AH_ACT_DISCRETE && K > 2 && !env->cfg.no_packed_core) {
+        p.actions8 = reinterpret_cast<const int8_t*>(io->actions);
+        p.reward = (R*)io->reward; p.done = io->done; p.score = io->score; p.game_over = io->game_over;
+        ah::step_packed_kernel<R, ah::IO_UNPACKED><<<pgrid, pth, 0, s>>>(p);
+        const cudaError_t pe = cudaGetLastError();
+        return pe == cudaSuccess ? AH_OK : cuda_fail(env, pe);
+    }
+    if (mode == ah::MODE_SIM && act == 3 && !env->cfg.no_packed_core) {
+        ah::step_packed_kernel<R, ah::IO_PHILOX><<<pgrid, pth, 0, s>>>(p);
+        const cudaError_t pe = cudaGetLastError();
+        return pe == cudaSuccess ? AH_OK : cuda_fail(env, pe);
     }
 #define AH_LAUNCH(ACT_, MODE_) ah::step_kernel<R, ACT_, MODE_><<<grid, threads, 0, s>>>(a)
 #define AH_LAUNCH_MODE(ACT_) do { if (mode == ah::MODE_LEAN) AH_LAUNCH(ACT_, ah::MODE_LEAN); \

@@ -47,7 +47,27 @@ struct PackedArgs {
     R* ring_reward; uint8_t* ring_done;   // [capacity][n]
     int64_t ring_capacity;
     unsigned long long* ring_appended;
+    // IO_UNPACKED: the general API's tensors -- time-major int8 actions in, four per-frame outputs out
+    const int8_t* actions8;               // i8 [K][n]
+    R* reward; uint8_t* done; int8_t* score; uint8_t* game_over;     // [K][n] each
 };
+
+// What crosses the register file per frame (compile-time; the arithmetic is the same in all four):
+//   IO_PACKED    quad-major uint8 actions in, one event byte per env-frame out              (the headline mode)
+//   IO_RING      IO_PACKED + the fused replay-ring append                                    (BASELINE config 4)
+//   IO_UNPACKED  int8 [K][n] actions in; reward real / done u8 / score i8 / game_over u8 [K][n] out   (BatchedAirHockey.step's
+//                default tensors: the event byte is decoded into the caller's four tensors as it is produced)
+//   IO_PHILOX    actions drawn in the kernel (Philox stream 1, frame-indexed), no per-frame output: pure simulation
+enum { IO_PACKED = 0, IO_RING = 1, IO_UNPACKED = 2, IO_PHILOX = 3 };
+
+// the actions of up to 4 consecutive frames of env i, gathered from the time-major int8 tensor into one word
+__device__ __forceinline__ uint32_t gather_quad_actions(const int8_t* p, uint32_t n, int count) {
+    uint32_t w = (uint32_t)(uint8_t)p[0];
+    if (count > 1) w |= (uint32_t)(uint8_t)p[n] << 8;
+    if (count > 2) w |= (uint32_t)(uint8_t)p[2 * (size_t)n] << 16;
+    if (count > 3) w |= (uint32_t)(uint8_t)p[3 * (size_t)n] << 24;
+    return w;
+}
 
 // ---- Rewards.__call__ as predicates (lib/rewards.py:118-142); see rewards_call for the line-by-line citations.
 // IN_FRAME: the puck was just advanced by Puck.update (5 <= px <= 895), which lets the FP32 build test the goal and
@@ -207,8 +227,9 @@ constexpr int kPackedThreads = AH_PACKED_THREADS;
 // RING: the append variant is bound by the write path (70 B per env-frame) and carries the ring cursor.  Measured (2^20 envs,
 // K = 8): 6 (66 registers, 7 resident blocks) 140.7 us, 8 (60 registers) 154.5 us, 9 (56, spills) 191 us -- more resident
 // warps put more half-row stores in flight than L1 can merge before they leave for L2.
-template <typename R, bool RING> struct PackedOcc { static constexpr int blocks = RING ? AH_PACKED_OCC_RING : AH_PACKED_OCC_F32; };
-template <bool RING> struct PackedOcc<double, RING> { static constexpr int blocks = 512 / AH_PACKED_THREADS; };
+// (IO_UNPACKED / IO_PHILOX need 58-60 registers: 8 blocks per SM instead of spilling at 9)
+template <typename R, int IO> struct PackedOcc { static constexpr int blocks = IO == 1 ? AH_PACKED_OCC_RING : (IO >= 2 ? 8 : AH_PACKED_OCC_F32); };
+template <int IO> struct PackedOcc<double, IO> { static constexpr int blocks = 512 / AH_PACKED_THREADS; };
 
 // AirHockey.reset with the env's NEXT Philox draw precomputed: the draw for reset index `resets` depends only on
 // (seed, env id, resets), so every thread computes it once at the top of the launch -- all 32 lanes together, in the
@@ -226,9 +247,11 @@ __device__ __forceinline__ void env_reset_cached(Env<R>& e, bool total, const Re
     e.rdx = R(0); e.rdy = R(0); e.odx = R(0); e.ody = R(0);
 }
 
-template <typename R, bool RING>
-__global__ void __launch_bounds__(kPackedThreads, PackedOcc<R, RING>::blocks)
+template <typename R, int IO>
+__global__ void __launch_bounds__(kPackedThreads, PackedOcc<R, IO>::blocks)
 step_packed_kernel(const PackedArgs<R> a) {
+    constexpr bool RING = IO == IO_RING;
+    constexpr bool ORDERED = IO == IO_RING || IO == IO_PHILOX;      // the launch reads a device counter at its start
     using V2 = typename std::conditional<sizeof(R) == 4, float2, double2>::type;
     __shared__ BlockStats bs;
     if (threadIdx.x < AH_NSTATS) bs.v[threadIdx.x] = 0;
@@ -247,10 +270,18 @@ step_packed_kernel(const PackedArgs<R> a) {
     // (finish_stats<true>: fence + ticket); the launch covers all envs (the host refuses sub-ranges with a ring)
     int64_t slot0 = 0;
     if constexpr (RING) slot0 = (int64_t)(*a.ring_appended % (unsigned long long)a.ring_capacity);
+    unsigned long long frame0 = 0ull;
+    if constexpr (IO == IO_PHILOX) frame0 = a.blk->frame;
 
     for (uint32_t i = a.i0 + blockIdx.x * blockDim.x + threadIdx.x; i < a.i_end; i += stride) {
         Env<R> e = load_env<R>(a.st, i);
-        uint32_t aw = a.actions[i];
+        uint32_t aw = 0;
+        const int8_t* ap = nullptr;                    // IO_UNPACKED: &actions8[first frame of the quad][i]
+        if constexpr (IO == IO_PACKED || IO == IO_RING) aw = a.actions[i];
+        if constexpr (IO == IO_UNPACKED) { ap = a.actions8 + i; aw = gather_quad_actions(ap, n, nK < 4 ? nK : 4); }
+        Philox4 ablock = {};
+        uint32_t ablock_id = 0xffffffffu;
+        int64_t row = (int64_t)i;                      // IO_UNPACKED: element (frame, i) of the [K][n] output tensors
         int go = (e.robot_score == 10) ? 1 : ((e.opp_score == 10) ? 2 : 0);   // only reachable through injected state
         // contact-test threshold: radius^2, or +inf while the velocity may be outside the speed limits (injected
         // state, table resets): the rare branch then runs once and clamps (limit_puck_speed is idempotent)
@@ -273,11 +304,20 @@ step_packed_kernel(const PackedArgs<R> a) {
         do {
             const int kc = left < 4 ? left : 4;
             uint32_t aw_next = 0;
-            if (left > 4) aw_next = a.actions[off + n];
+            if constexpr (IO == IO_PACKED || IO == IO_RING) { if (left > 4) aw_next = a.actions[off + n]; }
+            if constexpr (IO == IO_UNPACKED) {
+                if (left > 4) { ap += 4 * (size_t)n; aw_next = gather_quad_actions(ap, n, left - 4 < 4 ? left - 4 : 4); }
+            }
             uint32_t ev = 0;
             int jr = kc;                    // frames left in the quad, counting the current one
 #pragma unroll (kFrameUnroll)
             do {
+                if constexpr (IO == IO_PHILOX) {       // the frame's action from the env's action stream (csrc/ah_rng.cuh)
+                    const unsigned long long f = frame0 + (unsigned long long)(nK - left + kc - jr);
+                    const uint32_t bid = (uint32_t)(f >> 6);
+                    if (bid != ablock_id) { ablock = action_block(a.rs.seed, a.rs.env_id0 + (uint64_t)i, bid); ablock_id = bid; }
+                    aw = (uint32_t)action_from_block(ablock, (uint32_t)(f & 63u));
+                }
                 V2 nd;
                 if constexpr (RING) {
                     // no table load here: with 70 B of stores per frame in flight, a load that the frame's first instruction
@@ -327,6 +367,13 @@ step_packed_kernel(const PackedArgs<R> a) {
                     go = (e.robot_score == 10) ? 1 : go;                  // stats(): game.py:101-109
                     go = (e.opp_score == 10) ? 2 : go;
                 }
+                if constexpr (IO == IO_UNPACKED) {     // the event byte decoded into the caller's four tensors
+                    a.reward[row] = (R)(2 * (int)(byte & 7u) - 4);
+                    a.done[row] = (uint8_t)((byte >> 3) & 1u);
+                    a.score[row] = (int8_t)((int)((byte >> 4) & 3u) - 1);
+                    a.game_over[row] = (uint8_t)go;
+                    row += (int64_t)n;
+                }
                 byte += (uint32_t)go << 6;
                 ev = __byte_perm(ev, byte, 0x4321);                       // frames land in byte order
                 // ---- env.update_state(agent_name="computer"): sub-update #3   game.py:166
@@ -355,7 +402,7 @@ step_packed_kernel(const PackedArgs<R> a) {
                 }
             } while (--jr > 0);
             if (left < 4) ev >>= 8 * (4 - left);                           // partial last quad: frame 0 in byte 0
-            a.events[off] = ev;
+            if constexpr (IO == IO_PACKED || IO == IO_RING) a.events[off] = ev;
             // statistics of the quad from the packed word
             const uint32_t r3 = ev & 0x07070707u;
             r3sum = (int)__dp4a(r3, 0x01010101u, (uint32_t)r3sum);
@@ -376,8 +423,8 @@ step_packed_kernel(const PackedArgs<R> a) {
     // reward = 2 r3 - 4  =>  sum = 2 S1 - 4 F,  sum of squares = 4 S2 - 16 S1 + 16 F
     const int reward_sum = 2 * r3sum - 4 * frames;
     const int reward_sq = 4 * r3sq - 16 * r3sum + 16 * frames;
-    finish_stats<RING>(bs, a.blk, a.stats_bank, a.collect_stats, frames, reward_sum, reward_sq, dones, contacts & 0xffff, contacts >> 16,
-                       (int)overflow, bad, amb, a.i0 == 0 ? nK : 0, RING ? a.ring_appended : nullptr);
+    finish_stats<ORDERED>(bs, a.blk, a.stats_bank, a.collect_stats, frames, reward_sum, reward_sq, dones, contacts & 0xffff, contacts >> 16,
+                          (int)overflow, bad, amb, a.i0 == 0 ? nK : 0, RING ? a.ring_appended : nullptr);
 }
 
 }  // namespace ah

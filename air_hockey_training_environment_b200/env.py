@@ -189,7 +189,8 @@ class BatchedAirHockey:
     """N independent air-hockey games stepped on one GPU."""
 
     def __init__(self, n_envs: int, dtype: torch.dtype = torch.float32, device: Union[str, torch.device] = "cuda",
-                 seed: int = 0, env_id0: int = 0, dot_fma: bool = True, friction: bool = False, prefetch: bool = True):
+                 seed: int = 0, env_id0: int = 0, dot_fma: bool = True, friction: bool = False, prefetch: bool = True,
+                 packed_core: bool = True):
         if dtype not in (torch.float32, torch.float64):
             raise ValueError("dtype must be torch.float32 (throughput build) or torch.float64 (validation build)")
         self._lib = _capi.lib()                       # raises ImportError when the CUDA library is missing
@@ -200,7 +201,7 @@ class BatchedAirHockey:
             self.device = torch.device("cuda", torch.cuda.current_device())
         self.n, self.dtype, self.seed, self.env_id0 = int(n_envs), dtype, int(seed), int(env_id0)
         self._h = C.c_void_p()
-        cfg = _capi.AhConfig(int(dot_fma), int(friction), int(not prefetch))
+        cfg = _capi.AhConfig(int(dot_fma), int(friction), int(not prefetch), int(not packed_core))
         _capi.check(self._lib.ah_create(C.byref(self._h), self.n, _capi.AH_F32 if dtype == torch.float32 else _capi.AH_F64,
                                         self.device.index, self.seed, self.env_id0, C.byref(cfg)), "ah_create")
         kw = dict(dtype=dtype, device=self.device)

@@ -162,7 +162,10 @@ typedef struct ah_config {
     int32_t friction;   /* 1: apply Puck.friction_on_puck (puck.py:73-88) before the speed clamp; the      */
                         /*    reference never calls it (dead code), so the default is 0                    */
     int32_t no_prefetch; /* 1: never use the small-K persistent/prefetching variant of the step kernel (tuning / tests) */
-    int32_t reserved[5];
+    int32_t no_packed_core; /* 1: the general API's tensors (int8 [K][n] actions, four per-frame outputs) and the Philox  */
+                            /*    simulation run on round 1's step kernel instead of the packed-core kernel (tests compare */
+                            /*    the two; same results either way)                                                        */
+    int32_t reserved[4];
 } ah_config;
 
 /* ---- optional fused replay/rollout ring (replaces MemoryBuffer.append, lib/buffer.py:24-32, fed with the

@@ -292,3 +292,40 @@ def test_interleaved_steps_inside_a_cuda_graph():
             assert torch.equal(outs_a[k].events, outs_b[k].events) and torch.equal(outs_a[k].obs_next, outs_b[k].obs_next)
     assert same(snapshot(a), snapshot(b)) and a.stats() == b.stats()
     assert a.counters() == b.counters()
+
+
+# ---------------------------------------------------------------- the packed core behind the general API's tensors
+@pytest.mark.parametrize("dtype,K", [(torch.float32, 8), (torch.float32, 5), (torch.float64, 7), (torch.float32, 3)])
+def test_general_api_runs_on_the_packed_core_with_identical_results(dtype, K):
+    """``env.step(int8 [K, N] actions)`` with the default four per-frame outputs (K > 2) runs on the packed-core kernel
+    (IO_UNPACKED front-end: same arithmetic, the event byte decoded into the caller's tensors); ``packed_core=False`` keeps
+    round 1's step kernel.  Bitwise the same outputs, state, statistics and counters, incl. out-of-range action bytes."""
+    n = 3001
+    a, b = make_env(n, dtype, seed=31), make_env(n, dtype, seed=31, packed_core=False)
+    for env in (a, b):
+        env.step(None, K=600, out=env.make_outputs(600, ()))
+    g = torch.Generator(device="cuda").manual_seed(9)
+    for launch in range(5):
+        acts = torch.randint(-2, 7, (K, n), dtype=torch.int8, device="cuda", generator=g)
+        oa, ob = a.step(acts, K=K), b.step(acts, K=K)
+        for f in ("reward", "done", "score", "game_over", "obs_next"):
+            assert torch.equal(getattr(oa, f), getattr(ob, f)), (launch, f)
+    for x, y in zip((a.puck, a.robot, a.opponent, a.prev_dist, a.meta), (b.puck, b.robot, b.opponent, b.prev_dist, b.meta)):
+        assert torch.equal(x, y)
+    assert a.stats() == b.stats() and a.counters() == b.counters()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_philox_simulation_runs_on_the_packed_core_with_identical_results(dtype):
+    """``env.step(None, K)`` without per-frame outputs (pure simulation, in-kernel Philox actions keyed on the device
+    frame counter) on the packed core == round 1's kernel, across launches (the frame counter carries over)."""
+    n = 2500
+    a, b = make_env(n, dtype, seed=44), make_env(n, dtype, seed=44, packed_core=False)
+    for K in (70, 1, 9, 130):                          # crosses the 64-frame Philox action blocks at odd offsets
+        oa = a.step(None, K=K, out=a.make_outputs(K, ("obs_next",)))
+        ob = b.step(None, K=K, out=b.make_outputs(K, ("obs_next",)))
+        assert torch.equal(oa.obs_next, ob.obs_next)
+        assert a.counters() == b.counters()
+    for x, y in zip((a.puck, a.robot, a.opponent, a.prev_dist, a.meta), (b.puck, b.robot, b.opponent, b.prev_dist, b.meta)):
+        assert torch.equal(x, y)
+    assert a.stats() == b.stats()
