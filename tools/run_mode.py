@@ -1,5 +1,5 @@
 """Run ONE mode of the step kernel repeatedly (for ncu captures of the non-headline variants).
-usage: python tools/run_mode.py k1 | fp64 | policy | ring"""
+usage: python tools/run_mode.py k1 | fp64 | policy | ring | unpacked | philox"""
 import sys
 sys.path.insert(0, "/root/repo")
 import torch
@@ -35,5 +35,16 @@ elif mode == "ring":                   # config 4's per-GPU work: K = 8 step + f
     acts = [pack_actions(torch.randint(0, 4, (K, n), dtype=torch.int8, device="cuda")) for _ in range(4)]
     for i in range(60):
         env.step(acts[i % 4], K=K, out=out, ring=ring)
+elif mode in ("unpacked", "philox"):   # the packed core behind the general API's tensors / the Philox simulation
+    n, K = 1 << 20, 8
+    env = BatchedAirHockey(n, seed=1)
+    env.step(None, K=2000, out=env.make_outputs(2000, ()))
+    if mode == "unpacked":
+        out = env.make_outputs(K, ("reward", "done", "score", "game_over", "obs_next"))
+        acts = [torch.randint(0, 4, (K, n), dtype=torch.int8, device="cuda") for _ in range(4)]
+    else:
+        out, acts = env.make_outputs(K, ("obs_next",)), [None] * 4
+    for i in range(60):
+        env.step(acts[i % 4], K=K, out=out)
 torch.cuda.synchronize()
 print("ok", mode)
