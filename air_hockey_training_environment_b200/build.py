@@ -12,7 +12,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "ah_b200.cu")
-DEPS = [SRC, os.path.join(HERE, "csrc", "ah_physics.cuh"), os.path.join(HERE, "csrc", "ah_rng.cuh"),
+DEPS = [SRC, *(os.path.join(HERE, "csrc", h) for h in ("ah_physics.cuh", "ah_rng.cuh", "ah_step_packed.cuh", "ah_policy.cuh")),
         os.path.join(os.path.dirname(HERE), "include", "ah_b200.h")]
 LIB = os.path.join(HERE, "libah_b200.so")
 

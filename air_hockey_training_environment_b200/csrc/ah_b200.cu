@@ -112,6 +112,7 @@ struct ResetSrc {
     const double* table;   // [n][R][2] or nullptr => Philox
     int R;
     uint64_t seed, env_id0;
+    ResetKey key;          // reset-velocity stream of `seed` (ah_rng.cuh)
 };
 
 // AirHockey.reset  airhockey.py:171-187 ; Puck.reset puck.py:111-118 ; Mallet.reset mallet.py:78-84
@@ -129,7 +130,7 @@ __device__ __forceinline__ void env_reset(Env<R>& e, bool total, const ResetSrc&
         // env id, out of the frame loop -- four registers and a dozen instructions per env for a rare path)
         unsigned int iu = (unsigned int)i;
         asm volatile("" : "+r"(iu));
-        reset_velocity(rs.seed, rs.env_id0 + (uint64_t)iu, e.resets, dx, dy);
+        reset_velocity(rs.key, rs.env_id0 + (uint64_t)iu, e.resets, dx, dy);
     }
     e.resets += 1;
     e.px = K<R>::mid_x; e.py = K<R>::mid_y; e.pdx = dx; e.pdy = dy;   // puck to the centre, fresh velocity
@@ -878,7 +879,8 @@ template <typename R> ah::StatePtrs<R> state_ptrs(const ah_env* env) {
 }
 
 inline ah::ResetSrc reset_src(const ah_env* env, const double* table, int R) {
-    ah::ResetSrc rs; rs.table = table; rs.R = R; rs.seed = env->seed; rs.env_id0 = env->env_id0; return rs;
+    ah::ResetSrc rs; rs.table = table; rs.R = R; rs.seed = env->seed; rs.env_id0 = env->env_id0;
+    rs.key = ah::reset_key(env->seed); return rs;
 }
 
 inline unsigned small_grid(int64_t n) { return (unsigned)((n + 255) / 256); }

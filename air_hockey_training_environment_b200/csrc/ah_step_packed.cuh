@@ -263,7 +263,6 @@ step_packed_kernel(const PackedArgs<R> a) {
     const uint32_t stride = gridDim.x * blockDim.x;
     const bool dot_fma = a.dot_fma != 0;
     const int nK = a.K;
-    const int quads = (nK + 3) >> 2;
     int r3sum = 0, r3sq = 0, dones = 0, contacts = 0, frames = 0, bad = 0, amb = 0;
     unsigned overflow = 0;
     // RING: every block reads the ring's counter at its start, so it may only advance once every block is done
@@ -292,7 +291,7 @@ step_packed_kernel(const PackedArgs<R> a) {
 #else
         bool next_valid = false;
 #endif
-        if (next_valid) reset_velocity(a.rs.seed, a.rs.env_id0 + (uint64_t)i, e.resets, next_dx, next_dy);
+        if (next_valid) reset_velocity(a.rs.key, a.rs.env_id0 + (uint64_t)i, e.resets, next_dx, next_dy);
         int gf_base = e.game_frames;        // frames-in-game = gf_base + frames done in this launch
         // The current game's return is kept as "sum of r3 since r3_mark": reward = 2 r3 - 4, so
         // return = 2 (r3sum - r3_mark) - 4 frames_in_game.  One accumulator (r3sum) serves the launch statistics too.

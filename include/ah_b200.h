@@ -189,7 +189,9 @@ typedef struct ah_step_io {
     const void* actions;          /* device; see AH_ACT_* (NULL for AH_ACT_PHILOX) */
     int32_t action_kind;
     int32_t reset_table_len;      /* R */
-    const double* reset_table;    /* device double [n][R][2] (dx, dy) per reset, or NULL => in-kernel Philox.    */
+    const double* reset_table;    /* device double [n][R][2] (dx, dy) per reset, or NULL => drawn in the kernel  */
+                                  /* by a counter-based generator keyed (seed, global env id, reset index):      */
+                                  /* Philox4x32-10 in the AH_F64 build, pcg3d in the AH_F32 build.               */
                                   /* Stands in for the global np.random.uniform draws of puck.py:115-116.       */
     /* per-frame outputs, each nullable; [K][n]... */
     void* obs_state;              /* real [K][n][8]  Observation.state     (agent.py:61)  */

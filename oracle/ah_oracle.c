@@ -101,6 +101,26 @@ static void rng_reset_pair(uint64_t seed, uint64_t env_id, uint32_t reset_idx, d
     *dy = -10.0 + 20.0 * u1;   /* (puck.py:116) */
 }
 
+/* The FP32 THROUGHPUT build's reset draw (not reference either): pcg3d (Jarzynski & Olano, JCGT 9(3), 2020) on
+ * (env_id lo ^ mix lo, reset index ^ env_id hi, mix hi) with mix = splitmix64(seed); 24-bit uniforms, one binary32 fma each
+ * (csrc/ah_rng.cuh).  The result is a binary32 value, returned exactly in a double. */
+static uint64_t splitmix64(uint64_t seed) {
+    uint64_t z = seed + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+static void rng_reset_pair_f32(uint64_t seed, uint64_t env_id, uint32_t reset_idx, double* dx, double* dy) {
+    const uint64_t mix = splitmix64(seed);
+    uint32_t x = (uint32_t)env_id ^ (uint32_t)mix, y = reset_idx ^ (uint32_t)(env_id >> 32), z = (uint32_t)(mix >> 32);
+    x = x * 1664525u + 1013904223u; y = y * 1664525u + 1013904223u; z = z * 1664525u + 1013904223u;
+    x += y * z; y += z * x; z += x * y;
+    x ^= x >> 16; y ^= y >> 16; z ^= z >> 16;
+    x += y * z; y += z * x;
+    *dx = (double)fmaf((float)(x >> 8), 20.0f / 16777216.0f, -10.0f);
+    *dy = (double)fmaf((float)(y >> 8), 20.0f / 16777216.0f, -10.0f);
+}
+
 static int rng_action(uint64_t seed, uint64_t env_id, uint64_t frame) {
     uint32_t ctr[4] = {(uint32_t)env_id, (uint32_t)(env_id >> 32), (uint32_t)(frame >> 6), 1u};
     uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
@@ -112,6 +132,9 @@ static int rng_action(uint64_t seed, uint64_t env_id, uint64_t frame) {
 
 void orc_rng_reset_pair(uint64_t seed, uint64_t env_id, uint32_t reset_idx, double* out2) {
     rng_reset_pair(seed, env_id, reset_idx, &out2[0], &out2[1]);
+}
+void orc_rng_reset_pair_f32(uint64_t seed, uint64_t env_id, uint32_t reset_idx, double* out2) {
+    rng_reset_pair_f32(seed, env_id, reset_idx, &out2[0], &out2[1]);
 }
 int orc_rng_action(uint64_t seed, uint64_t env_id, uint64_t frame) { return rng_action(seed, env_id, frame); }
 
@@ -309,8 +332,8 @@ static void rewards_call(env_t* e, int dot_fma, int* reward, int* score, int* do
 
 /* ------------------------------------------------------------------ airhockey.py:171-187, puck.py:111-118, mallet.py:78-84 */
 typedef struct {
-    const double* table;  /* [R][2] for this env, or NULL => Philox */
-    int R;
+    const double* table;  /* [R][2] for this env, or NULL => Philox (rng 0) / the FP32 build's pcg3d (rng 1) */
+    int R, rng;
     int32_t cursor;       /* resets consumed */
     uint64_t seed, env_id;
     int overflow;
@@ -323,7 +346,8 @@ static void env_reset(env_t* e, int total, reset_src_t* rs) {
         if (rs->cursor < rs->R) { dx = rs->table[2 * rs->cursor]; dy = rs->table[2 * rs->cursor + 1]; }
         else { dx = 0.0; dy = 0.0; rs->overflow = 1; }
     } else {
-        rng_reset_pair(rs->seed, rs->env_id, (uint32_t)rs->cursor, &dx, &dy);
+        if (rs->rng == 1) rng_reset_pair_f32(rs->seed, rs->env_id, (uint32_t)rs->cursor, &dx, &dy);
+        else rng_reset_pair(rs->seed, rs->env_id, (uint32_t)rs->cursor, &dx, &dy);
     }
     rs->cursor += 1;
     e->puck.x = MID_X; e->puck.y = MID_Y; e->puck.dx = dx; e->puck.dy = dy;
@@ -407,12 +431,14 @@ typedef struct {
  * reset_cursor [n] in/out
  * returns 0, or 1 if a reset table overflowed.
  */
-int orc_frames(int64_t n, int T, double* state13, int32_t* scores2,
-               const int8_t* actions_i8, const double* actions_f64,
-               const double* reset_table, int R, int32_t* reset_cursor,
-               uint64_t seed, uint64_t env_id0, uint64_t frame0,
-               int dot_fma, int friction, int record_every, int nthreads,
-               const orc_outputs_t* out) {
+/* reset_rng: which in-kernel generator the table-less resets restate: 0 Philox4x32-10 (the FP64 build), 1 the FP32
+ * build's pcg3d */
+int orc_frames_ex(int64_t n, int T, double* state13, int32_t* scores2,
+                  const int8_t* actions_i8, const double* actions_f64,
+                  const double* reset_table, int R, int32_t* reset_cursor,
+                  uint64_t seed, uint64_t env_id0, uint64_t frame0,
+                  int dot_fma, int friction, int record_every, int nthreads, int reset_rng,
+                  const orc_outputs_t* out) {
     int overflow = 0;
     int64_t stats_acc[20];
     memset(stats_acc, 0, sizeof stats_acc);
@@ -425,7 +451,7 @@ int orc_frames(int64_t n, int T, double* state13, int32_t* scores2,
         load_env(&e, state13 + 13 * i, scores2 + 2 * i);
         reset_src_t rs;
         rs.table = reset_table ? reset_table + (size_t)i * R * 2 : NULL;
-        rs.R = R; rs.cursor = reset_cursor[i]; rs.seed = seed; rs.env_id = env_id0 + (uint64_t)i; rs.overflow = 0;
+        rs.R = R; rs.rng = reset_rng; rs.cursor = reset_cursor[i]; rs.seed = seed; rs.env_id = env_id0 + (uint64_t)i; rs.overflow = 0;
         for (int t = 0; t < T; ++t) {
             size_t o = (size_t)t * n + i;
             int kind = 0, ia = -1; double ax = 0, ay = 0;
@@ -477,6 +503,16 @@ int orc_frames(int64_t n, int T, double* state13, int32_t* scores2,
     }
     if (out->stats) for (int k = 0; k < 20; ++k) out->stats[k] += stats_acc[k];
     return overflow;
+}
+
+int orc_frames(int64_t n, int T, double* state13, int32_t* scores2,
+               const int8_t* actions_i8, const double* actions_f64,
+               const double* reset_table, int R, int32_t* reset_cursor,
+               uint64_t seed, uint64_t env_id0, uint64_t frame0,
+               int dot_fma, int friction, int record_every, int nthreads,
+               const orc_outputs_t* out) {
+    return orc_frames_ex(n, T, state13, scores2, actions_i8, actions_f64, reset_table, R, reset_cursor, seed, env_id0, frame0,
+                         dot_fma, friction, record_every, nthreads, 0, out);
 }
 
 /* predicates pinned by the reference's unit tests (tests/test_puck.py, tests/test_goal.py, tests/test_mallet.py) */

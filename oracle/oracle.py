@@ -42,6 +42,11 @@ def lib() -> C.CDLL:
         _lib.orc_frames.argtypes = [C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64,
                                     C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_Outputs)]
+        _lib.orc_frames_ex.restype = C.c_int
+        _lib.orc_frames_ex.argtypes = [C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64,
+                                       C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_Outputs)]
+        _lib.orc_rng_reset_pair_f32.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p]
         _lib.orc_init.argtypes = [C.c_int64, C.c_void_p, C.c_void_p]
         _lib.orc_update_state.restype = C.c_int
         _lib.orc_update_state.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
@@ -82,13 +87,14 @@ def run_frames(state: np.ndarray, scores: np.ndarray, T: int, *,
                reset_cursor: Optional[np.ndarray] = None,
                seed: int = 0, env_id0: int = 0, frame0: int = 0,
                dot_fma: int = DOT_FMA_DEFAULT, friction: bool = False,
-               record_every: int = 0, nthreads: int = 1,
+               record_every: int = 0, nthreads: int = 1, reset_rng: str = "philox",
                want=("obs_state", "obs_new_state", "obs_next", "reward", "score", "done", "game_over"),
                ) -> Dict[str, np.ndarray]:
     """Advance ``state``/``scores`` IN PLACE by T frames; returns the per-frame outputs asked for.
 
     actions: int8 [T,n] (discrete), float64 [T,n,2] (continuous) or None (Philox actions).
-    reset_table: float64 [n,R,2] or None (Philox resets keyed (seed, env_id0 + i)).
+    reset_table: float64 [n,R,2] or None (in-kernel resets keyed (seed, env_id0 + i): ``reset_rng`` "philox" restates the
+    FP64 build's Philox4x32-10 draw, "f32" the FP32 throughput build's pcg3d draw -- csrc/ah_rng.cuh).
     """
     n = state.shape[0]
     assert state.dtype == np.float64 and state.flags.c_contiguous and state.shape == (n, 13)
@@ -121,9 +127,9 @@ def run_frames(state: np.ndarray, scores: np.ndarray, T: int, *,
         out["scores_rec"] = np.zeros((T // record_every, n, 2), np.int32)
     out["stats"] = np.zeros(20, np.int64)
     o = _Outputs(**{k: _p(out.get(k)) for k, _ in _Outputs._fields_})
-    rc = lib().orc_frames(n, T, _p(state), _p(scores), _p(a_i8), _p(a_f64), _p(reset_table), R,
-                          _p(reset_cursor), seed, env_id0, frame0, int(dot_fma), int(friction),
-                          int(record_every), int(nthreads), C.byref(o))
+    rc = lib().orc_frames_ex(n, T, _p(state), _p(scores), _p(a_i8), _p(a_f64), _p(reset_table), R,
+                             _p(reset_cursor), seed, env_id0, frame0, int(dot_fma), int(friction),
+                             int(record_every), int(nthreads), {"philox": 0, "f32": 1}[reset_rng], C.byref(o))
     out["reset_cursor"] = reset_cursor
     out["reset_overflow"] = bool(rc)
     return out
@@ -158,6 +164,13 @@ def philox4x32_10(ctr, key) -> np.ndarray:
 def rng_reset_pair(seed: int, env_id: int, reset_idx: int) -> np.ndarray:
     o = np.zeros(2, np.float64)
     lib().orc_rng_reset_pair(seed, env_id, reset_idx, _p(o))
+    return o
+
+
+def rng_reset_pair_f32(seed: int, env_id: int, reset_idx: int) -> np.ndarray:
+    """The FP32 build's reset draw (pcg3d; binary32 values, exact in the returned float64)."""
+    o = np.zeros(2, np.float64)
+    lib().orc_rng_reset_pair_f32(seed, env_id, reset_idx, _p(o))
     return o
 
 

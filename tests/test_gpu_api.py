@@ -104,6 +104,41 @@ def test_update_score_and_reset():
     assert env.puck[0, 2:4].tolist() == want.tolist()
 
 
+def test_fp32_reset_draws_equal_the_oracle_restatement():
+    """The FP32 throughput build draws reset velocities from pcg3d keyed (splitmix64(seed), GLOBAL env id, reset index)
+    (csrc/ah_rng.cuh); the oracle restates it (tests/test_reference_pins.py pins and tests that restatement on the CPU).
+    Through the verbs (update_score, reset) and through the packed kernel's goal branch, also with env ids >= 2^32."""
+    from oracle import oracle
+    for seed, id0 in ((5, 0), (2 ** 63 + 11, 2 ** 40 + 5)):
+        n = 64
+        env = make_env(n, torch.float32, seed=seed, env_id0=id0)
+        env.update_score(torch.ones(n, dtype=torch.int8, device=env.device))
+        env.reset(total=False)
+        env.reset(total=True)
+        want = np.stack([oracle.rng_reset_pair_f32(seed, id0 + i, 2) for i in range(n)]).astype(np.float32)
+        assert np.array_equal(env.puck[:, 2:4].cpu().numpy().view(np.uint32), want.view(np.uint32))
+        assert env.reset_count.tolist() == [3] * n
+    # in the frame loop: put the puck in the robot's goal mouth so that every env scores in its first frame
+    from air_hockey_training_environment_b200.env import pack_actions
+    n, seed, id0 = 4096, 77, 123456
+    env = make_env(n, torch.float32, seed=seed, env_id0=id0)
+    env.puck[:, 0] = 20.0; env.puck[:, 2:4] = 0.0
+    acts = torch.full((1, n), 4, dtype=torch.int8, device=env.device)                  # no nudge
+    for packed in (True, False):
+        e = make_env(n, torch.float32, seed=seed, env_id0=id0, packed_core=packed)
+        e.puck.copy_(env.puck)
+        if packed:
+            e.step(pack_actions(acts), K=1, out=e.make_outputs(1, ("events", "obs_next")))
+        else:
+            e.step(acts, K=1, out=e.make_outputs(1, ("reward", "score")))
+        assert e.reset_count.tolist() == [1] * n and e.scores[:, 1].tolist() == [1] * n
+        want = np.stack([oracle.rng_reset_pair_f32(seed, id0 + i, 0) for i in range(n)]).astype(np.float32)
+        # the computer's sub-update follows the reset in the same frame: undo nothing, compare what it cannot change
+        # (computerAI only adds its +2 nudge when the puck is within 40 px of the opponent mallet: not at the centre spot)
+        got = e.puck[:, 2:4].cpu().numpy()
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), packed
+
+
 def test_bad_shapes_are_rejected():
     env = make_env(16)
     with pytest.raises(ValueError):

@@ -66,3 +66,64 @@ def test_philox_known_answers():
         [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
     assert oracle.philox4x32_10([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]).tolist() \
         == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+# ---- the FP32 throughput build's reset generator (pcg3d keyed by splitmix64(seed); csrc/ah_rng.cuh, oracle/ah_oracle.c)
+def _pcg3d_reset_pairs(seed, env_id, reset_idx):
+    """Independent numpy restatement (uint32 wrap-around arithmetic), vectorised over env_id / reset_idx."""
+    M = (1 << 64) - 1
+    z = (seed + 0x9E3779B97F4A7C15) & M
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & M
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M
+    z ^= z >> 31
+    env_id = np.asarray(env_id, np.uint64)
+    x = (env_id & np.uint64(0xFFFFFFFF)).astype(np.uint32) ^ np.uint32(z & 0xFFFFFFFF)
+    y = np.asarray(reset_idx, np.uint32) ^ (env_id >> np.uint64(32)).astype(np.uint32)
+    x, y = np.broadcast_arrays(x, y)
+    zz = np.full(x.shape, z >> 32, np.uint32)
+    with np.errstate(over="ignore"):
+        a, c = np.uint32(1664525), np.uint32(1013904223)
+        x = x * a + c; y = y * a + c; zz = zz * a + c
+        x = x + y * zz; y = y + zz * x; zz = zz + x * y
+        x = x ^ (x >> np.uint32(16)); y = y ^ (y >> np.uint32(16)); zz = zz ^ (zz >> np.uint32(16))
+        x = x + y * zz; y = y + zz * x
+    # 24-bit integer * 20 / 2^24 - 10: the product needs 29 bits, so a float64 evaluation rounded once to binary32 is the fma
+    dx = ((x >> np.uint32(8)).astype(np.float64) * (20.0 / 16777216.0) - 10.0).astype(np.float32)
+    dy = ((y >> np.uint32(8)).astype(np.float64) * (20.0 / 16777216.0) - 10.0).astype(np.float32)
+    return dx, dy
+
+
+def test_fp32_reset_generator_matches_its_restatement():
+    for seed, env, idx in [(0, 0, 0), (5, 0, 1), (1234, 1048575, 7), (2 ** 64 - 1, 2 ** 40 + 3, 2 ** 32 - 1), (99, 8388607, 1000)]:
+        dx, dy = _pcg3d_reset_pairs(seed, env, idx)
+        got = oracle.rng_reset_pair_f32(seed, env, idx)
+        assert got.tolist() == [float(dx), float(dy)], (seed, env, idx)
+    # known answers (binary32 patterns), pinned when the generator was introduced
+    kat = {(5, 0, 1): [0xbf302cdc, 0x40a1dae7], (1234, 1048575, 7): [0x3e5a79b0, 0xc10789bc],
+           (2 ** 64 - 1, 2 ** 40 + 3, 2 ** 32 - 1): [0xc1053a5d, 0xbfa95ef2]}
+    for args, want in kat.items():
+        assert oracle.rng_reset_pair_f32(*args).astype(np.float32).view(np.uint32).tolist() == want, args
+
+
+def test_fp32_reset_generator_statistics():
+    """U(-10, 10) per component; no structure along the env axis, the reset axis, between components or between seeds."""
+    env = np.arange(1 << 18, dtype=np.uint64)
+    dx, dy = _pcg3d_reset_pairs(1234, env[:, None], np.arange(8, dtype=np.uint32)[None, :])      # [2^18, 8]
+    for v in (dx, dy):
+        assert v.min() >= -10.0 and v.max() < 10.0
+        assert abs(v.mean()) < 0.02 and abs(v.var() - 100.0 / 3.0) < 0.1
+        h = np.bincount(((v.astype(np.float64) + 10.0) * (256 / 20.0)).astype(np.int64).ravel(), minlength=256)
+        chi2 = ((h - v.size / 256) ** 2 / (v.size / 256)).sum()
+        assert chi2 < 255 + 6 * np.sqrt(2 * 255), chi2                                       # 255 dof, 6 sigma
+
+    def corr(a, b):
+        a = a.astype(np.float64).ravel(); b = b.astype(np.float64).ravel()
+        return abs(np.corrcoef(a, b)[0, 1])
+    lim = 6.0 / np.sqrt(dx.size)
+    assert corr(dx, dy) < lim                                   # the two components of a draw
+    assert corr(dx[:-1], dx[1:]) < lim and corr(dy[:-1], dy[1:]) < lim            # neighbouring envs
+    assert corr(dx[:, :-1], dx[:, 1:]) < lim and corr(dy[:, :-1], dy[:, 1:]) < lim    # consecutive resets of an env
+    ex, ey = _pcg3d_reset_pairs(1235, env[:, None], np.arange(8, dtype=np.uint32)[None, :])   # the next seed
+    assert corr(dx, ex) < lim and corr(dy, ey) < lim
+    both = np.stack([dx.ravel(), dy.ravel()], 1).view(np.uint64).ravel()
+    assert np.unique(both).size > both.size - 8                # 48-bit draws: (almost) no repeated pair in 2^21
