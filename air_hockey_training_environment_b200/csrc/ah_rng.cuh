@@ -36,14 +36,15 @@ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint3
 }
 
 // U(-10, 10) pair for one reset, in the arithmetic of np.random.uniform: low + (high - low) * u  (puck.py:115-116)
-// The key of an env set's reset stream: the seed itself (Philox, FP64 build) and splitmix64(seed) (pcg3d, FP32 build).
-struct ResetKey { uint64_t seed; uint32_t mix_lo, mix_hi; };
+// The key of an env set's reset stream: the seed itself for Philox (FP64 build), splitmix64(seed) for pcg3d (FP32 build:
+// distinct seeds give unrelated streams, not shifted copies).  Computed once per launch on the host.
+struct ResetKey { uint64_t seed, mix; };
 inline ResetKey reset_key(uint64_t seed) {
     uint64_t z = seed + 0x9E3779B97F4A7C15ull;               // splitmix64 (Steele, Lea, Flood 2014), one step
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
     z ^= z >> 31;
-    return ResetKey{seed, (uint32_t)z, (uint32_t)(z >> 32)};
+    return ResetKey{seed, z};
 }
 
 __device__ __forceinline__ void reset_velocity(const ResetKey& key, uint64_t env_id, uint32_t reset_idx, double& dx, double& dy) {
@@ -57,10 +58,10 @@ __device__ __forceinline__ void reset_velocity(const ResetKey& key, uint64_t env
     dy = __dadd_rn(-10.0, __dmul_rn(20.0, u1));
 }
 
-// FP32 build: pcg3d on (env id lo ^ mix lo, reset index ^ env id hi, mix hi), mix = splitmix64(seed) (reset_key, host side:
-// distinct seeds give unrelated streams, not shifted copies).  24-bit uniforms, one fma each.
+// FP32 build: pcg3d on (env id lo ^ mix lo, reset index ^ env id hi, mix hi), mix = splitmix64(seed).  24-bit uniforms,
+// one fma each.
 __device__ __forceinline__ void reset_velocity(const ResetKey& key, uint64_t env_id, uint32_t reset_idx, float& dx, float& dy) {
-    uint32_t x = (uint32_t)env_id ^ key.mix_lo, y = reset_idx ^ (uint32_t)(env_id >> 32), z = key.mix_hi;
+    uint32_t x = (uint32_t)env_id ^ (uint32_t)key.mix, y = reset_idx ^ (uint32_t)(env_id >> 32), z = (uint32_t)(key.mix >> 32);
     x = x * 1664525u + 1013904223u; y = y * 1664525u + 1013904223u; z = z * 1664525u + 1013904223u;
     x += y * z; y += z * x; z += x * y;
     x ^= x >> 16; y ^= y >> 16; z ^= z >> 16;
