@@ -127,3 +127,18 @@ def test_fp32_reset_generator_statistics():
     assert corr(dx, ex) < lim and corr(dy, ey) < lim
     both = np.stack([dx.ravel(), dy.ravel()], 1).view(np.uint64).ravel()
     assert np.unique(both).size > both.size - 8                # 48-bit draws: (almost) no repeated pair in 2^21
+
+
+def test_oracle_frame_loop_uses_the_selected_reset_generator():
+    """run_frames(reset_rng=...) draws table-less resets from the generator it names: put the puck in the robot's goal
+    mouth, play one frame with no nudge, the puck's velocity is the first draw of that env's stream."""
+    for rng_name, pair in (("philox", oracle.rng_reset_pair), ("f32", oracle.rng_reset_pair_f32)):
+        st, sc = oracle.initial_state(3)
+        st[:, 0] = 20.0; st[:, 2:4] = 0.0
+        cur = np.array([0, 4, 9], np.int32)
+        out = oracle.run_frames(st, sc, 1, actions=np.full((1, 3), 4, np.int8), seed=321, env_id0=1000, reset_cursor=cur,
+                                reset_rng=rng_name, want=("score",))
+        assert out["score"].tolist() == [[-1, -1, -1]] and sc[:, 1].tolist() == [1, 1, 1]
+        assert out["reset_cursor"].tolist() == [1, 5, 10]
+        for i, c in enumerate((0, 4, 9)):
+            assert st[i, 2:4].tolist() == pair(321, 1000 + i, c).tolist(), (rng_name, i)
