@@ -309,7 +309,9 @@ enum { MODE_LEAN = 0, MODE_SIM = 1, MODE_GENERIC = 2 };
 // (4 x LDG.128 + LDG.32 + the action byte) before computing the current one, so every resident thread always has
 // 69 bytes in flight.  Costs 18 registers (64 -> ~84, 3 blocks/SM), which K = 1 can afford.
 template <typename R, int ACT, int MODE, bool PF = false>   // ACT: 1 discrete, 2 continuous, 3 philox, 4 in-kernel actor
-__global__ void __launch_bounds__(kThreads, ACT == 4 ? 2 : ((PF || MODE == MODE_GENERIC) ? (Occ<R>::blocks < 3 ? Occ<R>::blocks : 3) : Occ<R>::blocks))
+// (ACT 5 is launched with blocks of kPolThreads, 4 of which fit an SM's shared memory: up to 128 registers, no spills)
+__global__ void __launch_bounds__(ACT == 5 ? kPolThreads : kThreads,
+                                  ACT == 5 ? (sizeof(R) == 4 ? 4 : 2) : ACT == 4 ? 2 : ((PF || MODE == MODE_GENERIC) ? (Occ<R>::blocks < 3 ? Occ<R>::blocks : 3) : Occ<R>::blocks))
 step_kernel(const StepArgs<R> a) {
     using V2 = typename std::conditional<sizeof(R) == 4, float2, double2>::type;
     __shared__ BlockStats bs;
@@ -375,6 +377,7 @@ step_kernel(const StepArgs<R> a) {
         Philox4 ablock = {};
         uint32_t ablock_id = 0xffffffffu;
         unsigned long long sblock_id = ~0ull;                  // AH_ACT_POLICY: cached block of 4 sampling uniforms
+        PolicyRng prng;                                        // AH_ACT_POLICY_MLP: the same, for both uniform streams
         int64_t ring_slot = ring_slot0;                        // slot of frame k: (appended so far + k) mod capacity
         // warp-uniform per-frame base pointers (advanced by n per frame); the thread adds its 32-bit env index
         const int8_t* act_i8 = reinterpret_cast<const int8_t*>(a.actions);
@@ -422,7 +425,7 @@ step_kernel(const StepArgs<R> a) {
                 float y[8], v[8];
                 policy_forward(a.pol, s_pol, s_hs, x, y);
                 policy_head(a.pol, y, v);
-                const PolicyAction pa = policy_select(a.pol, v, a.rs.seed, a.rs.env_id0 + (uint64_t)i, frame0 + (unsigned long long)k, (int64_t)i);
+                const PolicyAction pa = policy_select(a.pol, v, a.rs.seed, a.rs.env_id0 + (uint64_t)i, frame0 + (unsigned long long)k, (int64_t)i, prng);
                 if (cont_act) {
                     ax = (R)pa.ax; ay = (R)pa.ay;
                     if (a.actions_real_out) reinterpret_cast<V2*>(a.actions_real_out)[(int64_t)k * n + i] = V2{ax, ay};
@@ -434,8 +437,13 @@ step_kernel(const StepArgs<R> a) {
                 if (a.probs_out) {
                     const int nv = cont_act ? 2 : a.pol.n_actions;
                     R* dst = a.probs_out + ((int64_t)k * n + i) * nv;
+                    if (sizeof(R) == 4 && nv == 4 && (reinterpret_cast<uintptr_t>(a.probs_out) & 15u) == 0) {       // one 128-bit store per env-frame
+                        typename Vec4T<R>::type q4; q4.x = (R)v[0]; q4.y = (R)v[1]; q4.z = (R)v[2]; q4.w = (R)v[3];
+                        *reinterpret_cast<typename Vec4T<R>::type*>(dst) = q4;
+                    } else {
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) if (q < nv) dst[q] = (R)v[q];
+                        for (int q = 0; q < 8; ++q) if (q < nv) dst[q] = (R)v[q];
+                    }
                 }
             } else {
                 const unsigned long long f = frame0 + (unsigned long long)k;
@@ -914,6 +922,9 @@ int make_policy_dev(const ah_policy* p, ah::PolicyDev* d, bool need_weights) {
         }
         d->n_floats = off;
         d->weights = p->weights;
+        d->narrow = 1;
+        for (int l = 0; l <= p->n_layers; ++l) if (p->width[l] > 8) d->narrow = 0;
+        if (getenv("AH_POLICY_NO_NARROW")) d->narrow = 0;      // tuning / test aid: force the general path
     }
     // epsilon schedule: the number of decrements after which epsilon <= final_epsilon (strategies.py:39-43)
     d->eps0 = p->epsilon; d->eps_final = p->final_epsilon; d->observe = p->observe;

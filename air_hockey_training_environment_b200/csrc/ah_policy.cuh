@@ -32,6 +32,7 @@ constexpr int kPolMaxFloats = (8 * kPolMaxW + kPolMaxW) + 3 * (kPolMaxW * kPolMa
 
 struct PolicyDev {                                      // by value in the kernel arguments
     int n_layers, width[5], act[4], w_off[4], b_off[4], n_floats;
+    int narrow;                                         // every width <= 8: the register-resident evaluation
     int head, select, n_actions;
     float eps0, eps_delta, eps_final; int observe, max_decrements;
     float inv_tau, clip_lo, clip_hi;
@@ -50,9 +51,53 @@ __device__ __forceinline__ float policy_activate(float v, int act) {
     return v;
 }
 
+// NARROW networks (every width <= 8: the reference's PPO actors 8-4-6-4-4 / 8-6-6-4-2, the A2C actor and the DDQN net
+// 8-8-4): activations stay in REGISTERS and every loop is unrolled to its compile-time bound with warp-uniform guards, so
+// the weight broadcasts (LDS.128) of a layer are issued ahead of the multiply-adds instead of one dependent
+// load -> FFMA per iteration.  A one-launch rollout of 65,536 envs has 3.5 warps per scheduler: it is bound by the
+// LATENCY of this chain, not by issue slots.  Same multiply-add order per output as the general path: same bits.
+__device__ __forceinline__ void policy_forward_narrow(const PolicyDev& P, const float* __restrict__ sw, const float (&x)[8], float (&y)[8]) {
+    float h[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) h[c] = x[c];
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+        if (l < P.n_layers) {
+            const int win = P.width[l], outp = (P.width[l + 1] + 3) & ~3, act = P.act[l];
+            const float* W = sw + P.w_off[l];
+            const float* B = sw + P.b_off[l];
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; j += 4) {
+                float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                if (j < outp) {
+                    acc = *reinterpret_cast<const float4*>(B + j);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        if (c < win) {
+                            const float4 w = *reinterpret_cast<const float4*>(W + c * outp + j);
+                            acc.x = fmaf(w.x, h[c], acc.x); acc.y = fmaf(w.y, h[c], acc.y);
+                            acc.z = fmaf(w.z, h[c], acc.z); acc.w = fmaf(w.w, h[c], acc.w);
+                        }
+                    }
+                    acc.x = policy_activate(acc.x, act); acc.y = policy_activate(acc.y, act);
+                    acc.z = policy_activate(acc.z, act); acc.w = policy_activate(acc.w, act);
+                }
+                o[j] = acc.x; o[j + 1] = acc.y; o[j + 2] = acc.z; o[j + 3] = acc.w;
+            }
+#pragma unroll
+            for (int c = 0; c < 8; ++c) h[c] = o[c];
+        }
+    }
+    const int wl = P.width[P.n_layers];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) y[q] = q < wl ? h[q] : 0.0f;
+}
+
 // x[8] -> y[8] (the first width[n_layers] outputs of the last layer, zero-filled)
 __device__ __forceinline__ void policy_forward(const PolicyDev& P, const float* __restrict__ sw, float* hs, const float (&x)[8],
                                                float (&y)[8]) {
+    if (P.narrow) { policy_forward_narrow(P, sw, x, y); return; }
     const int T = kPolThreads, tid = threadIdx.x;
     float* in = hs;
     float* out = hs + kPolMaxW * T;
@@ -137,15 +182,30 @@ __device__ __forceinline__ float policy_epsilon(const PolicyDev& P, unsigned lon
 
 struct PolicyAction { int ia; float ax, ay; };
 
+// The two uniform streams of an env, one 128-bit Philox block per 4 frames each: a caller that plays consecutive frames
+// (the step kernel's closed loop) keeps the blocks across frames -- one draw per 4 frames instead of one per frame.
+struct PolicyRng {
+    Philox4 b0, b1;
+    unsigned long long id0 = ~0ull, id1 = ~0ull;        // frame >> 2 of the cached block
+};
+__device__ __forceinline__ float policy_u0(PolicyRng& g, uint64_t seed, uint64_t env_id, unsigned long long f) {
+    if ((f >> 2) != g.id0) { g.b0 = sample_block(seed, env_id, f); g.id0 = f >> 2; }
+    return sample_uniform(g.b0, f);
+}
+__device__ __forceinline__ float policy_u1(PolicyRng& g, uint64_t seed, uint64_t env_id, unsigned long long f) {
+    if ((f >> 2) != g.id1) { g.b1 = sample_block2(seed, env_id, f); g.id1 = f >> 2; }
+    return sample_uniform(g.b1, f);
+}
+
 // One action for one env.  `f` = the global frame index (frames played before this one); v = policy_head's output.
 __device__ __forceinline__ PolicyAction policy_select(const PolicyDev& P, const float (&v)[8], uint64_t seed, uint64_t env_id,
-                                                      unsigned long long f, int64_t i) {
+                                                      unsigned long long f, int64_t i, PolicyRng& g) {
     PolicyAction r; r.ia = -1; r.ax = 0.0f; r.ay = 0.0f;
     const int A = P.n_actions, sel = P.select;
     float u0 = 0.0f, u1 = 0.0f;
     if (sel != AH_SELECT_GREEDY) {
-        u0 = sample_uniform(sample_block(seed, env_id, f), f);
-        if (sel != AH_SELECT_SAMPLE && sel != AH_SELECT_BOLTZMANN) u1 = sample_uniform(sample_block2(seed, env_id, f), f);
+        u0 = policy_u0(g, seed, env_id, f);
+        if (sel != AH_SELECT_SAMPLE && sel != AH_SELECT_BOLTZMANN) u1 = policy_u1(g, seed, env_id, f);
     }
     if (P.head == AH_HEAD_CONTINUOUS) {
         r.ax = v[0]; r.ay = v[1];
@@ -212,7 +272,8 @@ __global__ void __launch_bounds__(kPolThreads) policy_act_kernel(int64_t n, Poli
         policy_forward(P, sw, hs, x, y);
         policy_head(P, y, v);
     }
-    const PolicyAction a = policy_select(P, v, seed, env_id0 + (uint64_t)i, blk->frame, i);
+    PolicyRng g;
+    const PolicyAction a = policy_select(P, v, seed, env_id0 + (uint64_t)i, blk->frame, i, g);
     if (P.head == AH_HEAD_CONTINUOUS) {
         if (actions_real) { actions_real[2 * i] = (R)a.ax; actions_real[2 * i + 1] = (R)a.ay; }
     } else if (actions) {
