@@ -319,8 +319,9 @@ step_kernel(const StepArgs<R> a) {
     // instead of four compares and four selects per frame.  Entry 4 = "any other int": no nudge.
     __shared__ V2 s_nudge[8];
     __shared__ __align__(16) float s_actor[ACT == 4 ? 128 : 4];     // AH_ACT_POLICY: the actor's 114 weights
-    __shared__ __align__(16) float s_pol[ACT == 5 ? kPolMaxFloats : 4];              // AH_ACT_POLICY_MLP: weights
-    __shared__ float s_hs[ACT == 5 ? 2 * kPolMaxW * kPolThreads : 4];                //                    activations
+    extern __shared__ __align__(16) float pol_smem[];                                // AH_ACT_POLICY_MLP (ah_policy.cuh):
+    float* s_pol = pol_smem;                                                         //   weights
+    float* s_hs = pol_smem + (ACT == 5 ? policy_weight_floats(a.pol.n_floats) : 0);  //   activations (general path)
     if (ACT == 4)
         for (int t = threadIdx.x; t < AH_ACTOR_NWEIGHTS; t += blockDim.x) s_actor[t] = reinterpret_cast<const float*>(a.actions)[t];
     if (ACT == 5) policy_stage(a.pol, s_pol);
@@ -893,6 +894,10 @@ inline ah::ResetSrc reset_src(const ah_env* env, const double* table, int R) {
 
 inline unsigned small_grid(int64_t n) { return (unsigned)((n + 255) / 256); }
 
+inline size_t policy_smem_bytes(const ah::PolicyDev& d, int threads) {
+    return sizeof(float) * ((size_t)ah::policy_weight_floats(d.n_floats) + (d.narrow ? 0 : 2 * (size_t)ah::kPolMaxW * threads));
+}
+
 // ah_policy (host struct, validated) -> the by-value kernel argument
 int make_policy_dev(const ah_policy* p, ah::PolicyDev* d, bool need_weights) {
     if (!p || !d) return AH_EINVAL;
@@ -1044,9 +1049,11 @@ int launch_step(ah_env* env, const ah_step_io* io, int K, cudaStream_t s) {
     if (launched) {
     } else if (act == 4) {
         ah::step_kernel<R, 4, ah::MODE_GENERIC><<<grid, threads, 0, s>>>(a);
-    } else if (act == 5) {                                   // the activations array is sized for blocks of kPolThreads
-        const unsigned pg = (unsigned)((env->n + ah::kPolThreads - 1) / ah::kPolThreads);
-        ah::step_kernel<R, 5, ah::MODE_GENERIC><<<pg < (unsigned)max_blocks ? pg : (unsigned)max_blocks, ah::kPolThreads, 0, s>>>(a);
+    } else if (act == 5) {                                   // blocks of <= kPolThreads; dynamic shared memory sized by the network
+        int pt = ah::kPolThreads;
+        while (pt > 64 && (env->n + pt - 1) / pt < 4 * (int64_t)env->sms) pt >>= 1;
+        const unsigned pg = (unsigned)((env->n + pt - 1) / pt);
+        ah::step_kernel<R, 5, ah::MODE_GENERIC><<<pg < (unsigned)max_blocks ? pg : (unsigned)max_blocks, pt, policy_smem_bytes(a.pol, pt), s>>>(a);
     } else if (act == 1) AH_LAUNCH_MODE(1); else if (act == 2) AH_LAUNCH_MODE(2); else AH_LAUNCH_MODE(3);
 #undef AH_LAUNCH_MODE
 #undef AH_LAUNCH
@@ -1258,8 +1265,9 @@ int ah_policy_act(ah_env* env, const ah_policy* policy, const void* d_obs, const
     DeviceGuard g(env->device);
     cudaStream_t s = (cudaStream_t)stream;
     const unsigned grid = (unsigned)((env->n + ah::kPolThreads - 1) / ah::kPolThreads);
-    AH_DISPATCH(env, (ah::policy_act_kernel<float><<<grid, ah::kPolThreads, 0, s>>>(env->n, pd, (const float*)d_obs, (const float*)d_values_in, d_actions, (float*)d_actions_real, (float*)d_values_out, env->seed, env->env_id0, env->blk)),
-                (ah::policy_act_kernel<double><<<grid, ah::kPolThreads, 0, s>>>(env->n, pd, (const double*)d_obs, (const double*)d_values_in, d_actions, (double*)d_actions_real, (double*)d_values_out, env->seed, env->env_id0, env->blk)));
+    const size_t psm = d_values_in ? 0 : policy_smem_bytes(pd, ah::kPolThreads);
+    AH_DISPATCH(env, (ah::policy_act_kernel<float><<<grid, ah::kPolThreads, psm, s>>>(env->n, pd, (const float*)d_obs, (const float*)d_values_in, d_actions, (float*)d_actions_real, (float*)d_values_out, env->seed, env->env_id0, env->blk)),
+                (ah::policy_act_kernel<double><<<grid, ah::kPolThreads, psm, s>>>(env->n, pd, (const double*)d_obs, (const double*)d_values_in, d_actions, (double*)d_actions_real, (double*)d_values_out, env->seed, env->env_id0, env->blk)));
     AH_LAUNCH_RC(env);
 }
 

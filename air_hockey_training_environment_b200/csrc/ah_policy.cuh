@@ -30,6 +30,11 @@ constexpr int kPolThreads = AH_POL_THREADS;            // block size of every ke
 constexpr int kPolMaxW = AH_POLICY_MAX_WIDTH;
 constexpr int kPolMaxFloats = (8 * kPolMaxW + kPolMaxW) + 3 * (kPolMaxW * kPolMaxW + kPolMaxW);
 
+// DYNAMIC shared memory of a kernel that evaluates a policy: the staged weights, then (general path only) the two
+// activation arrays [kPolMaxW][blockDim.x].  Sized per launch from the network -- 1.2 KB for the reference's PPO actor,
+// 46 KB for the widest net -- so that a small network does not cap the resident blocks per SM.
+__host__ __device__ inline int policy_weight_floats(int n_floats) { return (n_floats + 3) & ~3; }
+
 struct PolicyDev {                                      // by value in the kernel arguments
     int n_layers, width[5], act[4], w_off[4], b_off[4], n_floats;
     int narrow;                                         // every width <= 8: the register-resident evaluation
@@ -45,48 +50,93 @@ __device__ __forceinline__ void policy_stage(const PolicyDev& P, float* sw) {
     for (int t = threadIdx.x; t < P.n_floats; t += blockDim.x) sw[t] = P.weights[t];
 }
 
+// tanh(v) = 1 - 2 / (exp(2 v) + 1) on the fast exponential and reciprocal (|error| < 2e-7; saturates to +-1 through
+// exp -> inf / 0): 6 instructions where libm's tanhf inlines ~40 at each of the unrolled call sites -- the closed loop's
+// frame body must stay small enough for the instruction cache (14 warps per SM, each at its own PC)
+__device__ __forceinline__ float policy_tanh(float v) {
+    return 1.0f - __fdividef(2.0f, __expf(2.0f * v) + 1.0f);
+}
 __device__ __forceinline__ float policy_activate(float v, int act) {
     if (act == AH_ACTV_RELU) return fmaxf(v, 0.0f);
-    if (act == AH_ACTV_TANH) return tanhf(v);
+    if (act == AH_ACTV_TANH) return policy_tanh(v);
     return v;
 }
 
 // NARROW networks (every width <= 8: the reference's PPO actors 8-4-6-4-4 / 8-6-6-4-2, the A2C actor and the DDQN net
-// 8-8-4): activations stay in REGISTERS and every loop is unrolled to its compile-time bound with warp-uniform guards, so
-// the weight broadcasts (LDS.128) of a layer are issued ahead of the multiply-adds instead of one dependent
-// load -> FFMA per iteration.  A one-launch rollout of 65,536 envs has 3.5 warps per scheduler: it is bound by the
-// LATENCY of this chain, not by issue slots.  Same multiply-add order per output as the general path: same bits.
+// 8-8-4): activations stay in REGISTERS.  A one-launch rollout of 65,536 envs has 3.5 warps per scheduler, so the closed
+// loop is bound by the latency and the SIZE of this code, not by issue slots: the layer shapes those networks use are
+// compiled as exact, fully unrolled bodies (the weight broadcasts -- LDS.128 -- of a layer are issued ahead of its
+// multiply-adds, nothing is predicated off), any other shape <= 8 runs the guarded body; the loop over the layers is
+// NOT unrolled (one copy of each body in the instruction stream).  Same multiply-add order per output as the general
+// path: same bits.
+template <int WIN, int OUTP>
+__device__ __forceinline__ void narrow_layer(const float* __restrict__ W, const float* __restrict__ B, int act, float (&h)[8]) {
+    float o[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+    for (int j = 0; j < OUTP; j += 4) {
+        float4 acc = *reinterpret_cast<const float4*>(B + j);
+#pragma unroll
+        for (int c = 0; c < WIN; ++c) {
+            const float4 w = *reinterpret_cast<const float4*>(W + c * OUTP + j);
+            acc.x = fmaf(w.x, h[c], acc.x); acc.y = fmaf(w.y, h[c], acc.y);
+            acc.z = fmaf(w.z, h[c], acc.z); acc.w = fmaf(w.w, h[c], acc.w);
+        }
+        o[j] = acc.x; o[j + 1] = acc.y; o[j + 2] = acc.z; o[j + 3] = acc.w;
+    }
+    if (act == AH_ACTV_RELU) {
+#pragma unroll
+        for (int q = 0; q < OUTP; ++q) o[q] = fmaxf(o[q], 0.0f);
+    } else if (act == AH_ACTV_TANH) {
+#pragma unroll
+        for (int q = 0; q < OUTP; ++q) o[q] = policy_tanh(o[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) h[q] = o[q];
+}
+
+// any (win, outp) with win <= 8, outp in {4, 8}: the same body behind warp-uniform guards
+__device__ __forceinline__ void narrow_layer_any(const float* __restrict__ W, const float* __restrict__ B, int win, int outp, int act,
+                                                 float (&h)[8]) {
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; j += 4) {
+        float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (j < outp) {
+            acc = *reinterpret_cast<const float4*>(B + j);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                if (c < win) {
+                    const float4 w = *reinterpret_cast<const float4*>(W + c * outp + j);
+                    acc.x = fmaf(w.x, h[c], acc.x); acc.y = fmaf(w.y, h[c], acc.y);
+                    acc.z = fmaf(w.z, h[c], acc.z); acc.w = fmaf(w.w, h[c], acc.w);
+                }
+            }
+            acc.x = policy_activate(acc.x, act); acc.y = policy_activate(acc.y, act);
+            acc.z = policy_activate(acc.z, act); acc.w = policy_activate(acc.w, act);
+        }
+        o[j] = acc.x; o[j + 1] = acc.y; o[j + 2] = acc.z; o[j + 3] = acc.w;
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) h[c] = o[c];
+}
+
 __device__ __forceinline__ void policy_forward_narrow(const PolicyDev& P, const float* __restrict__ sw, const float (&x)[8], float (&y)[8]) {
     float h[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) h[c] = x[c];
-#pragma unroll
-    for (int l = 0; l < 4; ++l) {
-        if (l < P.n_layers) {
-            const int win = P.width[l], outp = (P.width[l + 1] + 3) & ~3, act = P.act[l];
-            const float* W = sw + P.w_off[l];
-            const float* B = sw + P.b_off[l];
-            float o[8];
-#pragma unroll
-            for (int j = 0; j < 8; j += 4) {
-                float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                if (j < outp) {
-                    acc = *reinterpret_cast<const float4*>(B + j);
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        if (c < win) {
-                            const float4 w = *reinterpret_cast<const float4*>(W + c * outp + j);
-                            acc.x = fmaf(w.x, h[c], acc.x); acc.y = fmaf(w.y, h[c], acc.y);
-                            acc.z = fmaf(w.z, h[c], acc.z); acc.w = fmaf(w.w, h[c], acc.w);
-                        }
-                    }
-                    acc.x = policy_activate(acc.x, act); acc.y = policy_activate(acc.y, act);
-                    acc.z = policy_activate(acc.z, act); acc.w = policy_activate(acc.w, act);
-                }
-                o[j] = acc.x; o[j + 1] = acc.y; o[j + 2] = acc.z; o[j + 3] = acc.w;
-            }
-#pragma unroll
-            for (int c = 0; c < 8; ++c) h[c] = o[c];
+#pragma unroll 1
+    for (int l = 0; l < P.n_layers; ++l) {
+        const int win = P.width[l], outp = (P.width[l + 1] + 3) & ~3, act = P.act[l];
+        const float* W = sw + P.w_off[l];
+        const float* B = sw + P.b_off[l];
+        switch (win * 16 + outp) {
+            case 8 * 16 + 4: narrow_layer<8, 4>(W, B, act, h); break;
+            case 8 * 16 + 8: narrow_layer<8, 8>(W, B, act, h); break;
+            case 6 * 16 + 4: narrow_layer<6, 4>(W, B, act, h); break;
+            case 6 * 16 + 8: narrow_layer<6, 8>(W, B, act, h); break;
+            case 4 * 16 + 4: narrow_layer<4, 4>(W, B, act, h); break;
+            case 4 * 16 + 8: narrow_layer<4, 8>(W, B, act, h); break;
+            default: narrow_layer_any(W, B, win, outp, act, h); break;
         }
     }
     const int wl = P.width[P.n_layers];
@@ -98,7 +148,7 @@ __device__ __forceinline__ void policy_forward_narrow(const PolicyDev& P, const 
 __device__ __forceinline__ void policy_forward(const PolicyDev& P, const float* __restrict__ sw, float* hs, const float (&x)[8],
                                                float (&y)[8]) {
     if (P.narrow) { policy_forward_narrow(P, sw, x, y); return; }
-    const int T = kPolThreads, tid = threadIdx.x;
+    const int T = blockDim.x, tid = threadIdx.x;
     float* in = hs;
     float* out = hs + kPolMaxW * T;
 #pragma unroll
@@ -254,8 +304,9 @@ __global__ void __launch_bounds__(kPolThreads) policy_act_kernel(int64_t n, Poli
                                                                  int8_t* __restrict__ actions, R* __restrict__ actions_real,
                                                                  R* __restrict__ values_out, uint64_t seed, uint64_t env_id0,
                                                                  const DevBlock* blk) {
-    __shared__ __align__(16) float sw[kPolMaxFloats];
-    __shared__ float hs[2 * kPolMaxW * kPolThreads];
+    extern __shared__ __align__(16) float pol_smem[];
+    float* sw = pol_smem;
+    float* hs = pol_smem + policy_weight_floats(P.n_floats);
     if (!values_in) policy_stage(P, sw);
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
