@@ -76,6 +76,34 @@ def test_network_in_kernel_equals_torch_module(which):
         assert torch.equal(acts.long(), vals.argmax(1))              # np.argmax: first maximum
 
 
+@pytest.mark.parametrize("which", ["ppo", "a2c", "continuous", "odd"])
+def test_register_path_of_narrow_networks_equals_the_general_path_bitwise(which, monkeypatch):
+    """Networks whose widths are all <= 8 are evaluated from registers (policy_forward_narrow: exact unrolled bodies for
+    the reference's layer shapes, a guarded body for any other, here 8-5-7-3); AH_POLICY_NO_NARROW forces the general
+    shared-memory path.  Same multiply-add order per output: the head values must be the same BITS."""
+    from air_hockey_training_environment_b200 import policy
+    n = 3000
+    env = make_env(n, seed=3)
+    net = {"ppo": policy.ppo_actor_discrete, "a2c": policy.a2c_actor, "continuous": policy.ppo_actor_continuous,
+           "odd": lambda: nn.Sequential(nn.Linear(8, 5), nn.Tanh(), nn.Linear(5, 7), nn.ReLU(), nn.Linear(7, 3)).eval()}[which]()
+    net = randomize(net).cuda().eval()
+    head = {"ppo": None, "a2c": None, "continuous": "continuous", "odd": "values"}[which]
+    dp = policy.DevicePolicy(net, env.device, head=head, select="greedy")
+    obs = scaled_obs(n, env.device)
+    got = []
+    for force_general in (False, True):
+        if force_general:
+            monkeypatch.setenv("AH_POLICY_NO_NARROW", "1")
+        vals = torch.empty(n, dp.n_actions, device=env.device)
+        env.policy_act(dp, obs=obs, values_out=vals)
+        got.append(vals.clone())
+    monkeypatch.delenv("AH_POLICY_NO_NARROW")
+    assert torch.equal(got[0].view(torch.int32), got[1].view(torch.int32))
+    with torch.no_grad():
+        want = net(obs)
+    assert (got[0] - want).abs().max().item() < 2e-4 * max(1.0, want.abs().max().item())
+
+
 # ---------------------------------------------------------------- discrete strategies vs a numpy restatement
 def restate_discrete(select, v, u0, u1, t, kw):
     """lib/exploration/strategies.py on ONE env: v = head values, (u0, u1) the frame's uniforms, t = step() call number."""
