@@ -75,12 +75,22 @@ class HostStepper:
         n, dev, q = env.n, env.device, (int(K) + 3) // 4
         self._lib = _capi.lib()
         self.d_act = [torch.empty(q, n, 4, dtype=torch.uint8, device=dev) for _ in range(slots)]
-        self.outs = [env.make_outputs(K, ("events", "obs_next")) for _ in range(slots)]
-        self.d_pos = [torch.empty(n, 4, dtype=torch.int16, device=dev) for _ in range(slots)]
-        self.d_vel = [torch.empty(n, 4, dtype=torch.float32, device=dev) for _ in range(slots)]
-        self.h = [HostResult(torch.empty(q, n, 4, dtype=torch.uint8).pin_memory(),
-                             torch.empty(n, 4, dtype=torch.int16).pin_memory(),
-                             torch.empty(n, 4, dtype=torch.float32).pin_memory(), K=int(K)) for _ in range(slots)]
+        # a step's results live in ONE buffer per slot -- [velocities f32 [n,4] | locations i16 [n,4] | event bytes u8 [q,n,4]],
+        # every part 8-byte aligned -- on the device and in pinned host memory: one device->host copy per step
+        nbytes = 16 * n + 8 * n + 4 * q * n
+
+        def parts(buf):
+            return (buf[24 * n:].view(q, n, 4), buf[16 * n:24 * n].view(torch.int16).view(n, 4), buf[:16 * n].view(torch.float32).view(n, 4))
+
+        self.d_buf = [torch.empty(nbytes, dtype=torch.uint8, device=dev) for _ in range(slots)]
+        self.h_buf = [torch.empty(nbytes, dtype=torch.uint8).pin_memory() for _ in range(slots)]
+        self.outs, self.d_pos, self.d_vel = [], [], []
+        for b in self.d_buf:
+            ev, pos, vel = parts(b)
+            o = env.make_outputs(K, ("obs_next",))
+            o.events = ev
+            self.outs.append(o); self.d_pos.append(pos); self.d_vel.append(vel)
+        self.h = [HostResult(*parts(b), K=int(K)) for b in self.h_buf]
         self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
         self.e_in = [torch.cuda.Event() for _ in range(slots)]
         self.e_run = [torch.cuda.Event() for _ in range(slots)]
@@ -122,9 +132,7 @@ class HostStepper:
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(self.e_run[s])
             h = self.h[s]
-            h.events.copy_(o.events, non_blocking=True)
-            h.obs_pos.copy_(self.d_pos[s], non_blocking=True)
-            h.obs_vel.copy_(self.d_vel[s], non_blocking=True)
+            self.h_buf[s].copy_(self.d_buf[s], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self.s_out)
             self.e_out[s] = ev

@@ -761,13 +761,13 @@ def run_e2e(env, dev, n, K, warm, steps, world):
     """The public HOST-buffer API (air_hockey_training_environment_b200.host.HostStepper): per step, H2D of the uint8
     quad-major actions from pinned host memory, the fused packed step, and D2H of the step's results (one event byte per
     env-frame = reward, done, score, game_over; the next observation as 4 x int16 + 4 x f32) into pinned host memory --
-    all inside the timed region; 3 slots / 3 streams so the copies overlap the kernels.  Every result is waited for on
+    all inside the timed region; 4 slots / 3 streams so the copies overlap the kernels.  Every result is waited for on
     the host before its slot is reused.  Its roofline is the host link: the same copies WITHOUT the kernels, on the same
     streams and buffers, concurrently on every rank (`roofline.peak`)."""
     import torch
     import torch.distributed as dist
     from air_hockey_training_environment_b200.host import HostStepper
-    slots = 3
+    slots = 4
     st = HostStepper(env, K=K, slots=slots)
     h_act = [torch.randint(0, 4, ((K + 3) // 4, n, 4), dtype=torch.uint8).pin_memory() for _ in range(slots)]
 
@@ -786,9 +786,7 @@ def run_e2e(env, dev, n, K, warm, steps, world):
             with torch.cuda.stream(st.s_in):
                 st.d_act[s].copy_(h_act[s], non_blocking=True)
             with torch.cuda.stream(st.s_out):
-                st.h[s].events.copy_(st.outs[s].events, non_blocking=True)
-                st.h[s].obs_pos.copy_(st.d_pos[s], non_blocking=True)
-                st.h[s].obs_vel.copy_(st.d_vel[s], non_blocking=True)
+                st.h_buf[s].copy_(st.d_buf[s], non_blocking=True)     # events + compact observation: one buffer per slot
 
     def sync():
         if world > 1:
@@ -821,7 +819,7 @@ def run_e2e(env, dev, n, K, warm, steps, world):
                          "peak_source": "measured in this run: the same pinned copies on the same streams without the kernels, "
                                         "all ranks concurrently"},
             "note": "HostStepper: pinned host actions in (1 B/frame/env); event byte (1 B/frame/env) and the next observation "
-                    "(4 x int16 + 4 x f32 per env) out, lossless; 3 slots / 3 streams; host clock around barrier + synchronize"}
+                    "(4 x int16 + 4 x f32 per env) out, lossless; 4 slots / 3 streams; host clock around barrier + synchronize"}
 
 
 if __name__ == "__main__":
