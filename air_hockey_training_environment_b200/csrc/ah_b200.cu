@@ -202,16 +202,26 @@ __device__ __forceinline__ void finish_stats(BlockStats& bs, DevBlock* blk, int 
     }
     const int lane = threadIdx.x & 31;
     int arrived = 0;
+    // every warp total is known to every lane (REDUX): lane q adds statistic q -- ONE shared atomic instruction with six
+    // active lanes and six addresses instead of six single-lane atomics (each of which ptxas wraps in its vote / leader /
+    // popc aggregation sequence: ~40 instructions per warp per launch)
+    {
+        int v = 0;
+        v = lane == AH_STAT_FRAMES ? fs : v;
+        v = lane == AH_STAT_DONES ? dd : v;
+        v = lane == AH_STAT_REWARD_SUM ? rs : v;
+        v = lane == AH_STAT_REWARD_SQ_SUM ? rq : v;
+        v = lane == AH_STAT_CONTACTS_ROBOT ? cr : v;
+        v = lane == AH_STAT_CONTACTS_OPPONENT ? co : v;
+        if (rare) {
+            v = lane == AH_STAT_RESET_TABLE_OVERFLOW ? ov : v;
+            v = lane == AH_STAT_NONFINITE ? nf : v;
+            v = lane == AH_STAT_DONE_AMBIGUOUS ? am : v;
+        }
+        if (v != 0) stat_add(bs, lane, v);
+    }
+    __syncwarp();
     if (lane == 0) {
-        stat_add(bs, AH_STAT_DONES, dd);
-        stat_add(bs, AH_STAT_FRAMES, fs);
-        stat_add(bs, AH_STAT_REWARD_SUM, rs);
-        stat_add(bs, AH_STAT_REWARD_SQ_SUM, rq);
-        if (cr) stat_add(bs, AH_STAT_CONTACTS_ROBOT, cr);
-        if (co) stat_add(bs, AH_STAT_CONTACTS_OPPONENT, co);
-        if (ov) stat_add(bs, AH_STAT_RESET_TABLE_OVERFLOW, ov);
-        if (nf) stat_add(bs, AH_STAT_NONFINITE, nf);
-        if (am) stat_add(bs, AH_STAT_DONE_AMBIGUOUS, am);
         __threadfence_block();
         arrived = atomicAdd(&bs.warps_done, 1);
     }
