@@ -34,7 +34,11 @@ class AhConfig(C.Structure):
 
 class AhRing(C.Structure):
     _fields_ = [("state", C.c_void_p), ("new_state", C.c_void_p), ("action", C.c_void_p), ("reward", C.c_void_p),
-                ("done", C.c_void_p), ("capacity", C.c_int64), ("appended", C.c_void_p)]
+                ("done", C.c_void_p), ("capacity", C.c_int64), ("appended", C.c_void_p),
+                ("format", C.c_int32), ("reserved0", C.c_int32), ("state_pos", C.c_void_p), ("new_state_pos", C.c_void_p)]
+
+
+AH_RING_ROWS, AH_RING_COMPACT = 0, 1
 
 
 AH_ACTV_LINEAR, AH_ACTV_RELU, AH_ACTV_TANH = 0, 1, 2

@@ -782,7 +782,8 @@ __global__ void ring_sample_kernel(int64_t n, int64_t capacity, const unsigned l
                                    int64_t batch, uint64_t seed, uint64_t draw,
                                    const R* __restrict__ r_state, const R* __restrict__ r_new_state, const void* __restrict__ r_action,
                                    const R* __restrict__ r_reward, const uint8_t* __restrict__ r_done,
-                                   R* state, void* action, R* reward, uint8_t* done, R* new_state, int64_t* index) {
+                                   R* state, void* action, R* reward, uint8_t* done, R* new_state, int64_t* index,
+                                   const short* __restrict__ r_state_pos, const short* __restrict__ r_new_state_pos) {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= batch) return;
     using V = typename Vec4T<R>::type;
@@ -802,15 +803,25 @@ __global__ void ring_sample_kernel(int64_t n, int64_t capacity, const unsigned l
     const uint64_t age = f / (uint64_t)n, env = f % (uint64_t)n;
     const uint64_t slot = (appended - 1ull - age) % (unsigned long long)capacity;     // age 0 = the newest tuple
     const int64_t row = (int64_t)(slot * (uint64_t)n + env);
-    const V* src0 = reinterpret_cast<const V*>(r_state) + 2 * row;
-    const V* src1 = reinterpret_cast<const V*>(r_new_state) + 2 * row;
     V* dst0 = reinterpret_cast<V*>(state) + 2 * s;
     V* dst1 = reinterpret_cast<V*>(new_state) + 2 * s;
-    dst0[0] = src0[0]; dst0[1] = src0[1];
-    dst1[0] = src1[0]; dst1[1] = src1[1];
+    if (r_state_pos) {                                    // AH_RING_COMPACT: int16 locations + velocities, int8 reward
+        const short4 p0 = reinterpret_cast<const short4*>(r_state_pos)[row], p1 = reinterpret_cast<const short4*>(r_new_state_pos)[row];
+        V a0, a1;
+        a0.x = (R)p0.x; a0.y = (R)p0.y; a0.z = (R)p0.z; a0.w = (R)p0.w;
+        a1.x = (R)p1.x; a1.y = (R)p1.y; a1.z = (R)p1.z; a1.w = (R)p1.w;
+        dst0[0] = a0; dst0[1] = reinterpret_cast<const V*>(r_state)[row];
+        dst1[0] = a1; dst1[1] = reinterpret_cast<const V*>(r_new_state)[row];
+        reward[s] = (R)reinterpret_cast<const int8_t*>(r_reward)[row];
+    } else {
+        const V* src0 = reinterpret_cast<const V*>(r_state) + 2 * row;
+        const V* src1 = reinterpret_cast<const V*>(r_new_state) + 2 * row;
+        dst0[0] = src0[0]; dst0[1] = src0[1];
+        dst1[0] = src1[0]; dst1[1] = src1[1];
+        reward[s] = r_reward[row];
+    }
     if (continuous) reinterpret_cast<V2*>(action)[s] = reinterpret_cast<const V2*>(r_action)[row];
     else reinterpret_cast<int8_t*>(action)[s] = reinterpret_cast<const int8_t*>(r_action)[row];
-    reward[s] = r_reward[row];
     done[s] = r_done[row];
     if (index) index[s] = (int64_t)f;
 }
@@ -1005,6 +1016,12 @@ int launch_step(ah_env* env, const ah_step_io* io, int K, cudaStream_t s) {
             p.ring_action = reinterpret_cast<int8_t*>(io->ring->action);
             p.ring_reward = (R*)io->ring->reward; p.ring_done = io->ring->done; p.ring_capacity = io->ring->capacity;
             p.ring_appended = reinterpret_cast<unsigned long long*>(io->ring->appended);
+            if (io->ring->format == AH_RING_COMPACT) {
+                p.ring_state_pos = reinterpret_cast<short*>(io->ring->state_pos);
+                p.ring_new_state_pos = reinterpret_cast<short*>(io->ring->new_state_pos);
+                p.ring_reward8 = reinterpret_cast<int8_t*>(io->ring->reward);
+                ah::step_packed_kernel<R, ah::IO_RING_COMPACT><<<pgrid, pth, 0, s>>>(p);
+            } else
             ah::step_packed_kernel<R, ah::IO_RING><<<pgrid, pth, 0, s>>>(p);
         } else {
             ah::step_packed_kernel<R, ah::IO_PACKED><<<pgrid, pth, 0, s>>>(p);
@@ -1248,6 +1265,11 @@ int ah_step(ah_env* env, const ah_step_io* io, int K, void* stream) {
         if (r->capacity <= 0 || !r->state || !r->new_state || !r->action || !r->reward || !r->done || !r->appended) return AH_EINVAL;
         if (reinterpret_cast<uintptr_t>(r->appended) & 7u) return AH_EINVAL;
         if (!aligned16(r->state) || !aligned16(r->new_state)) return AH_EINVAL;
+        if (r->format != AH_RING_ROWS && r->format != AH_RING_COMPACT) return AH_EINVAL;
+        if (r->format == AH_RING_COMPACT) {      // the compact layout is written by the packed FP32 kernel only
+            if (env->dtype != AH_F32 || !io->events || !r->state_pos || !r->new_state_pos) return AH_EINVAL;
+            if ((reinterpret_cast<uintptr_t>(r->state_pos) | reinterpret_cast<uintptr_t>(r->new_state_pos)) & 7u) return AH_EINVAL;
+        }
     }
     DeviceGuard g(env->device);
     cudaStream_t s = (cudaStream_t)stream;
@@ -1378,16 +1400,22 @@ int ah_ring_sample(ah_env* env, const ah_ring* ring, int continuous, int64_t bat
     if (!env || !ring || batch <= 0 || !d_state || !d_action || !d_reward || !d_done || !d_new_state) return AH_EINVAL;
     if (ring->capacity <= 0 || !ring->state || !ring->new_state || !ring->action || !ring->reward || !ring->done || !ring->appended) return AH_EINVAL;
     if (!aligned16(d_state) || !aligned16(d_new_state) || !aligned16(ring->state) || !aligned16(ring->new_state)) return AH_EINVAL;
+    const bool compact = ring->format == AH_RING_COMPACT;
+    if (ring->format != AH_RING_ROWS && !compact) return AH_EINVAL;
+    if (compact && (continuous || !ring->state_pos || !ring->new_state_pos ||
+                    ((reinterpret_cast<uintptr_t>(ring->state_pos) | reinterpret_cast<uintptr_t>(ring->new_state_pos)) & 7u))) return AH_EINVAL;
+    const short* sp0 = compact ? reinterpret_cast<const short*>(ring->state_pos) : nullptr;
+    const short* sp1 = compact ? reinterpret_cast<const short*>(ring->new_state_pos) : nullptr;
     DeviceGuard g(env->device);
     cudaStream_t s = (cudaStream_t)stream;
     const unsigned grid = (unsigned)((batch + 255) / 256);
     const unsigned long long* ap = reinterpret_cast<const unsigned long long*>(ring->appended);
     AH_DISPATCH(env, (ah::ring_sample_kernel<float><<<grid, 256, 0, s>>>(env->n, ring->capacity, ap, continuous, batch, env->seed, draw,
                           (const float*)ring->state, (const float*)ring->new_state, ring->action, (const float*)ring->reward, ring->done,
-                          (float*)d_state, d_action, (float*)d_reward, d_done, (float*)d_new_state, d_index)),
+                          (float*)d_state, d_action, (float*)d_reward, d_done, (float*)d_new_state, d_index, sp0, sp1)),
                 (ah::ring_sample_kernel<double><<<grid, 256, 0, s>>>(env->n, ring->capacity, ap, continuous, batch, env->seed, draw,
                           (const double*)ring->state, (const double*)ring->new_state, ring->action, (const double*)ring->reward, ring->done,
-                          (double*)d_state, d_action, (double*)d_reward, d_done, (double*)d_new_state, d_index)));
+                          (double*)d_state, d_action, (double*)d_reward, d_done, (double*)d_new_state, d_index, sp0, sp1)));
     AH_LAUNCH_RC(env);
 }
 

@@ -47,6 +47,9 @@ struct PackedArgs {
     R* ring_reward; uint8_t* ring_done;   // [capacity][n]
     int64_t ring_capacity;
     unsigned long long* ring_appended;
+    // IO_RING_COMPACT (AH_RING_COMPACT): ring_state / ring_new_state hold the velocities [capacity][n][4], the locations go
+    // to int16 [capacity][n][4], the reward to int8 [capacity][n]
+    short* ring_state_pos; short* ring_new_state_pos; int8_t* ring_reward8;
     // IO_UNPACKED: the general API's tensors -- time-major int8 actions in, four per-frame outputs out
     const int8_t* actions8;               // i8 [K][n]
     R* reward; uint8_t* done; int8_t* score; uint8_t* game_over;     // [K][n] each
@@ -58,7 +61,18 @@ struct PackedArgs {
 //   IO_UNPACKED  int8 [K][n] actions in; reward real / done u8 / score i8 / game_over u8 [K][n] out   (BatchedAirHockey.step's
 //                default tensors: the event byte is decoded into the caller's four tensors as it is produced)
 //   IO_PHILOX    actions drawn in the kernel (Philox stream 1, frame-indexed), no per-frame output: pure simulation
-enum { IO_PACKED = 0, IO_RING = 1, IO_UNPACKED = 2, IO_PHILOX = 3 };
+//   IO_RING_COMPACT  IO_RING with the compact tuple layout (include/ah_b200.h: AH_RING_COMPACT): 51 instead of 70 bytes per
+//                env-frame and only whole-sector stores (one STG.128 + one STG.64 per observation, each contiguous per warp)
+enum { IO_PACKED = 0, IO_RING = 1, IO_UNPACKED = 2, IO_PHILOX = 3, IO_RING_COMPACT = 4 };
+
+// Observation -> compact ring row: velocities as they are, locations int()-truncated to int16 (exact: 0 <= x < 2^15)
+__device__ __forceinline__ void store_obs_compact(float* vel, short* pos, int64_t row, const Env<float>& e) {
+    reinterpret_cast<float4*>(vel)[row] = make_float4(e.rdx, e.rdy, e.pdx, e.pdy);
+    const uint32_t a = (uint32_t)(__float2int_rz(e.rx) & 0xffff) | ((uint32_t)__float2int_rz(e.ry) << 16);
+    const uint32_t b = (uint32_t)(__float2int_rz(e.px) & 0xffff) | ((uint32_t)__float2int_rz(e.py) << 16);
+    reinterpret_cast<uint2*>(pos)[row] = make_uint2(a, b);
+}
+__device__ __forceinline__ void store_obs_compact(double*, short*, int64_t, const Env<double>&) {}      // (AH_F32 only)
 
 // the actions of up to 4 consecutive frames of env i, gathered from the time-major int8 tensor into one word
 __device__ __forceinline__ uint32_t gather_quad_actions(const int8_t* p, uint32_t n, int count) {
@@ -228,7 +242,10 @@ constexpr int kPackedThreads = AH_PACKED_THREADS;
 // K = 8): 6 (66 registers, 7 resident blocks) 140.7 us, 8 (60 registers) 154.5 us, 9 (56, spills) 191 us -- more resident
 // warps put more half-row stores in flight than L1 can merge before they leave for L2.
 // (IO_UNPACKED / IO_PHILOX need 58-60 registers: 8 blocks per SM instead of spilling at 9)
-template <typename R, int IO> struct PackedOcc { static constexpr int blocks = IO == 1 ? AH_PACKED_OCC_RING : (IO >= 2 ? 8 : AH_PACKED_OCC_F32); };
+#ifndef AH_PACKED_OCC_RINGC
+#define AH_PACKED_OCC_RINGC 8
+#endif
+template <typename R, int IO> struct PackedOcc { static constexpr int blocks = IO == 1 ? AH_PACKED_OCC_RING : (IO == 4 ? AH_PACKED_OCC_RINGC : (IO >= 2 ? 8 : AH_PACKED_OCC_F32)); };
 template <int IO> struct PackedOcc<double, IO> { static constexpr int blocks = 512 / AH_PACKED_THREADS; };
 
 // AirHockey.reset with the env's NEXT Philox draw precomputed: the draw for reset index `resets` depends only on
@@ -250,8 +267,9 @@ __device__ __forceinline__ void env_reset_cached(Env<R>& e, bool total, const Re
 template <typename R, int IO>
 __global__ void __launch_bounds__(kPackedThreads, PackedOcc<R, IO>::blocks)
 step_packed_kernel(const PackedArgs<R> a) {
-    constexpr bool RING = IO == IO_RING;
-    constexpr bool ORDERED = IO == IO_RING || IO == IO_PHILOX;      // the launch reads a device counter at its start
+    constexpr bool RING = IO == IO_RING || IO == IO_RING_COMPACT;
+    constexpr bool COMPACT = IO == IO_RING_COMPACT;
+    constexpr bool ORDERED = RING || IO == IO_PHILOX;      // the launch reads a device counter at its start
     using V2 = typename std::conditional<sizeof(R) == 4, float2, double2>::type;
     __shared__ BlockStats bs;
     if (threadIdx.x < AH_NSTATS) bs.v[threadIdx.x] = 0;
@@ -276,7 +294,7 @@ step_packed_kernel(const PackedArgs<R> a) {
         Env<R> e = load_env<R>(a.st, i);
         uint32_t aw = 0;
         const int8_t* ap = nullptr;                    // IO_UNPACKED: &actions8[first frame of the quad][i]
-        if constexpr (IO == IO_PACKED || IO == IO_RING) aw = a.actions[i];
+        if constexpr (IO == IO_PACKED || RING) aw = a.actions[i];
         if constexpr (IO == IO_UNPACKED) { ap = a.actions8 + i; aw = gather_quad_actions(ap, n, nK < 4 ? nK : 4); }
         Philox4 ablock = {};
         uint32_t ablock_id = 0xffffffffu;
@@ -303,7 +321,7 @@ step_packed_kernel(const PackedArgs<R> a) {
         do {
             const int kc = left < 4 ? left : 4;
             uint32_t aw_next = 0;
-            if constexpr (IO == IO_PACKED || IO == IO_RING) { if (left > 4) aw_next = a.actions[off + n]; }
+            if constexpr (IO == IO_PACKED || RING) { if (left > 4) aw_next = a.actions[off + n]; }
             if constexpr (IO == IO_UNPACKED) {
                 if (left > 4) { ap += 4 * (size_t)n; aw_next = gather_quad_actions(ap, n, left - 4 < 4 ? left - 4 : 4); }
             }
@@ -332,11 +350,13 @@ step_packed_kernel(const PackedArgs<R> a) {
                 // ---- robot.move(a): sub-update #1                      game.py:136 -> agent.py:32-36
                 move_robot<R>(e, false, nd.x, nd.y);
                 physics_tail_thr<R, false>(e, dot_fma, thr, contacts);
-                if constexpr (RING) store_obs<R>(a.ring_state, rrow, get_state<R>(e, true));       // Observation.state      agent.py:61
+                if constexpr (COMPACT) store_obs_compact(a.ring_state, a.ring_state_pos, rrow, e);
+                else if constexpr (RING) store_obs<R>(a.ring_state, rrow, get_state<R>(e, true));  // Observation.state      agent.py:61
                 // ---- robot.step(a) -> self.move(a): sub-update #2      agent.py:64
                 move_robot<R>(e, false, nd.x, nd.y);
                 physics_tail_thr<R, false>(e, dot_fma, thr, contacts);
-                if constexpr (RING) store_obs<R>(a.ring_new_state, rrow, get_state<R>(e, true));   // Observation.new_state  agent.py:67
+                if constexpr (COMPACT) store_obs_compact(a.ring_new_state, a.ring_new_state_pos, rrow, e);
+                else if constexpr (RING) store_obs<R>(a.ring_new_state, rrow, get_state<R>(e, true));   // Observation.new_state  agent.py:67
                 // ---- Rewards                                           agent.py:70-71
                 // event byte: (reward + 4) / 2 = 1 + closer + wall + 2 done, done << 3, (score + 1) << 4, game_over << 6
                 uint32_t byte; bool scored; int sc = 0;
@@ -352,7 +372,8 @@ step_packed_kernel(const PackedArgs<R> a) {
                     if (scored) sc = score_f > 0.0f ? 1 : -1;
                 }
                 if constexpr (RING) {        // the rest of the Observation tuple: reward = 2 (byte & 7) - 4, done = bit 3
-                    a.ring_reward[rrow] = (R)(2 * (int)(byte & 7u) - 4);
+                    if constexpr (COMPACT) a.ring_reward8[rrow] = (int8_t)(2 * (int)(byte & 7u) - 4);
+                    else a.ring_reward[rrow] = (R)(2 * (int)(byte & 7u) - 4);
                     a.ring_done[rrow] = (uint8_t)((byte >> 3) & 1u);
                     slot += 1; rrow += (int64_t)n;
                     if (slot == a.ring_capacity) { slot = 0; rrow = i; }
@@ -401,7 +422,7 @@ step_packed_kernel(const PackedArgs<R> a) {
                 }
             } while (--jr > 0);
             if (left < 4) ev >>= 8 * (4 - left);                           // partial last quad: frame 0 in byte 0
-            if constexpr (IO == IO_PACKED || IO == IO_RING) a.events[off] = ev;
+            if constexpr (IO == IO_PACKED || RING) a.events[off] = ev;
             // statistics of the quad from the packed word
             const uint32_t r3 = ev & 0x07070707u;
             r3sum = (int)__dp4a(r3, 0x01010101u, (uint32_t)r3sum);

@@ -89,26 +89,64 @@ class ReplayRing:
     FIELDS = ("state", "action", "reward", "done", "new_state")
 
     def __init__(self, capacity: int, n_envs: int, dtype: torch.dtype, device, continuous: bool = False,
-                 default: Optional[Dict[str, float]] = None):
+                 default: Optional[Dict[str, float]] = None, compact: bool = False):
+        """compact: the AH_RING_COMPACT layout (include/ah_b200.h) -- 51 instead of 70 bytes per tuple, written by the packed
+        FP32 rollout kernel only: the observations' int()-truncated locations as int16 ``state_pos`` / ``new_state_pos``
+        [capacity, N, 4], their velocities as float32 ``state`` / ``new_state`` [capacity, N, 4], ``reward`` as int8.
+        ``retreive`` and ``sample`` return the same tensors either way."""
         self.capacity, self.n = int(capacity), int(n_envs)
-        self.continuous = continuous
-        self.state = torch.zeros(capacity, n_envs, 8, dtype=dtype, device=device)
-        self.new_state = torch.zeros(capacity, n_envs, 8, dtype=dtype, device=device)
+        self.continuous, self.compact, self.dtype = continuous, bool(compact), dtype
+        if compact and (dtype != torch.float32 or continuous):
+            raise ValueError("the compact ring layout holds float32 discrete-action tuples")
+        obs_w = 4 if compact else 8
+        self.state = torch.zeros(capacity, n_envs, obs_w, dtype=dtype, device=device)
+        self.new_state = torch.zeros(capacity, n_envs, obs_w, dtype=dtype, device=device)
         self.action = (torch.zeros(capacity, n_envs, 2, dtype=dtype, device=device) if continuous
                        else torch.zeros(capacity, n_envs, dtype=torch.int8, device=device))
-        self.reward = torch.zeros(capacity, n_envs, dtype=dtype, device=device)
+        self.reward = torch.zeros(capacity, n_envs, dtype=torch.int8 if compact else dtype, device=device)
         self.done = torch.zeros(capacity, n_envs, dtype=torch.uint8, device=device)
         self.counter = torch.zeros(1, dtype=torch.int64, device=device)
         self._c = _capi.AhRing(self.state.data_ptr(), self.new_state.data_ptr(), self.action.data_ptr(),
                                self.reward.data_ptr(), self.done.data_ptr(), self.capacity, self.counter.data_ptr())
+        self._arrays = ["state", "new_state", "action", "reward", "done", "counter"]
+        if compact:
+            self.state_pos = torch.zeros(capacity, n_envs, 4, dtype=torch.int16, device=device)
+            self.new_state_pos = torch.zeros(capacity, n_envs, 4, dtype=torch.int16, device=device)
+            self._c.format = _capi.AH_RING_COMPACT
+            self._c.state_pos, self._c.new_state_pos = self.state_pos.data_ptr(), self.new_state_pos.data_ptr()
+            self._arrays += ["state_pos", "new_state_pos"]
         self._draw = 0
         if default:                                    # lib/buffer.py:19-22: a buffer full of default entries
             self.fill(default)
 
+    def _put(self, field: str, index, value) -> None:
+        """Write ``value`` (a scalar or a tensor in the PUBLIC shape of ``field``) at ``index`` of the ring's arrays."""
+        dst = getattr(self, field)
+        if self.compact and field in ("state", "new_state"):
+            pos = getattr(self, field + "_pos")
+            if torch.is_tensor(value):
+                value = value.to(dst.device)
+                pos[index] = torch.trunc(value[..., :4]).to(torch.int16)
+                dst[index] = value[..., 4:].to(dst.dtype)
+            else:
+                pos[index] = int(value)
+                dst[index] = value
+        else:
+            dst[index] = value.to(device=dst.device, dtype=dst.dtype) if torch.is_tensor(value) else value
+
+    def _get(self, field: str, index) -> torch.Tensor:
+        """Rows ``index`` of ``field`` in its public shape and dtype (the compact layout decoded)."""
+        v = getattr(self, field)[index]
+        if self.compact and field in ("state", "new_state"):
+            return torch.cat([getattr(self, field + "_pos")[index].to(v.dtype), v], dim=-1)
+        if self.compact and field == "reward":
+            return v.to(self.dtype)
+        return v
+
     def fill(self, default: Dict[str, float]) -> None:
         """Fill every slot with a default tuple (``MemoryBuffer(capacity, default)``, lib/buffer.py:19-22)."""
         for k in self.FIELDS:
-            getattr(self, k).fill_(default.get(k, 0))
+            self._put(k, slice(None), default.get(k, 0))
         self.counter.fill_(self.capacity)
 
     def append(self, state: torch.Tensor, action: torch.Tensor, reward: torch.Tensor, done: torch.Tensor,
@@ -118,6 +156,11 @@ class ReplayRing:
         Stream-ordered, no host sync: the slot is computed on the device from the ring's counter."""
         slot = self.counter % self.capacity
         for k, v in zip(self.FIELDS, (state, action, reward, done, new_state)):
+            if self.compact and k in ("state", "new_state"):
+                v = v.to(self.state.device)
+                getattr(self, k + "_pos").index_copy_(0, slot, torch.trunc(v[..., :4]).to(torch.int16).reshape(1, self.n, 4))
+                getattr(self, k).index_copy_(0, slot, v[..., 4:].to(self.dtype).reshape(1, self.n, 4))
+                continue
             dst = getattr(self, k)
             dst.index_copy_(0, slot, v.to(dst.dtype).reshape((1,) + tuple(dst.shape[1:])))
         self.counter += 1
@@ -141,7 +184,7 @@ class ReplayRing:
         """``MemoryBuffer.retreive`` (lib/buffer.py:34-45): the held tuples, newest first, as ``[len, N, ...]`` tensors;
         ``average=True`` returns the one-entry column average ``int(sum(col) / len)`` (truncated, :37-38)."""
         idx = self.order()
-        got = {k: getattr(self, k)[idx] for k in self.FIELDS}
+        got = {k: self._get(k, idx) for k in self.FIELDS}
         if average:
             got = {k: torch.trunc(v.to(torch.float64).sum(0, keepdim=True) / max(1, idx.numel())).to(v.dtype)
                    for k, v in got.items()}
@@ -157,7 +200,7 @@ class ReplayRing:
             raise ValueError("Sample larger than population or is negative")
         if draw is None:
             draw, self._draw = self._draw, self._draw + 1
-        dev, dt, B = self.state.device, self.state.dtype, int(batch_size)
+        dev, dt, B = self.state.device, self.dtype, int(batch_size)
         if out is None:
             out = {"state": torch.empty(B, 8, dtype=dt, device=dev), "new_state": torch.empty(B, 8, dtype=dt, device=dev),
                    "action": (torch.empty(B, 2, dtype=dt, device=dev) if self.continuous
@@ -178,10 +221,10 @@ class ReplayRing:
             self.fill(default)
 
     def state_dict(self) -> Dict[str, torch.Tensor]:
-        return {k: getattr(self, k).clone() for k in ("state", "new_state", "action", "reward", "done", "counter")}
+        return {k: getattr(self, k).clone() for k in self._arrays}
 
     def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
-        for k in ("state", "new_state", "action", "reward", "done", "counter"):
+        for k in self._arrays:
             getattr(self, k).copy_(sd[k])
 
 
@@ -496,6 +539,8 @@ class BatchedAirHockey:
             if ring.continuous != (io.action_kind in (_capi.AH_ACT_CONTINUOUS, _capi.AH_ACT_CONTINUOUS_REPEAT)
                                    or (policy is not None and policy.continuous)):
                 raise ValueError("ring action layout (discrete/continuous) does not match the actions given")
+            if ring.compact and (out is None or out.events is None):
+                raise ValueError("a compact ring is appended by the packed rollout mode only (packed actions + out.events)")
             io.ring = C.pointer(ring._c)
         return StepPlan(io, C.byref(io), int(K), out, (actions, reset_table, ring, policy_weights, policy))
 

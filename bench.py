@@ -644,29 +644,41 @@ def run_rollout_k1(env, dev, n):
 
 def run_ring_append(env, dev, n, K, world=1):
     """BASELINE config 4: per GPU 2^20 envs, the headline step PLUS the fused replay-ring append of the Observation tuple
-    (state 8 reals, action, reward, done, new_state 8 reals = 70 B per env-frame; replaces MemoryBuffer.append,
+    (state, action, reward, done, new_state: 70 B per env-frame as reals, 51 B in the compact layout; replaces MemoryBuffer.append,
     lib/buffer.py:24-32), sharded over `world` GPUs with the per-rollout NCCL all-reduce of the statistics inside the
     timed region and its payload checked.  HBM-bound (write-heavy): the roofline is per GPU."""
     import torch
     from air_hockey_training_environment_b200 import ReplayRing
     from air_hockey_training_environment_b200.env import pack_actions
-    ring = ReplayRing(2 * K, n, env.dtype, dev)
     out = env.make_outputs(K, ("events", "obs_next"))
     acts = [pack_actions(torch.randint(0, 4, (K, n), dtype=torch.int8, device=dev)) for _ in range(4)]
-    red = StatsReducer(env, world, dev)
-    reps = 96
-    ms = _time_loop(dev, lambda i: env.step(acts[i % 4], K=K, out=out, ring=ring), 16, reps, world, red)
-    chk = red.check(world * n * K * reps)
     hbm_peak, src, _ = peaks()
-    b = n * (2 * STATE_BYTES + 32 + K * (1 + 1) + K * 70)      # state in + out, obs_next, action + event byte, the 70-B tuple
-    ach = b / (ms * 1e-3) / 1e9
-    del ring
-    torch.cuda.empty_cache()
-    return {"value": world * n * K / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "n_gpus": world, "envs_total": world * n,
-            "ring_capacity_frames": 2 * K, "stats_allreduce": chk,
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                         "per": "GPU", "traffic": profile_fact("ring_dram_bytes_per_launch"), "kernel": "ah::step_packed_kernel<float, RING>",
-                         "algorithmic_bytes_per_launch": b, "bytes_per_env_step": b / (n * K)}}
+    res = {}
+    # the compact tuple layout (AH_RING_COMPACT: int16 locations + f32 velocities + int8 reward = 51 B, whole-sector stores) is
+    # the one config 4 is quoted on; the rows layout (the reference's tuple as 70 B of reals) is timed beside it
+    for key, compact, tuple_bytes in (("", True, 51), ("rows_layout_", False, 70)):
+        ring = ReplayRing(2 * K, n, env.dtype, dev, compact=compact)
+        red = StatsReducer(env, world, dev)
+        reps = 96
+        ms = _time_loop(dev, lambda i: env.step(acts[i % 4], K=K, out=out, ring=ring), 16, reps, world, red)
+        chk = red.check(world * n * K * reps)
+        b = n * (2 * STATE_BYTES + 32 + K * (1 + 1) + K * tuple_bytes)      # state in + out, obs_next, action + event byte, the tuple
+        ach = b / (ms * 1e-3) / 1e9
+        del ring
+        torch.cuda.empty_cache()
+        if compact:
+            res = {"value": world * n * K / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "n_gpus": world, "envs_total": world * n,
+                   "ring_capacity_frames": 2 * K, "ring_layout": "compact (51 B per tuple)", "stats_allreduce": chk,
+                   "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                                "per": "GPU", "traffic": None, "kernel": "ah::step_packed_kernel<float, IO_RING_COMPACT>",
+                                "algorithmic_bytes_per_launch": b, "bytes_per_env_step": b / (n * K)}}
+        else:
+            res["rows_layout"] = {"value": world * n * K / (ms * 1e-3), "ms_per_step": ms, "stats_frames_ok": chk["ok"],
+                                  "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                                               "traffic": profile_fact("ring_dram_bytes_per_launch"),
+                                               "kernel": "ah::step_packed_kernel<float, IO_RING>",
+                                               "algorithmic_bytes_per_launch": b, "bytes_per_env_step": b / (n * K)}}
+    return res
 
 
 def run_unpacked(env, dev, n, K):

@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define AH_ABI_VERSION 2
+#define AH_ABI_VERSION 3
 #define AH_ACTOR_NWEIGHTS 114   /* W1[4][8] b1[4] W2[6][4] b2[6] W3[4][6] b3[4] W4[4][4] b4[4], see ah_actor_sample */
 
 typedef struct ah_env ah_env;
@@ -181,7 +181,17 @@ typedef struct ah_ring {
     uint64_t* appended; /* device uint64[1], owned by the ring: Observation tuples appended so far.  The step kernel   */
                         /* reads the write slot from it and advances it (so captured graphs advance it too);          */
                         /* MemoryBuffer.purge (lib/buffer.py:52-61) = set it to 0                                     */
+    /* AH_RING_COMPACT (AH_F32, discrete actions, packed rollout mode): the same tuples in 51 instead of 70 bytes, every    */
+    /* array contiguous per warp -- the observation's four locations are int()-truncated in the reference                  */
+    /* (airhockey.py:136-147), so they are kept as int16; `state` / `new_state` then hold only the four velocities,         */
+    /* float [capacity][n][4]; `reward` is int8 [capacity][n] (lib/rewards.py:118-142 returns integers in [-4, 6]).          */
+    /* ah_ring_sample decodes to the same outputs either way.                                                              */
+    int32_t format;       /* AH_RING_ROWS (0) or AH_RING_COMPACT */
+    int32_t reserved0;
+    void* state_pos;      /* AH_RING_COMPACT: int16 [capacity][n][4]  int(agent.x), int(agent.y), int(puck.x), int(puck.y) */
+    void* new_state_pos;  /* AH_RING_COMPACT: int16 [capacity][n][4] */
 } ah_ring;
+enum { AH_RING_ROWS = 0, AH_RING_COMPACT = 1 };
 
 /* ---- inputs / outputs of the fused step ---- */
 typedef struct ah_step_io {

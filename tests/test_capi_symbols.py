@@ -37,7 +37,7 @@ def test_every_declared_symbol_is_exported_and_bound():
 
 def test_abi_version_and_strerror():
     lib = _capi.lib()
-    assert lib.ah_abi_version() == 2
+    assert lib.ah_abi_version() == 3
     assert _capi.strerror(_capi.AH_OK) == "ok"
     assert "agent" in _capi.strerror(_capi.AH_EAGENT)
     assert "CUDA" in _capi.strerror(_capi.AH_ECUDA)
@@ -46,7 +46,7 @@ def test_abi_version_and_strerror():
 def test_struct_layouts_match_header():
     # sizes the C side assumes (LP64): ah_config 32 B, ah_ring 56 B, ah_step_io 160 B
     assert C.sizeof(_capi.AhConfig) == 32
-    assert C.sizeof(_capi.AhRing) == 56
+    assert C.sizeof(_capi.AhRing) == 80
     assert C.sizeof(_capi.AhStepIO) == 160
 
 

@@ -308,3 +308,79 @@ def test_packed_mode_ring_append_under_graph_replay_and_argument_errors():
     assert all(torch.equal(got[k], want[k]) for k in want)
     with pytest.raises(AhError):                          # the append needs the whole env range in one launch
         env.step(acts, K=K, out=out, ring=ring, env_range=(0, 256))
+
+
+# ---------------------------------------------------------------- the compact ring layout (AH_RING_COMPACT)
+@pytest.mark.parametrize("K,cap", [(8, 16), (3, 7), (5, 4)])
+def test_compact_ring_holds_the_same_tuples_as_the_rows_layout(K, cap):
+    """``ReplayRing(compact=True)`` (int16 locations + float32 velocities + int8 reward: 51 instead of 70 bytes per tuple,
+    written by ah::step_packed_kernel<float, IO_RING_COMPACT>) against the rows layout on the same games: retreive() and
+    sample() return identical tensors, launch after launch, across wrap-arounds; env state, events and statistics equal."""
+    from air_hockey_training_environment_b200 import ReplayRing
+    from air_hockey_training_environment_b200.env import pack_actions
+    n = 1000
+    a, b = make_env(n, torch.float32, seed=21), make_env(n, torch.float32, seed=21)
+    for env in (a, b):
+        env.step(None, K=700, out=env.make_outputs(700, ()))
+    ra = ReplayRing(cap, n, a.dtype, a.device, compact=True)
+    rb = ReplayRing(cap, n, b.dtype, b.device)
+    assert ra.state.shape == (cap, n, 4) and ra.state_pos.dtype == torch.int16 and ra.reward.dtype == torch.int8
+    g = torch.Generator(device="cuda").manual_seed(6)
+    for launch in range(5):
+        acts = pack_actions(torch.randint(0, 4, (K, n), dtype=torch.int8, device="cuda", generator=g))
+        oa = a.step(acts, K=K, out=a.make_outputs(K, ("events", "obs_next")), ring=ra)
+        ob = b.step(acts, K=K, out=b.make_outputs(K, ("events", "obs_next")), ring=rb)
+        assert torch.equal(oa.events, ob.events) and torch.equal(oa.obs_next, ob.obs_next)
+        assert ra.appended == rb.appended == (launch + 1) * K
+        got, want = ra.retreive(), rb.retreive()
+        for k in want:
+            assert got[k].dtype == want[k].dtype and torch.equal(got[k], want[k]), (launch, k)
+        B = min(4096, len(rb) * n)
+        sa, sb = ra.sample(B, a, draw=launch, with_index=True), rb.sample(B, b, draw=launch, with_index=True)
+        for k in sb:
+            assert sa[k].dtype == sb[k].dtype and torch.equal(sa[k], sb[k]), (launch, k)
+    for x, y in zip((a.puck, a.robot, a.opponent, a.prev_dist, a.meta), (b.puck, b.robot, b.opponent, b.prev_dist, b.meta)):
+        assert torch.equal(x, y)
+    assert a.stats() == b.stats()
+
+
+def test_compact_ring_host_verbs_checkpoint_and_argument_errors():
+    """fill / append / purge / state_dict on the compact layout behave like the rows layout; the layout is refused where
+    no kernel writes it (the general kernel, the FP64 build, continuous actions)."""
+    from air_hockey_training_environment_b200 import AhError, ReplayRing
+    from air_hockey_training_environment_b200.env import pack_actions
+    n, cap = 64, 5
+    env = make_env(n, torch.float32, seed=2)
+    rc, rr = ReplayRing(cap, n, env.dtype, env.device, compact=True), ReplayRing(cap, n, env.dtype, env.device)
+    default = {"state": 3, "action": 1, "reward": -2, "done": 0, "new_state": 7}
+    for r in (rc, rr):
+        r.fill(default)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for _ in range(7):                                   # wraps
+        st = torch.floor(torch.rand(n, 8, device="cuda", generator=g) * 400)
+        st[:, 4:] = torch.rand(n, 4, device="cuda", generator=g) * 20 - 10
+        ns = st + 1
+        act = torch.randint(0, 4, (n,), dtype=torch.int8, device="cuda", generator=g)
+        rew = (torch.randint(0, 6, (n,), device="cuda", generator=g) * 2 - 4).to(torch.float32)
+        dn = torch.randint(0, 2, (n,), dtype=torch.uint8, device="cuda", generator=g)
+        for r in (rc, rr):
+            r.append(st, act, rew, dn, ns)
+        got, want = rc.retreive(), rr.retreive()
+        assert all(torch.equal(got[k], want[k]) for k in want)
+    avg_c, avg_r = rc.retreive(average=True), rr.retreive(average=True)
+    assert all(torch.equal(avg_c[k], avg_r[k]) for k in avg_r)
+    sd = rc.state_dict()
+    rc.purge()
+    assert len(rc) == 0
+    rc.load_state_dict(sd)
+    got, want = rc.retreive(), rr.retreive()
+    assert all(torch.equal(got[k], want[k]) for k in want)
+    acts = torch.randint(0, 4, (4, n), dtype=torch.int8, device="cuda")
+    with pytest.raises(ValueError):                      # the general kernel does not write the compact layout
+        env.step(acts, K=4, out=env.make_outputs(4, ("reward", "done")), ring=rc)
+    with pytest.raises(ValueError):
+        ReplayRing(cap, n, torch.float64, env.device, compact=True)
+    with pytest.raises(ValueError):
+        ReplayRing(cap, n, torch.float32, env.device, continuous=True, compact=True)
+    env.step(pack_actions(acts), K=4, out=env.make_outputs(4, ("events", "obs_next")), ring=rc)      # the packed mode does
+    assert rc.appended == sd["counter"].item() + 4
