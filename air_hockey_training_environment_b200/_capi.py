@@ -39,6 +39,7 @@ class AhRing(C.Structure):
 
 
 AH_RING_ROWS, AH_RING_COMPACT = 0, 1
+AH_RING_COUNTERS = 4
 
 
 AH_ACTV_LINEAR, AH_ACTV_RELU, AH_ACTV_TANH = 0, 1, 2
@@ -69,7 +70,8 @@ class AhStepIO(C.Structure):
                 ("ring", C.POINTER(AhRing)), ("actions_out", C.c_void_p), ("probs_out", C.c_void_p),
                 ("events", C.c_void_p), ("policy", C.POINTER(AhPolicy)), ("actions_real_out", C.c_void_p),
                 ("env_first", C.c_int64), ("env_count", C.c_int64),
-                ("stats_bank", C.c_int32), ("reserved0", C.c_int32)]
+                ("stats_bank", C.c_int32), ("ring_counter_first", C.c_int32), ("ring_counter_count", C.c_int32),
+                ("reserved0", C.c_int32)]
 
 
 class AhError(RuntimeError):

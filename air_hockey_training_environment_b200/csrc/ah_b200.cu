@@ -26,8 +26,8 @@ struct DevBlock {
     unsigned long long stats[2][AH_NSTATS];   // AH_STAT_*, two banks (ah_step_io.stats_bank)
     unsigned long long frame;              // global frame counter (Philox action index)
     unsigned long long xchg_epoch;         // ah_stats_allreduce: exchanges done so far (all ranks call it equally often)
-    unsigned int ticket;                   // last-block-done detection
-    unsigned int pad[43];
+    unsigned int ticket[4];                // last-block-done detection, one per concurrent ordered launch (ring counter index)
+    unsigned int pad[40];
 };
 static_assert(sizeof(DevBlock) == 512, "DevBlock is 512 bytes");
 
@@ -187,7 +187,9 @@ __device__ __forceinline__ void stat_add(BlockStats& bs, int which, int x) {
 template <bool ORDERED = true>
 __device__ __forceinline__ void finish_stats(BlockStats& bs, DevBlock* blk, int bank, int collect_stats, int frames, int reward_sum,
                                              int reward_sq, int dones, int contacts_r, int contacts_o, int overflow, int bad,
-                                             int ambiguous, int K, unsigned long long* ring_appended) {
+                                             int ambiguous, int K, unsigned long long* ring_appended, int ring_counters = 1,
+                                             int ticket = 0, int ring_frames = -1) {
+    if (ring_frames < 0) ring_frames = K;
     const int fs = __reduce_add_sync(0xffffffffu, frames);
     const int rs = __reduce_add_sync(0xffffffffu, reward_sum);
     const int rq = __reduce_add_sync(0xffffffffu, reward_sq);
@@ -241,10 +243,14 @@ __device__ __forceinline__ void finish_stats(BlockStats& bs, DevBlock* blk, int 
         return;
     }
     __threadfence();
-    if (atomicAdd(&blk->ticket, 1u) == gridDim.x - 1) {
-        blk->frame = *(volatile unsigned long long*)&blk->frame + (unsigned long long)K;
-        if (ring_appended) *ring_appended = *(volatile unsigned long long*)ring_appended + (unsigned long long)K;
-        blk->ticket = 0;
+    if (atomicAdd(&blk->ticket[ticket], 1u) == gridDim.x - 1) {
+        // (K == 0: a sub-range launch that does not own env 0 must not touch the frame counter, see above)
+        if (K != 0) blk->frame = *(volatile unsigned long long*)&blk->frame + (unsigned long long)K;
+        if (ring_appended) {                     // this launch's ring counters (ah_step_io.ring_counter_first / _count)
+            const unsigned long long next = *(volatile unsigned long long*)ring_appended + (unsigned long long)ring_frames;
+            for (int c = 0; c < ring_counters; ++c) ring_appended[c] = next;
+        }
+        blk->ticket[ticket] = 0;
         __threadfence();
     }
 }
@@ -547,7 +553,7 @@ step_kernel(const StepArgs<R> a) {
     }
 
     finish_stats(bs, a.blk, a.stats_bank, a.collect_stats, frames, reward_sum, reward_sq, dones, contacts_r, contacts_o, (int)overflow, bad, amb, K,
-                 a.ring_capacity > 0 ? a.ring_appended : nullptr);
+                 a.ring_capacity > 0 ? a.ring_appended : nullptr, AH_RING_COUNTERS);
 }
 
 }  // namespace ah
@@ -1016,6 +1022,9 @@ int launch_step(ah_env* env, const ah_step_io* io, int K, cudaStream_t s) {
             p.ring_action = reinterpret_cast<int8_t*>(io->ring->action);
             p.ring_reward = (R*)io->ring->reward; p.ring_done = io->ring->done; p.ring_capacity = io->ring->capacity;
             p.ring_appended = reinterpret_cast<unsigned long long*>(io->ring->appended);
+            if (io->ring_counter_count > 0) {           // a slice of a step: its own counter(s) and ticket
+                p.ring_appended += io->ring_counter_first; p.ring_counters = io->ring_counter_count; p.ticket = io->ring_counter_first;
+            } else { p.ring_counters = AH_RING_COUNTERS; p.ticket = 0; }
             if (io->ring->format == AH_RING_COMPACT) {
                 p.ring_state_pos = reinterpret_cast<short*>(io->ring->state_pos);
                 p.ring_new_state_pos = reinterpret_cast<short*>(io->ring->new_state_pos);
@@ -1250,7 +1259,8 @@ int ah_step(ah_env* env, const ah_step_io* io, int K, void* stream) {
     if ((io->env_first != 0 || io->env_count != 0) && !io->events) return AH_EINVAL;     // sub-ranges: packed mode only
     if (io->events) {
         if ((reinterpret_cast<uintptr_t>(io->events) & 3u) || (reinterpret_cast<uintptr_t>(io->actions) & 3u)) return AH_EINVAL;
-        if (io->ring && (io->env_first != 0 || (io->env_count != 0 && io->env_count != env->n))) return AH_EINVAL;   // ring append: whole-n launches
+        // ring append from a sub-range: the slice must name its own ring counter(s) (ah_step_io.ring_counter_first / _count)
+        if (io->ring && (io->env_first != 0 || (io->env_count != 0 && io->env_count != env->n)) && io->ring_counter_count <= 0) return AH_EINVAL;
         if (io->reward || io->done || io->score || io->game_over || io->obs_state || io->obs_new_state ||
             io->actions_out || io->probs_out || (io->obs_next && io->obs_next_per_frame) || env->cfg.friction) return AH_EINVAL;
     }
@@ -1266,6 +1276,8 @@ int ah_step(ah_env* env, const ah_step_io* io, int K, void* stream) {
         if (reinterpret_cast<uintptr_t>(r->appended) & 7u) return AH_EINVAL;
         if (!aligned16(r->state) || !aligned16(r->new_state)) return AH_EINVAL;
         if (r->format != AH_RING_ROWS && r->format != AH_RING_COMPACT) return AH_EINVAL;
+        if (io->ring_counter_count < 0 || io->ring_counter_first < 0 || io->ring_counter_first + io->ring_counter_count > AH_RING_COUNTERS) return AH_EINVAL;
+        if (io->ring_counter_count > 0 && !io->events) return AH_EINVAL;                       // sliced appends: packed mode only
         if (r->format == AH_RING_COMPACT) {      // the compact layout is written by the packed FP32 kernel only
             if (env->dtype != AH_F32 || !io->events || !r->state_pos || !r->new_state_pos) return AH_EINVAL;
             if ((reinterpret_cast<uintptr_t>(r->state_pos) | reinterpret_cast<uintptr_t>(r->new_state_pos)) & 7u) return AH_EINVAL;

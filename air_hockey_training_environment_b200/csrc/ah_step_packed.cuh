@@ -50,6 +50,7 @@ struct PackedArgs {
     // IO_RING_COMPACT (AH_RING_COMPACT): ring_state / ring_new_state hold the velocities [capacity][n][4], the locations go
     // to int16 [capacity][n][4], the reward to int8 [capacity][n]
     short* ring_state_pos; short* ring_new_state_pos; int8_t* ring_reward8;
+    int ring_counters, ticket;            // how many of the ring's counters this launch advances; its last-block ticket
     // IO_UNPACKED: the general API's tensors -- time-major int8 actions in, four per-frame outputs out
     const int8_t* actions8;               // i8 [K][n]
     R* reward; uint8_t* done; int8_t* score; uint8_t* game_over;     // [K][n] each
@@ -284,7 +285,7 @@ step_packed_kernel(const PackedArgs<R> a) {
     int r3sum = 0, r3sq = 0, dones = 0, contacts = 0, frames = 0, bad = 0, amb = 0;
     unsigned overflow = 0;
     // RING: every block reads the ring's counter at its start, so it may only advance once every block is done
-    // (finish_stats<true>: fence + ticket); the launch covers all envs (the host refuses sub-ranges with a ring)
+    // (finish_stats<true>: fence + ticket); a slice of a step reads and advances its own counter (ring_counter_first)
     int64_t slot0 = 0;
     if constexpr (RING) slot0 = (int64_t)(*a.ring_appended % (unsigned long long)a.ring_capacity);
     unsigned long long frame0 = 0ull;
@@ -444,7 +445,7 @@ step_packed_kernel(const PackedArgs<R> a) {
     const int reward_sum = 2 * r3sum - 4 * frames;
     const int reward_sq = 4 * r3sq - 16 * r3sum + 16 * frames;
     finish_stats<ORDERED>(bs, a.blk, a.stats_bank, a.collect_stats, frames, reward_sum, reward_sq, dones, contacts & 0xffff, contacts >> 16,
-                          (int)overflow, bad, amb, a.i0 == 0 ? nK : 0, RING ? a.ring_appended : nullptr);
+                          (int)overflow, bad, amb, a.i0 == 0 ? nK : 0, RING ? a.ring_appended : nullptr, a.ring_counters, RING ? a.ticket : 0, nK);
 }
 
 }  // namespace ah

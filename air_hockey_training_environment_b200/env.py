@@ -82,7 +82,7 @@ class ReplayRing:
     (lib/types.py:7), filled from inside the step kernel.  Layout ``[capacity, N, ...]``; like the reference's
     ``appendleft`` + ``retreive`` the newest entry comes first when read back.
 
-    The ring owns its append counter as a device tensor (``counter``, uint64 as int64[1]): the step kernel reads the
+    The ring owns its append counter as a device tensor (``counter``, uint64 as int64[AH_RING_COUNTERS], equal copies): the step kernel reads the
     write slot from it and advances it, so it is correct under CUDA-graph replay, and ``purge()`` is a stream-ordered
     ``counter.zero_()``.  ``len(ring)`` / ``order()`` / ``retreive()`` read it back (one host sync); ``sample`` does not."""
 
@@ -105,7 +105,9 @@ class ReplayRing:
                        else torch.zeros(capacity, n_envs, dtype=torch.int8, device=device))
         self.reward = torch.zeros(capacity, n_envs, dtype=torch.int8 if compact else dtype, device=device)
         self.done = torch.zeros(capacity, n_envs, dtype=torch.uint8, device=device)
-        self.counter = torch.zeros(1, dtype=torch.int64, device=device)
+        # AH_RING_COUNTERS equal copies of the append count: a step issued as concurrent env slices (InterleavedStepper)
+        # gives every slice its own copy to read and advance; counter[0] is the one the readers use
+        self.counter = torch.zeros(_capi.AH_RING_COUNTERS, dtype=torch.int64, device=device)
         self._c = _capi.AhRing(self.state.data_ptr(), self.new_state.data_ptr(), self.action.data_ptr(),
                                self.reward.data_ptr(), self.done.data_ptr(), self.capacity, self.counter.data_ptr())
         self._arrays = ["state", "new_state", "action", "reward", "done", "counter"]
@@ -154,7 +156,7 @@ class ReplayRing:
         """``MemoryBuffer.append(Observation(...))`` (lib/buffer.py:24-32) from device tensors ([N, ...], one tuple per
         env) -- the host-side verb; rollouts append from inside the step kernel instead (``step(ring=...)``).
         Stream-ordered, no host sync: the slot is computed on the device from the ring's counter."""
-        slot = self.counter % self.capacity
+        slot = self.counter[:1] % self.capacity
         for k, v in zip(self.FIELDS, (state, action, reward, done, new_state)):
             if self.compact and k in ("state", "new_state"):
                 v = v.to(self.state.device)
@@ -168,7 +170,7 @@ class ReplayRing:
     @property
     def appended(self) -> int:
         """Observation tuples appended since the last purge (reads the device counter)."""
-        return int(self.counter.item())
+        return int(self.counter[0].item())
 
     def __len__(self) -> int:      # lib/buffer.py:63-66
         return min(self.appended, self.capacity)
@@ -439,7 +441,7 @@ class BatchedAirHockey:
                   out: Optional[StepOutputs] = None, reset_table: Optional[torch.Tensor] = None,
                   ring: Optional[ReplayRing] = None, collect_stats: bool = True,
                   policy_weights: Optional[torch.Tensor] = None, env_range: Optional[Sequence[int]] = None,
-                  stats_bank: int = 0, policy=None) -> "StepPlan":
+                  stats_bank: int = 0, policy=None, ring_counters: Optional[Sequence[int]] = None) -> "StepPlan":
         """Validate the arguments of one step and freeze them into a ``StepPlan`` that ``launch`` can enqueue any number
         of times (the tensors are referenced, not copied: replays read / write the same memory).
 
@@ -455,6 +457,8 @@ class BatchedAirHockey:
                  (continuous head) / ``out.probs`` (head values, [K,N,n_actions]) receive what it did
         env_range: (first, count) -- packed mode only: step just that slice of the envs (tensor shapes stay those of the
                  full N), so one step can be issued as disjoint slices on different streams (host.InterleavedStepper)
+        ring_counters: (first, count) -- with ``ring`` and ``env_range``: which of the ring's counter copies this slice reads
+                 and advances (``ah_step_io.ring_counter_first``; InterleavedStepper assigns them)
         policy_weights: float32 [114] device tensor (``rollout.FusedActor.weights``): closed loop -- every frame the
                  reference-shaped actor is evaluated IN the kernel on the env's current observation and the action
                  is sampled from its softmax (``actions`` must be None); ``out.actions`` / ``out.probs`` receive them
@@ -533,6 +537,8 @@ class BatchedAirHockey:
         io.stats_bank = int(stats_bank)
         if env_range is not None:
             io.env_first, io.env_count = int(env_range[0]), int(env_range[1])
+        if ring_counters is not None:
+            io.ring_counter_first, io.ring_counter_count = int(ring_counters[0]), int(ring_counters[1])
         if ring is not None:
             if ring.n != self.n or ring.state.dtype != self.dtype or ring.state.device != self.device:
                 raise ValueError("ring does not match this environment")
@@ -671,7 +677,13 @@ class InterleavedStepper:
         if plans is None:                                    # validated once per (actions, outputs, bank) combination
             if len(self._plans) > 64:
                 self._plans.clear()
-            plans = [self.env.plan_step(actions, K, out=out, env_range=rng, stats_bank=self.bank, **kw) for rng in self.ranges]
+            P = len(self.ranges)
+            if kw.get("ring") is not None and P > _capi.AH_RING_COUNTERS:
+                raise ValueError(f"a ring append can be issued as at most {_capi.AH_RING_COUNTERS} slices")
+            # with a ring: slice j reads and advances the ring's counter copy j (the last slice: all the remaining copies)
+            rc = [(j, 1 if j < P - 1 else _capi.AH_RING_COUNTERS - j) if kw.get("ring") is not None else None for j in range(P)]
+            plans = [self.env.plan_step(actions, K, out=out, env_range=rng, stats_bank=self.bank, ring_counters=rc[j], **kw)
+                     for j, rng in enumerate(self.ranges)]
             self._plans[key] = plans
         for s, plan in zip(self._raw_streams, plans):
             self.env.launch(plan, s)

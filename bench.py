@@ -578,14 +578,17 @@ def align_start(dev, world):
         dist.all_reduce(_align_buf[dev])
 
 
-def _time_loop(dev, fn, warm, reps, world=1, red=None):
+def _time_loop(dev, fn, warm, reps, world=1, red=None, join=None):
     """Average ms per call of fn(i): CUDA events on the current stream around `reps` calls; at world > 1 bracketed by
     barriers and reduced with MAX over the ranks.  `red` (a StatsReducer) is stepped after every call and its final
-    all-reduce is inside the timed region."""
+    all-reduce is inside the timed region.  `join` (an InterleavedStepper's): makes the current stream wait for the work fn
+    queued on other streams, before the closing event."""
     import torch
     import torch.distributed as dist
 
     def sync():
+        if join is not None:
+            join()
         if red is not None:
             red.flush()
         if world > 1:
@@ -609,6 +612,8 @@ def _time_loop(dev, fn, warm, reps, world=1, red=None):
             red.after_step()
     if red is not None:
         red.finish()
+    if join is not None:
+        join()
     b.record(s)
     sync()
     ms = a.elapsed_time(b)
@@ -648,7 +653,7 @@ def run_ring_append(env, dev, n, K, world=1):
     lib/buffer.py:24-32), sharded over `world` GPUs with the per-rollout NCCL all-reduce of the statistics inside the
     timed region and its payload checked.  HBM-bound (write-heavy): the roofline is per GPU."""
     import torch
-    from air_hockey_training_environment_b200 import ReplayRing
+    from air_hockey_training_environment_b200 import InterleavedStepper, ReplayRing
     from air_hockey_training_environment_b200.env import pack_actions
     out = env.make_outputs(K, ("events", "obs_next"))
     acts = [pack_actions(torch.randint(0, 4, (K, n), dtype=torch.int8, device=dev)) for _ in range(4)]
@@ -658,17 +663,28 @@ def run_ring_append(env, dev, n, K, world=1):
     # the one config 4 is quoted on; the rows layout (the reference's tuple as 70 B of reals) is timed beside it
     for key, compact, tuple_bytes in (("", True, 51), ("rows_layout_", False, 70)):
         ring = ReplayRing(2 * K, n, env.dtype, dev, compact=compact)
-        red = StatsReducer(env, world, dev)
         reps = 96
-        ms = _time_loop(dev, lambda i: env.step(acts[i % 4], K=K, out=out, ring=ring), 16, reps, world, red)
-        chk = red.check(world * n * K * reps)
+        if compact:          # the step as 2 env slices on 2 streams, each with its own copy of the ring's counter
+            st = InterleavedStepper(env, parts=2)
+            red = StatsReducer(env, world, dev, stepper=st)
+            ms = _time_loop(dev, lambda i: st.step(acts[i % 4], K, out, ring=ring), 16, reps, world, red, join=st.join)
+            chk = red.check(world * n * K * reps)
+            red1 = StatsReducer(env, world, dev)
+            ms_one = _time_loop(dev, lambda i: env.step(acts[i % 4], K=K, out=out, ring=ring), 16, reps, world, red1)
+            red1.check(world * n * K * reps)
+        else:
+            red = StatsReducer(env, world, dev)
+            ms = _time_loop(dev, lambda i: env.step(acts[i % 4], K=K, out=out, ring=ring), 16, reps, world, red)
+            chk = red.check(world * n * K * reps)
+        assert ring.counter.tolist() == [ring.appended] * 4
         b = n * (2 * STATE_BYTES + 32 + K * (1 + 1) + K * tuple_bytes)      # state in + out, obs_next, action + event byte, the tuple
         ach = b / (ms * 1e-3) / 1e9
         del ring
         torch.cuda.empty_cache()
         if compact:
             res = {"value": world * n * K / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "n_gpus": world, "envs_total": world * n,
-                   "ring_capacity_frames": 2 * K, "ring_layout": "compact (51 B per tuple)", "stats_allreduce": chk,
+                   "ring_capacity_frames": 2 * K, "ring_layout": "compact (51 B per tuple)", "launches_per_step": 2,
+                   "single_launch_ms_per_step": ms_one, "stats_allreduce": chk,
                    "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                                 "per": "GPU", "traffic": None, "kernel": "ah::step_packed_kernel<float, IO_RING_COMPACT>",
                                 "algorithmic_bytes_per_launch": b, "bytes_per_env_step": b / (n * K)}}

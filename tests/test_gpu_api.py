@@ -406,7 +406,7 @@ def test_guard_bands_survive_every_kernel(dtype):
     ring.state, ring.new_state = carve((3, n, 8), dtype), carve((3, n, 8), dtype)
     ring.action, ring.reward, ring.done = carve((3, n), torch.int8), carve((3, n), dtype), carve((3, n), torch.uint8)
     from air_hockey_training_environment_b200 import _capi
-    ring.counter = carve((1,), torch.int64, ring.counter)
+    ring.counter = carve((4,), torch.int64, ring.counter)            # AH_RING_COUNTERS copies
     ring._c = _capi.AhRing(ring.state.data_ptr(), ring.new_state.data_ptr(), ring.action.data_ptr(), ring.reward.data_ptr(),
                            ring.done.data_ptr(), 3, ring.counter.data_ptr())
     acts = torch.randint(0, 4, (K, n), dtype=torch.int8, device=dev)

@@ -383,4 +383,39 @@ def test_compact_ring_host_verbs_checkpoint_and_argument_errors():
     with pytest.raises(ValueError):
         ReplayRing(cap, n, torch.float32, env.device, continuous=True, compact=True)
     env.step(pack_actions(acts), K=4, out=env.make_outputs(4, ("events", "obs_next")), ring=rc)      # the packed mode does
-    assert rc.appended == sd["counter"].item() + 4
+    assert rc.appended == int(sd["counter"][0]) + 4
+
+
+@pytest.mark.parametrize("compact,parts", [(True, 2), (False, 3), (True, 4)])
+def test_ring_append_from_interleaved_slices_equals_whole_launches(compact, parts):
+    """A step issued as P concurrent env slices (InterleavedStepper) appends to the ring too: every slice reads and
+    advances its own copy of the ring's counter (ah_step_io.ring_counter_first / _count), so no launch waits for or races
+    with another.  Same ring contents, counters, env state and statistics as whole-n launches; whole-n and sliced steps
+    can alternate."""
+    from air_hockey_training_environment_b200 import InterleavedStepper, ReplayRing
+    from air_hockey_training_environment_b200.env import pack_actions
+    n, K, cap = 5000, 8, 20                               # ragged slices
+    a, b = make_env(n, torch.float32, seed=31), make_env(n, torch.float32, seed=31)
+    for env in (a, b):
+        env.step(None, K=600, out=env.make_outputs(600, ()))
+    ra = ReplayRing(cap, n, a.dtype, a.device, compact=compact)
+    rb = ReplayRing(cap, n, b.dtype, b.device, compact=compact)
+    st = InterleavedStepper(a, parts=parts, align=128)
+    oa, ob = a.make_outputs(K, ("events", "obs_next")), b.make_outputs(K, ("events", "obs_next"))
+    g = torch.Generator(device="cuda").manual_seed(8)
+    for launch in range(6):
+        acts = pack_actions(torch.randint(0, 4, (K, n), dtype=torch.int8, device="cuda", generator=g))
+        if launch == 3:                                   # a whole-n launch in between keeps every counter copy in step
+            a.step(acts, K=K, out=oa, ring=ra)
+        else:
+            st.step(acts, K, oa, ring=ra)
+            st.join()
+        b.step(acts, K=K, out=ob, ring=rb)
+        torch.cuda.synchronize()
+        assert ra.counter.tolist() == rb.counter.tolist() == [(launch + 1) * K] * 4
+        assert torch.equal(oa.events, ob.events) and torch.equal(oa.obs_next, ob.obs_next)
+        got, want = ra.retreive(), rb.retreive()
+        assert all(torch.equal(got[k], want[k]) for k in want), launch
+    for x, y in zip((a.puck, a.robot, a.opponent, a.prev_dist, a.meta), (b.puck, b.robot, b.opponent, b.prev_dist, b.meta)):
+        assert torch.equal(x, y)
+    assert a.stats() == b.stats() and a.counters() == b.counters()
