@@ -223,7 +223,7 @@ typedef struct ah_step_io {
      * actions: u8 [ceil(K/4)][n][4], 32-bit aligned.  Requires action_kind == AH_ACT_DISCRETE_PACKED4 and excludes the
      * other per-frame outputs (reward, done, score, game_over, obs_state, obs_new_state, per-frame obs_next,
      * actions_out, probs_out) and the friction flag; obs_next [n][8] and the fused ring append (`ring`, discrete action
-     * layout, whole-n launches only) stay available. */
+     * layout; from sub-range launches too, see ring_counter_first) stay available. */
     uint8_t* events;
     /* AH_ACT_POLICY_MLP: the policy to evaluate (host struct; its weights are a device pointer), and where the continuous
      * actions it chose go (real [K][n][2], nullable; discrete ones go to actions_out, head values to probs_out as

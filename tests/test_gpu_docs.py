@@ -23,5 +23,5 @@ def test_integration_md_quick_start_blocks_run():
         exec(compile(code, "INTEGRATION.md", "exec"), ns)
     torch.cuda.synchronize()
     assert ns["batch"]["obs"].shape == (17, 2048, 8)
-    assert ns["ev"]["reward"].shape == (8, 4096) and ns["ring8"].appended == 8 and ns["ring"].appended == 16
+    assert ns["ev"]["reward"].shape == (8, 4096) and ns["ring8"].appended == 16 and ns["ring"].appended == 16
     assert ns["res"].reward.shape[0] == 8
