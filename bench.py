@@ -686,7 +686,8 @@ def run_ring_append(env, dev, n, K, world=1):
                    "ring_capacity_frames": 2 * K, "ring_layout": "compact (51 B per tuple)", "launches_per_step": 2,
                    "single_launch_ms_per_step": ms_one, "stats_allreduce": chk,
                    "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                                "per": "GPU", "traffic": None, "kernel": "ah::step_packed_kernel<float, IO_RING_COMPACT>",
+                                "per": "GPU", "traffic": profile_fact("ringc_dram_bytes_per_launch"),
+                                "kernel": "ah::step_packed_kernel<float, IO_RING_COMPACT>",
                                 "algorithmic_bytes_per_launch": b, "bytes_per_env_step": b / (n * K)}}
         else:
             res["rows_layout"] = {"value": world * n * K / (ms * 1e-3), "ms_per_step": ms, "stats_frames_ok": chk["ok"],

@@ -1,5 +1,5 @@
 """Run ONE mode of the step kernel repeatedly (for ncu captures of the non-headline variants).
-usage: python tools/run_mode.py k1 | fp64 | policy | ring | unpacked | philox"""
+usage: python tools/run_mode.py k1 | fp64 | policy | ring | ringc | unpacked | philox"""
 import sys
 sys.path.insert(0, "/root/repo")
 import torch
@@ -24,12 +24,13 @@ elif mode == "policy":                 # in-kernel actor rollout (config 5)
     col = RolloutCollector(BatchedAirHockey(65536, seed=1), 128, single_launch=True)
     for i in range(12):
         col.collect()
-elif mode == "ring":                   # config 4's per-GPU work: K = 8 step + fused replay-ring append (HBM-bound, write-heavy)
+elif mode in ("ring", "ringc"):        # config 4's per-GPU work: K = 8 step + fused replay-ring append (HBM-bound, write-heavy);
+                                       # ringc = the compact tuple layout (AH_RING_COMPACT)
     from air_hockey_training_environment_b200 import ReplayRing
     n, K = 1 << 20, 8
     env = BatchedAirHockey(n, seed=1)
     env.step(None, K=2000, out=env.make_outputs(2000, ()))
-    ring = ReplayRing(2 * K, n, env.dtype, env.device)
+    ring = ReplayRing(2 * K, n, env.dtype, env.device, compact=(mode == "ringc"))
     from air_hockey_training_environment_b200.env import pack_actions
     out = env.make_outputs(K, ("events", "obs_next"))
     acts = [pack_actions(torch.randint(0, 4, (K, n), dtype=torch.int8, device="cuda")) for _ in range(4)]
