@@ -182,7 +182,12 @@ __device__ __forceinline__ void policy_head(const PolicyDev& P, const float (&y)
     const int A = P.n_actions;
 #pragma unroll
     for (int q = 0; q < 8; ++q) v[q] = 0.0f;
-    if (P.head == AH_HEAD_SOFTMAX) {
+    if (P.head == AH_HEAD_SOFTMAX && A == 4) {          // the reference's four actions: the loop below without its guards
+        const float m = fmaxf(fmaxf(fmaxf(y[0], y[1]), y[2]), y[3]);          // (same operation order: same bits)
+        const float e0 = __expf(y[0] - m), e1 = __expf(y[1] - m), e2 = __expf(y[2] - m), e3 = __expf(y[3] - m);
+        const float inv = 1.0f / (((e0 + e1) + e2) + e3);
+        v[0] = e0 * inv; v[1] = e1 * inv; v[2] = e2 * inv; v[3] = e3 * inv;
+    } else if (P.head == AH_HEAD_SOFTMAX) {
         float m = y[0];
 #pragma unroll
         for (int q = 1; q < 8; ++q) if (q < A) m = fmaxf(m, y[q]);
@@ -214,6 +219,10 @@ __device__ __forceinline__ int policy_argmax(const float (&v)[8], int A) {      
 
 // np.random.choice(A, p): the first index whose cumulative probability exceeds u
 __device__ __forceinline__ int policy_choice(const float (&p)[8], int A, float u) {
+    if (A == 4) {                                        // four actions: the loop below without its guards (same sums)
+        const float c0 = p[0], c1 = c0 + p[1], c2 = c1 + p[2];
+        return u < c0 ? 0 : (u < c1 ? 1 : (u < c2 ? 2 : 3));
+    }
     float c = 0.0f; int act = A - 1;
     bool found = false;
 #pragma unroll
